@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- descriptor + energy + force atoms/s on the synthetic Cu fcc cell of BASELINE.json.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+    python bench.py --impl reference --steps K --warmup W     (the reference's dense CPU algorithm, bounded sample)
+
+A step is one pass of the hot path over the whole cell: K0 wrap -> K1 cell-list neighbour list -> K2/K3 radial
+and angular symmetry functions with analytic summed gradients -> K5 normalise -> K6 atomic MLP (e, dE/dg) ->
+K4c force contraction.  N=1 workload: configs[3] of BASELINE.json, 63^3 fcc cells = 1,000,188 Cu atoms, rc = 6 A,
+32 G2 + 64 G4 (the literal table is nnmd_b200.workloads.bench_table), fp32, reference (wrap-only) PBC semantics.
+N>1: the same cell sharded spatially in x-slabs with a halo of rc (nnmd_b200.dist), strong scaling.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "descriptor+energy+force atoms/s (Cu fcc, 1M atoms)"
+HIDDEN = [64, 64]
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (nvml, 100 ms period)."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        except Exception:
+            self._nv = None
+        return self
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in {**self.BAD, **self.NOTE}.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_net(nf: int, device, dtype=torch.float32):
+    from nnmd_b200.nn import AtomicNN
+    torch.manual_seed(0)
+    net = AtomicNN(nf, list(HIDDEN))
+    for layer in net.model:  # the reference's initialisation (bpnn.py:149-157)
+        torch.nn.init.xavier_uniform_(layer.weight)
+        torch.nn.init.constant_(layer.bias, 0)
+    return net.to(device=device, dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's algorithm (dense O(N^2)/O(N^3) tensors + autograd, restated in oracle/dense_oracle.py) on the
+    host cores, on a bounded sample of the same lattice and the same 96-row table."""
+    from nnmd_b200.workloads import bench_table, fcc_cell
+    from oracle import dense_oracle as O2
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sfd = bench_table()
+    ncell = args.ref_cells
+    pos, cell, pbc = fcc_cell(ncell, dtype=torch.float32)
+    n = pos.shape[0]
+    net = make_net(len(sfd["features"]), "cpu")
+    Ws = [m.weight.detach() for m in net.model]
+    bs = [m.bias.detach() for m in net.model]
+
+    def step():
+        g, dg = O2.descriptors(pos[None], cell, pbc, sfd, pow_mode="complex64")
+        e, dE, f = O2.energy_force(g, dg, Ws, bs)
+        return float(e.sum()), f
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = n / dt
+    sample = (f"{n}-atom ({ncell}^3 cells) block of the same jittered Cu fcc lattice, same 96-function table, fp32, "
+              f"dense O(N^3) torch restatement of the reference (oracle/dense_oracle.py, complex64 pow); the reference "
+              f"cannot hold the 1M-atom cell (N^3 temporaries)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Cu fcc, rc=6 A, 32 G2 + 64 G4, MLP 96-64-64-1: descriptor+energy+force", "atoms": n},
+            "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------- ours
+def cpu_baseline_port(sfd, seconds_target=20.0):
+    """The O(N) cell-list C restatement (oracle/nl_oracle.c, OpenMP, fp64) on all host cores, bounded sample."""
+    from nnmd_b200.workloads import fcc_cell
+    from oracle import nl_oracle as O3
+    threads = O3.max_threads()
+    ncell = 8
+    pos, cell, pbc = fcc_cell(ncell, dtype=torch.float64)
+    t0 = time.perf_counter()
+    O3.raw_descriptors(pos[None], cell, pbc, sfd)
+    dt = time.perf_counter() - t0
+    if dt < seconds_target / 8 and ncell < 16:  # grow once if the box is fast
+        ncell = 12
+        pos, cell, pbc = fcc_cell(ncell, dtype=torch.float64)
+        t0 = time.perf_counter()
+        O3.raw_descriptors(pos[None], cell, pbc, sfd)
+        dt = time.perf_counter() - t0
+    n = pos.shape[0]
+    return {"value": n / dt, "unit": "atoms/s", "cores": threads, "kind": "port",
+            "sample": f"{n}-atom ({ncell}^3 cells) block of the same lattice and table; descriptors + summed gradients only "
+                      f"(the >99% share), O(N) cell-list C restatement oracle/nl_oracle.c, fp64, OpenMP x{threads}, one pass {dt:.1f} s"}
+
+
+def run_ours(args):
+    from nnmd_b200 import _lib, dist
+    from nnmd_b200.engine import energy_forces
+    from nnmd_b200.nn import BPNN
+    from nnmd_b200.workloads import bench_table, fcc_cell
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as td
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    sfd = bench_table()
+    nf = len(sfd["features"])
+    pos, cell, pbc = fcc_cell(args.cells, dtype=torch.float32)
+    n_atoms = pos.shape[0]
+    cell_d, pbc_d = cell.to(dev), pbc.to(dev)
+    net = make_net(nf, dev)
+    lib = _lib.load()
+
+    # ---- spatial shard of this rank (whole cell for N=1): owned atoms first, halo atoms after
+    shard = dist.SlabShard.from_global(pos, cell, pbc, rc=6.0, rank=rank, world=world)
+    local_pos = shard.exchange_halo(dev)           # (n_local, 3) on the GPU: owned + halo (NCCL send/recv for N>1)
+    n_owned = shard.n_owned
+
+    def step_device():
+        # N>1: the halo exchange is part of every step (positions change every MD step)
+        lp = shard.exchange_halo(dev) if world > 1 else local_pos
+        res = energy_forces(lp[None], cell_d, pbc_d, sfd, net, mode=args.mode, n_centres=n_owned,
+                            mlp_precision=args.mlp, check=False)
+        if world > 1:
+            td.all_reduce(res.energy)  # total energy of the structure
+        return res
+
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as td
+            td.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res = step_device()
+    torch.cuda.synchronize()
+    assert int(res.flag.item()) == 0, "NaN flag raised in the bench workload"
+    mean_nbrs = float(res.nlist.total) / max(n_owned, 1)
+
+    # ---- timed region: K steps, device events, L2 flushed between steps
+    lib.nnmd_profile_enable(1)
+    _lib.profile_read()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = _lib.launch_count()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        for k in range(args.steps):
+            flush_buf.zero_()
+            starts[k].record()
+            res = step_device()
+            ends[k].record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    prof = _lib.profile_read()
+    lib.nnmd_profile_enable(0)
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as td
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = n_atoms / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API (BPNN.predict): pinned host positions in, energy + forces out
+    e2e = None
+    if world == 1:
+        bp = BPNN(dtype=torch.float32)
+        bp.species, bp.atomic_nets, bp.pbc = ["Cu"], [net], None
+        host = pos.clone().pin_memory()
+        def step_e2e():
+            E, F = bp.predict({"Cu": host}, cell, {"Cu": sfd}, pbc=pbc)
+            return E.cpu(), F.cpu()
+        step_e2e()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            E, F = step_e2e()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": n_atoms / dt, "unit": "atoms/s", "h2d_bytes_per_step": int(host.numel() * 4),
+               "d2h_bytes_per_step": int(F.numel() * 4 + E.numel() * 4), "api": "nnmd_b200.nn.BPNN.predict",
+               "ms_per_step": dt * 1e3}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (angular K3): algorithmic bytes per centre atom
+    peak, peak_src = load_peaks()
+    n_ang = sum(1 for k in sfd["features"] if k in (4, 5))
+    ang_ms, ang_n = prof["angular"]
+    ang_ms_per_launch = ang_ms / max(ang_n, 1)
+    bytes_per_atom = 16 + 4 * mean_nbrs + 16 + n_ang * 4 + (n_ang * 12 if args.mode == "materialize" else 0)
+    achieved = bytes_per_atom * n_owned / (ang_ms_per_launch * 1e-3) / 1e9 if ang_ms_per_launch > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "angular_kernel<float,2,DG>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": ang_ms_per_launch, "algorithmic_bytes_per_atom": bytes_per_atom,
+                "note": "K3 is bound by the FP32 FMA pipe and the SFU (ex2), not by HBM; see DESIGN.md and profiles/",
+                "stage_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+    line = {"metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "synthetic Cu fcc 1M-atom cell, rc=6 A, 32 G2 + 64 G4: descriptor+force eval"
+                                   if args.cells == 63 else f"synthetic Cu fcc {args.cells}^3 cells",
+                       "atoms": n_atoms, "cells": args.cells, "mlp": [nf] + HIDDEN + [1], "mode": args.mode,
+                       "mlp_precision": args.mlp, "pbc": "reference wrap-only (SURVEY Q1)", "mean_neighbours": mean_nbrs,
+                       "l2": "256 MiB buffer written between timed steps; per-step working set (neighbour list + dG) is >1 GB",
+                       "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, halo rc, NCCL send/recv"},
+            "clocks": clocks.summary(), "gpu_launches": launches, "roofline": roofline}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_port(sfd)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=63, help="fcc conventional cells per edge (63 -> 1,000,188 atoms)")
+    ap.add_argument("--mode", default="materialize", choices=["materialize", "fused"])
+    ap.add_argument("--mlp", default="exact", choices=["exact", "tf32"])
+    ap.add_argument("--ref-cells", type=int, default=3, help="reference arm sample: cells per edge (3 -> 108 atoms)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as td
+        if td.is_initialized():
+            td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

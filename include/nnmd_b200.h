@@ -1,0 +1,155 @@
+/*
+ * nnmd_b200.h -- C ABI of the B200-native descriptor -> energy -> force path.
+ *
+ * The reference (ded-otshelnik/nnmd) has no FFI of its own: its boundary is the set of
+ * Python signatures in nnmd/features/__init__.py:13-23 and nnmd/nn/__init__.py:1-6.  The
+ * entry points below are what a binding for that path attaches to; each one names the
+ * reference code it replaces (paths relative to the reference checkout).  The Python host
+ * (nnmd_b200/) reaches them through ctypes with raw device pointers (torch owns all the
+ * device memory and the stream); INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a CUDA device pointer, "host" a host pointer
+ *   - `dtype` is NNMD_F32 or NNMD_F64: the working precision of positions, descriptors,
+ *     gradients, energies and forces (the reference's `dtype` of the cartesians tensor)
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call
+ *     only enqueues work, nothing here synchronises except where stated
+ *   - return value: NNMD_OK or an NNMD_ERR_* code; nnmd_last_error() gives the text
+ *   - there is no CPU implementation behind any of these: without a CUDA device the
+ *     calls fail with NNMD_ERR_CUDA
+ */
+#ifndef NNMD_B200_H
+#define NNMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNMD_F32 0
+#define NNMD_F64 1
+
+#define NNMD_OK 0
+#define NNMD_ERR_INVALID 1  /* bad argument (text in nnmd_last_error) */
+#define NNMD_ERR_CUDA 2     /* CUDA runtime error */
+#define NNMD_ERR_CAPACITY 3 /* a neighbour row does not fit the shared-memory budget */
+
+/* bits of the device-side status word `flag` (uint32, dev) */
+#define NNMD_FLAG_NAN_G 1u  /* 0/0 or non-finite value in the normalised descriptors  (calculate_sf.py:106-107) */
+#define NNMD_FLAG_NAN_DG 2u /* non-finite value in the descriptor gradients           (calculate_sf.py:108-109) */
+
+/* symmetry-function kinds = nnmd/features/symm_funcs.py:6-15 (SymmetryFunction enum values) */
+#define NNMD_G1 1
+#define NNMD_G2 2
+#define NNMD_G4 4
+#define NNMD_G5 5
+
+int nnmd_abi_version(void);
+const char *nnmd_last_error(void);
+/* number of SMs of the current device (grid sizing), or -1 */
+int nnmd_device_sm_count(void);
+
+/* Instrumentation for bench.py: number of kernel launches issued by this library so far, and optional
+ * CUDA-event timing per kernel class on the launching stream (classes: 0 nlist, 1 radial, 2 angular,
+ * 3 normalize, 4 contract, 5 mlp, 6 wrap).  nnmd_profile_read synchronises the device and resets. */
+#define NNMD_PROF_NCLASS 7
+long long nnmd_launch_count(void);
+int nnmd_profile_enable(int on);
+int nnmd_profile_read(double *ms, long long *count);
+
+/* ---------------------------------------------------------------------------------------
+ * K0  wrap-only periodic boundaries            replaces symm_funcs.py:53-82 map_positions_pbc
+ *   pos    dev  (n_total,3) working dtype
+ *   cell, inv_cell, pbc  host double[9], double[9], double[3]; values are ROUNDED to the working
+ *          dtype inside (the host computes inv_cell in the working dtype like torch.linalg.inv does)
+ *   has_cell  0 when det(cell)==0: positions pass through unchanged (symm_funcs.py:71-72)
+ *   posw   dev  (n_total,4) working dtype, xyz + zero pad: the layout every later kernel reads
+ * ------------------------------------------------------------------------------------- */
+int nnmd_wrap_positions(int dtype, const void *pos, int64_t n_total, const double *cell, const double *inv_cell,
+                        const double *pbc, int has_cell, void *posw, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  cell-list neighbour list     replaces symm_funcs.py:85-104 calculate_distances +
+ *                                  symm_funcs.py:18-31 _pairwise_filter (dense (B,N,N) mask)
+ * The list is CSR over centre atoms: row c = frame*n_centres + i holds the GLOBAL indices
+ * frame*n_atoms + j of every j with 0 < |p_j - p_i| < rc, ascending.  Centres are the first
+ * n_centres atoms of each frame (n_centres < n_atoms only for spatial shards that carry halo atoms).
+ *
+ *   step 1  nnmd_nlist_workspace_bytes -> size of `ws` (dev scratch, owned by the caller)
+ *   step 2  nnmd_nlist_count : bins atoms, counts neighbours, writes offsets (int64, n_rows+1)
+ *           and stats = {total pairs, longest row} (int64[2], dev)
+ *   step 3  caller reads stats (the one host sync of the build), allocates idx (int32, total)
+ *   step 4  nnmd_nlist_fill  : writes the sorted rows
+ * ------------------------------------------------------------------------------------- */
+int64_t nnmd_nlist_workspace_bytes(int64_t n_frames, int64_t n_atoms);
+int nnmd_nlist_count(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
+                     void *ws, int64_t *offsets, int64_t *stats, void *stream);
+int nnmd_nlist_fill(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
+                    const void *ws, const int64_t *offsets, int64_t max_row, int32_t *idx, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Symmetry-function plan: the parameter table of one species
+ *   replaces the per-call `symm_funcs_data` walk of calculate_sf.py:64-81
+ *   kinds  host int32[nf]  (NNMD_G1|G2|G4|G5; anything else -> NNMD_ERR_INVALID,
+ *                           "Unknown symmetry function number: k" like calculate_sf.py:81)
+ *   params host double[nf*4], the reference's POSITIONAL binding:
+ *          G1 (rc) ; G2 (rc, eta, rs) ; G4/G5 (rc, eta, zeta, lambda)
+ * ------------------------------------------------------------------------------------- */
+typedef struct nnmd_sf_plan nnmd_sf_plan;
+int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, const double *params, nnmd_sf_plan **plan);
+void nnmd_sf_plan_destroy(nnmd_sf_plan *plan);
+double nnmd_sf_plan_rc_max(const nnmd_sf_plan *plan);
+
+/* ---------------------------------------------------------------------------------------
+ * K2 + K3 + K4a  descriptors and their summed gradients
+ *   replaces symm_funcs.py:107-277 (f_cutoff, g1/g2/g4/g5_function) and the per-function
+ *   torch.autograd.grad of calculate_sf.py:85-90
+ *   G   dev (n_rows, nf)    UN-normalised symmetry functions, column order = plan order
+ *   dG  dev (n_rows, nf, 3) d(sum_i G_i,f)/d r_a  (SURVEY Q6), or NULL to skip
+ *   flag dev uint32, OR-ed with NNMD_FLAG_NAN_DG
+ * ------------------------------------------------------------------------------------- */
+int nnmd_sf_eval(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
+                 const int64_t *offsets, const int32_t *idx, int64_t max_row, void *G, void *dG, uint32_t *flag,
+                 void *stream);
+
+/* K5  L2 normalisation over the feature axis + NaN guard   replaces calculate_sf.py:100-109
+ *   ghat may alias G */
+int nnmd_sf_normalize(int dtype, const void *G, int64_t n_rows, int nf, void *ghat, uint32_t *flag, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4b  fused force: F[a,:] (+)= -sum_f w[a,f] * d(sum_i G_i,f)/d r_a without materialising dG
+ *   replaces the chain autograd.grad (calculate_sf.py:85-90) -> einsum (bpnn.py:353, :538-544)
+ *   w      dev (n_rows, nf)  dE/dg_hat of the centre atom
+ *   force  dev (n_rows, 3)   overwritten
+ *   virial dev (n_frames, 9) or NULL:  -1/2 sum_a sum_t u_at (x) f_at, pairwise-decomposed
+ *          (extension, the reference has no virial: SURVEY Q8)
+ * ------------------------------------------------------------------------------------- */
+int nnmd_sf_force(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
+                  const int64_t *offsets, const int32_t *idx, int64_t max_row, const void *w, void *force,
+                  void *virial, void *stream);
+
+/* K4c  force contraction against a materialised dG      replaces bpnn.py:353  einsum("ijk,ijkl->ijl")
+ *   force[a,:] = -sum_f dE[a,f] * dG[a,f,:] */
+int nnmd_force_contract(int dtype, const void *dE, const void *dG, int64_t n_rows, int nf, void *force, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K6  atomic MLP: energy per atom and dE/dx      replaces atomic_nn.py:43-48 AtomicNN.forward and
+ *                                                the autograd.grad of bpnn.py:347-349 / :537-538
+ *   n_layers linear layers; sizes host int32[n_layers+1] = (in, h1, ..., 1)
+ *   weights / biases: host arrays of n_layers DEVICE pointers; W_l is (sizes[l+1], sizes[l]) row-major
+ *   (torch.nn.Linear layout, state_dict keys model.{l}.weight|bias); sigmoid after every layer but the last
+ *   x dev (n_rows, sizes[0]); e dev (n_rows); dEdx dev (n_rows, sizes[0]) or NULL
+ *   precision: NNMD_MLP_EXACT = fp32/fp64 FMA; NNMD_MLP_TF32 = tensor cores (dtype F32 only)
+ * ------------------------------------------------------------------------------------- */
+#define NNMD_MLP_EXACT 0
+#define NNMD_MLP_TF32 1
+int nnmd_mlp_energy_grad(int dtype, int precision, int n_layers, const int32_t *sizes, const void *const *weights,
+                         const void *const *biases, const void *x, int64_t n_rows, void *e, void *dEdx,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNMD_B200_H */

@@ -1,0 +1,806 @@
+// sf.cu -- K2 radial pair kernel, K3 angular triplet kernel, K4a summed-gradient output,
+//          K4b fused force, K4c force contraction, K5 normalisation (sm_100a).
+//
+// What is computed (reference: nnmd/features/symm_funcs.py:107-277, calculate_sf.py:85-104; math as
+// implemented = SURVEY.md Appendix A):
+//   fc(d)  = 1/2 (cos(pi d / rc) + 1),  d < rc
+//   G1_a   = sum_j fc(d_aj)                       G2_a = sum_j exp(-eta (d_aj - rs)^2) fc(d_aj)
+//   G4_a   = 2^(1-zeta) sum_{j != k} P(c_ajk) exp(-eta (x^2 + y^2 + z^2)) fc(x) fc(y) fc(z)
+//   G5_a   = 2^(1-zeta) sum_{j != k} P(c_ajk) exp(-eta (x^2 + y^2))       fc(x) fc(y) fc(z)
+//            x = d_aj, y = d_ak, z = d_jk, ALL three inside (0, rc)  
+//            P(c) = (1 + lambda |c|)^zeta if |c| > 1e-3 else 0        
+//   dG[a,f,:] = d (sum_i G_i,f) / d r_a                               
+//
+// Because every contributing triplet is a closed triangle, both G_a and dG[a] are gathered from
+// atom a's own neighbour row: no atomics, fixed summation order.
+//
+// K3 work decomposition (one warp per centre atom, one launch per (kind, rc, eta) group):
+//   phase 0  lanes over the neighbour row: u, d, 1/d, fc, fc', psi = exp(-eta d^2) fc, psi' -> shared memory
+//   phase 1  lanes over closed triangles (j<k, z<rc): everything that does not depend on the function
+//            (three cosines, their derivatives, the radial products, log2 of the two bases 1+-|c|)
+//            is reduced to a 38-real record in shared memory
+//   phase 2  lanes over FUNCTIONS (G lanes x FPL functions per lane, 32/G triangles in flight):
+//            per centre one ex2 and five FMA-pipe ops, six more per triangle for the direction vectors
+// The inner loop is bound by the FP32 FMA pipe and the SFU (ex2), not by HBM: see DESIGN.md.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <new>
+#include <tuple>
+
+#include "sf_plan.h"
+
+namespace nnmd {
+
+// =============================================================================================
+// plan
+// =============================================================================================
+template <typename T>
+static int upload(const std::vector<double> &h, void **dptr) {
+    std::vector<T> tmp(h.size());
+    for (size_t i = 0; i < h.size(); ++i) tmp[i] = T(h[i]);
+    NNMD_CUDA_CHECK(cudaMalloc(dptr, std::max<size_t>(tmp.size(), 1) * sizeof(T)));
+    if (!tmp.empty()) NNMD_CUDA_CHECK(cudaMemcpy(*dptr, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return NNMD_OK;
+}
+static int upload_int(const std::vector<int> &h, int **dptr) {
+    NNMD_CUDA_CHECK(cudaMalloc((void **)dptr, std::max<size_t>(h.size(), 1) * sizeof(int)));
+    if (!h.empty()) NNMD_CUDA_CHECK(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return NNMD_OK;
+}
+static int upload_real(int dtype, const std::vector<double> &h, void **dptr) {
+    return dtype == NNMD_F32 ? upload<float>(h, dptr) : upload<double>(h, dptr);
+}
+
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static int build_group(int dtype, int kind, double rc, double eta, const std::vector<int> &members,
+                       const double *params, std::vector<AngGroup> &out) {
+    // members: function indices sharing (kind, rc, eta).  Split so that one launch holds <= 32 lanes x 4.
+    bool pm1 = true;
+    for (int f : members) {
+        const double lam = params[4 * f + 3];
+        if (!(lam == 1.0 || lam == -1.0)) pm1 = false;
+    }
+    // order: lambda class (+ first), then zeta -- lanes of one class share the record block they read
+    std::vector<int> ord(members);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+        const double la = params[4 * a + 3], lb = params[4 * b + 3];
+        if (pm1 && la != lb) return la > lb;
+        return params[4 * a + 2] < params[4 * b + 2];
+    });
+    size_t pos = 0;
+    while (pos < ord.size()) {
+        const size_t chunk = std::min<size_t>(ord.size() - pos, 128);
+        std::vector<int> part(ord.begin() + pos, ord.begin() + pos + chunk);
+        pos += chunk;
+        // classes inside this part
+        std::vector<int> plus, minus;
+        for (int f : part) ((pm1 && params[4 * f + 3] < 0) ? minus : plus).push_back(f);
+        int fpl = 1;
+        auto slots_for = [&](int l) { return int((plus.size() + l - 1) / l + (minus.size() + l - 1) / l); };
+        while (fpl < ANG_MAX_FPL && slots_for(fpl) > 32) fpl <<= 1;
+        if (slots_for(fpl) > 32) return set_err(NNMD_ERR_INVALID, "internal: angular group does not fit a warp");
+        AngGroup g;
+        g.kind = kind; g.rc = rc; g.eta = eta; g.pm1 = pm1 ? 1 : 0; g.fpl = fpl;
+        g.lanes = next_pow2(std::max(slots_for(fpl), 1));
+        g.n_slots = g.lanes * fpl;
+        std::vector<double> zeta(g.n_slots, 1.0), lam(g.n_slots, 1.0), coef(g.n_slots, 0.0);
+        std::vector<int> col(g.n_slots, -1);
+        int slot = 0;
+        auto place = [&](const std::vector<int> &cls, double lam_pad) {
+            const int lanes_cls = int((cls.size() + fpl - 1) / fpl);
+            for (int l = 0; l < lanes_cls; ++l)
+                for (int i = 0; i < fpl; ++i, ++slot) {
+                    const size_t k = size_t(l) * fpl + i;
+                    lam[slot] = lam_pad;
+                    if (k < cls.size()) {
+                        const int f = cls[k];
+                        zeta[slot] = params[4 * f + 2];
+                        lam[slot] = params[4 * f + 3];
+                        // 2^(1-zeta), times 2 because the reference sums ORDERED (j,k) (symm_funcs.py:216-219)
+                        coef[slot] = 2.0 * std::pow(2.0, 1.0 - params[4 * f + 2]);
+                        col[slot] = f;
+                    }
+                }
+        };
+        place(plus, 1.0);
+        place(minus, -1.0);
+        int r;
+        if ((r = upload_real(dtype, zeta, &g.d_zeta))) return r;
+        if ((r = upload_real(dtype, lam, &g.d_lam))) return r;
+        if ((r = upload_real(dtype, coef, &g.d_coef))) return r;
+        if ((r = upload_int(col, &g.d_col))) return r;
+        g.cols = col;
+        out.push_back(g);
+    }
+    return NNMD_OK;
+}
+
+// =============================================================================================
+// shared-memory staging of one neighbour row (phase 0, used by K2 and K3)
+// =============================================================================================
+template <typename T>
+struct NbView {
+    T *ux, *uy, *uz, *d, *invd, *fc, *dfc, *psi, *dpsi;
+    __device__ __forceinline__ void bind(T *base, int cap) {
+        ux = base; uy = ux + cap; uz = uy + cap; d = uz + cap; invd = d + cap;
+        fc = invd + cap; dfc = fc + cap; psi = dfc + cap; dpsi = psi + cap;
+    }
+};
+
+// Gathers the neighbours of centre `gi` that lie inside rc into shared memory; returns their number.
+// ANG: also stage fc, fc', psi, psi' for the group's (rc, eta).
+template <typename T, bool ANG>
+__device__ __forceinline__ int stage_row(const T *__restrict__ posw, const int32_t *__restrict__ idx, int64_t o0,
+                                         int64_t o1, T xa, T ya, T za, T rc, T inv_rc, T eta, NbView<T> nb, int cap) {
+    const int lane = lane_id();
+    int nn = 0;
+    for (int64_t base = o0; base < o1; base += 32) {
+        const int64_t e = base + lane;
+        bool keep = false;
+        T ux = 0, uy = 0, uz = 0, d = 0;
+        if (e < o1) {
+            const int j = __ldg(idx + e);
+            T xj, yj, zj;
+            load_pos<T>(posw, j, xj, yj, zj);
+            ux = xj - xa; uy = yj - ya; uz = zj - za;
+            d = M<T>::sqrt_(ux * ux + uy * uy + uz * uz);
+            keep = (d < rc) && (d > T(0));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int p = nn + __popc(m & ((1u << lane) - 1u));
+            if (p < cap) {
+                nb.ux[p] = ux; nb.uy[p] = uy; nb.uz[p] = uz; nb.d[p] = d;
+                nb.invd[p] = M<T>::rcp(d);
+                if (ANG) {
+                    T s, c;
+                    M<T>::sincospi_(d * inv_rc, &s, &c);
+                    const T fc = T(0.5) * (c + T(1));
+                    const T dfc = T(-0.5) * M<T>::pi() * inv_rc * s;
+                    const T ex = M<T>::exp_(-eta * d * d);
+                    nb.fc[p] = fc; nb.dfc[p] = dfc;
+                    nb.psi[p] = ex * fc;
+                    nb.dpsi[p] = ex * (dfc - T(2) * eta * d * fc);
+                }
+            }
+        }
+        nn += __popc(m);
+    }
+    __syncwarp();
+    return min(nn, cap);
+}
+
+// =============================================================================================
+// K2 radial
+// =============================================================================================
+enum { MODE_G = 0, MODE_DG = 1, MODE_FORCE = 2 };
+
+template <typename T>
+struct RadArgs {
+    const T *posw;
+    int64_t n_rows, n_atoms, n_centres;
+    const int64_t *offsets;
+    const int32_t *idx;
+    int cap;
+    int n;  // radial functions
+    T rc_max;
+    const T *rc, *eta, *rs;
+    const int *col;
+    int nf;  // row stride of the outputs
+    T *G, *dG;
+    const T *w;
+    T *force;
+    uint32_t *flag;
+};
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) radial_kernel(RadArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    T *base = reinterpret_cast<T *>(smem_raw) + size_t(warp) * 5 * a.cap;
+    NbView<T> nb;
+    nb.bind(base, a.cap);
+    bool bad = false;
+    for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
+        const int64_t frame = row / a.n_centres;
+        const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
+        T xa, ya, za;
+        load_pos<T>(a.posw, gi, xa, ya, za);
+        const int nn = stage_row<T, false>(a.posw, a.idx, a.offsets[row], a.offsets[row + 1], xa, ya, za, a.rc_max,
+                                           T(0), T(0), nb, a.cap);
+        T fx = 0, fy = 0, fz = 0;  // MODE_FORCE partial sums
+        for (int f0 = 0; f0 < a.n; f0 += 32) {
+            const int f = f0 + lane;
+            const bool act = f < a.n;
+            const T rc = act ? a.rc[f] : T(1), eta = act ? a.eta[f] : T(0), rs = act ? a.rs[f] : T(0);
+            const T inv_rc = M<T>::rcp(rc);
+            T val = 0, gx = 0, gy = 0, gz = 0;
+            if (act) {
+                for (int t = 0; t < nn; ++t) {
+                    const T d = nb.d[t];
+                    if (d < rc) {
+                        T s, c;
+                        M<T>::sincospi_(d * inv_rc, &s, &c);
+                        const T fc = T(0.5) * (c + T(1));
+                        const T dfc = T(-0.5) * M<T>::pi() * inv_rc * s;
+                        const T dr = d - rs;
+                        const T ex = M<T>::exp_(-eta * dr * dr);  // G1: eta = 0 -> 1
+                        val += ex * fc;
+                        if (MODE != MODE_G) {
+                            const T dphi = ex * (dfc - T(2) * eta * dr * fc);
+                            // own-atom gradient plus the identical term inside every neighbour's G_j
+                            const T sc = T(-2) * dphi * nb.invd[t];
+                            gx = M<T>::fma_(sc, nb.ux[t], gx);
+                            gy = M<T>::fma_(sc, nb.uy[t], gy);
+                            gz = M<T>::fma_(sc, nb.uz[t], gz);
+                        }
+                    }
+                }
+                const int col = a.col[f];
+                const int64_t o = row * a.nf + col;
+                if (MODE == MODE_G || MODE == MODE_DG) a.G[o] = val;
+                if (MODE == MODE_DG) {
+                    a.dG[3 * o] = gx; a.dG[3 * o + 1] = gy; a.dG[3 * o + 2] = gz;
+                    bad |= !(isfinite(gx) && isfinite(gy) && isfinite(gz));
+                }
+                if (MODE == MODE_FORCE) {
+                    const T wv = a.w[o];
+                    fx -= wv * gx; fy -= wv * gy; fz -= wv * gz;
+                }
+            }
+        }
+        if (MODE == MODE_FORCE) {
+            fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+            if (lane == 0) { a.force[3 * row] += fx; a.force[3 * row + 1] += fy; a.force[3 * row + 2] += fz; }
+        }
+        __syncwarp();
+    }
+    if (MODE == MODE_DG && bad) atomicOr(a.flag, NNMD_FLAG_NAN_DG);
+}
+
+// =============================================================================================
+// K3 angular
+// =============================================================================================
+template <typename T>
+struct AngArgs {
+    const T *posw;
+    int64_t n_rows, n_atoms, n_centres;
+    const int64_t *offsets;
+    const int32_t *idx;
+    int cap;
+    int kind, pm1, lanes, log_lanes;
+    T rc, eta;
+    const T *zeta, *lam, *coef;
+    const int *col;
+    int nf;
+    T *G, *dG;
+    const T *w;
+    T *force;
+    uint32_t *flag;
+};
+
+template <typename T>
+__device__ __forceinline__ void st4(T *p, T a, T b, T c, T d);
+template <> __device__ __forceinline__ void st4<float>(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void st4<double>(double *p, double a, double b, double c, double d) {
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(c, d);
+}
+template <typename T> struct Q4 { T a, b, c, d; };
+template <typename T> __device__ __forceinline__ Q4<T> ld4(const T *p);
+template <> __device__ __forceinline__ Q4<float> ld4<float>(const float *p) {
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    return {v.x, v.y, v.z, v.w};
+}
+template <> __device__ __forceinline__ Q4<double> ld4<double>(const double *p) {
+    const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
+    return {u.x, u.y, v.x, v.y};
+}
+
+// cosine at a centre with adjacent sides (p, q), opposite side r (squares given), thresholds of symm_funcs.py:193-197
+template <typename T>
+__device__ __forceinline__ T cos_law(T p2, T q2, T r2, T p, T q, T ip, T iq, bool &live) {
+    live = (T(2) * p * q) >= T(1e-3);
+    return live ? (p2 + q2 - r2) * (T(0.5) * ip * iq) : T(0);
+}
+
+// phase 1: one lane reduces one closed triangle (tj < tk) to its record
+template <typename T, int MODE>
+__device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk, int kind, int pm1, T rc, T inv_rc, T eta,
+                                            T *__restrict__ rec) {
+    const T x = nb.d[tj], y = nb.d[tk], ix = nb.invd[tj], iy = nb.invd[tk];
+    const T ujx = nb.ux[tj], ujy = nb.uy[tj], ujz = nb.uz[tj];
+    const T ukx = nb.ux[tk], uky = nb.uy[tk], ukz = nb.uz[tk];
+    const T wx = ujx - ukx, wy = ujy - uky, wz = ujz - ukz;
+    const T z2 = wx * wx + wy * wy + wz * wz;
+    const T z = M<T>::sqrt_(z2), iz = M<T>::rcp(z);
+    const T x2 = x * x, y2 = y * y;
+    const T fz = T(0.5) * (M<T>::cospi_(z * inv_rc) + T(1));
+    const T psz = M<T>::exp_(-eta * z2) * fz;
+    const T psx = nb.psi[tj], psy = nb.psi[tk], dpsx = nb.dpsi[tj], dpsy = nb.dpsi[tk];
+
+    T c[3], dcx[3], dcy[3], E[3], Ex[3], Ey[3];
+    bool live[3];
+    c[0] = cos_law<T>(x2, y2, z2, x, y, ix, iy, live[0]);  // centre a : sides x, y   opposite z
+    c[1] = cos_law<T>(x2, z2, y2, x, z, ix, iz, live[1]);  // centre j : sides x, z   opposite y
+    c[2] = cos_law<T>(y2, z2, x2, y, z, iy, iz, live[2]);  // centre k : sides y, z   opposite x
+    dcx[0] = live[0] ? iy - c[0] * ix : T(0);  dcy[0] = live[0] ? ix - c[0] * iy : T(0);
+    dcx[1] = live[1] ? iz - c[1] * ix : T(0);  dcy[1] = live[1] ? -y * ix * iz : T(0);
+    dcx[2] = live[2] ? -x * iy * iz : T(0);    dcy[2] = live[2] ? iz - c[2] * iy : T(0);
+    if (kind == NNMD_G4) {
+        const T e = psx * psy * psz;
+        E[0] = E[1] = E[2] = e;
+        Ex[0] = Ex[1] = Ex[2] = dpsx * psy * psz;
+        Ey[0] = Ey[1] = Ey[2] = psx * dpsy * psz;
+    } else {  // G5 keeps fc of the opposite side
+        const T fcx = nb.fc[tj], fcy = nb.fc[tk], dfcx = nb.dfc[tj], dfcy = nb.dfc[tk];
+        E[0] = psx * psy * fz;   Ex[0] = dpsx * psy * fz;   Ey[0] = psx * dpsy * fz;
+        E[1] = psx * psz * fcy;  Ex[1] = dpsx * psz * fcy;  Ey[1] = psx * psz * dfcy;
+        E[2] = psy * psz * fcx;  Ex[2] = psy * psz * dfcx;  Ey[2] = dpsy * psz * fcx;
+    }
+    // class blocks: [L0 Ax0 Bx0 Ay0 | By0 L1 Ax1 Bx1 | Ay1 By1 L2 Ax2 | Bx2 Ay2 By2 V0]
+    T blk[2][REC_CLASS];
+#pragma unroll
+    for (int X = 0; X < 3; ++X) {
+        const T ac = M<T>::abs_(c[X]);
+        const bool on = ac > T(1e-3);  // symm_funcs.py:210-211: the angular factor is 0 for |cos| <= 1e-3
+        const T sg = c[X] > T(0) ? T(1) : T(-1);
+        const T ax = on ? sg * E[X] * dcx[X] : T(0), ay = on ? sg * E[X] * dcy[X] : T(0);
+        const T ex = on ? Ex[X] : T(0), ey = on ? Ey[X] : T(0);
+        if (pm1) {
+            const T bp = T(1) + ac, bm = M<T>::max_(T(1) - ac, T(0));
+            const T lp = on ? M<T>::log2_(bp) : T(0);
+            const T lm = on ? M<T>::max_(M<T>::log2_(bm), -M<T>::big()) : T(0);
+            blk[0][5 * X + 0] = lp;  blk[0][5 * X + 1] = ax;   blk[0][5 * X + 2] = bp * ex;
+            blk[0][5 * X + 3] = ay;  blk[0][5 * X + 4] = bp * ey;
+            blk[1][5 * X + 0] = lm;  blk[1][5 * X + 1] = -ax;  blk[1][5 * X + 2] = bm * ex;
+            blk[1][5 * X + 3] = -ay; blk[1][5 * X + 4] = bm * ey;
+            if (X == 0) { blk[0][15] = on ? bp * E[0] : T(0); blk[1][15] = on ? bm * E[0] : T(0); }
+        } else {  // general lambda: the lane finishes base, log and the lambda factors itself
+            blk[0][5 * X + 0] = on ? ac : T(0);  blk[0][5 * X + 1] = ax;  blk[0][5 * X + 2] = ex;
+            blk[0][5 * X + 3] = ay;              blk[0][5 * X + 4] = ey;
+            if (X == 0) blk[0][15] = on ? E[0] : T(0);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st4<T>(rec + 4 * q, blk[0][4 * q], blk[0][4 * q + 1], blk[0][4 * q + 2], blk[0][4 * q + 3]);
+    if (pm1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            st4<T>(rec + REC_CLASS + 4 * q, blk[1][4 * q], blk[1][4 * q + 1], blk[1][4 * q + 2], blk[1][4 * q + 3]);
+    }
+    if (MODE != MODE_G) {
+        st4<T>(rec + REC_TAIL, ujx * ix, ujy * ix, ujz * ix, ukx * iy);
+        st4<T>(rec + REC_TAIL + 4, uky * iy, ukz * iy, T(0), T(0));
+    }
+}
+
+template <typename T, int FPL, int MODE>
+__global__ void __launch_bounds__(128) angular_kernel(AngArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    // per-warp shared memory: records | neighbour fields | pair queue
+    const size_t per_warp = size_t(ANG_BATCH) * REC_STRIDE * sizeof(T) + size_t(NB_FIELDS) * a.cap * sizeof(T) + 64 * sizeof(int);
+    unsigned char *wbase = smem_raw + per_warp * warp;
+    T *recs = reinterpret_cast<T *>(wbase);
+    NbView<T> nb;
+    nb.bind(recs + ANG_BATCH * REC_STRIDE, a.cap);
+    int *queue = reinterpret_cast<int *>(recs + ANG_BATCH * REC_STRIDE + size_t(NB_FIELDS) * a.cap);
+
+    const int G = a.lanes, grp = lane >> a.log_lanes, fl = lane & (G - 1), ngrp = 32 >> a.log_lanes;
+    const T inv_rc = M<T>::rcp(a.rc);
+    // this lane's functions
+    T zeta[FPL], zm1[FPL], lam[FPL], coef[FPL];
+    int col[FPL];
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) {
+        const int s = fl * FPL + i;
+        zeta[i] = a.zeta[s]; zm1[i] = zeta[i] - T(1); lam[i] = a.lam[s]; coef[i] = a.coef[s]; col[i] = a.col[s];
+    }
+    const int cls_off = (a.pm1 && lam[0] < T(0)) ? REC_CLASS : 0;
+    bool bad = false;
+
+    for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
+        const int64_t frame = row / a.n_centres;
+        const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
+        T xa, ya, za;
+        load_pos<T>(a.posw, gi, xa, ya, za);
+        const int nn = stage_row<T, true>(a.posw, a.idx, a.offsets[row], a.offsets[row + 1], xa, ya, za, a.rc, inv_rc,
+                                          a.eta, nb, a.cap);
+        T val[FPL], gx[FPL], gy[FPL], gz[FPL];
+#pragma unroll
+        for (int i = 0; i < FPL; ++i) val[i] = gx[i] = gy[i] = gz[i] = T(0);
+
+        int head = 0, qn = 0;  // ring buffer of closed (tj,tk) pairs, warp-uniform
+        // process `cnt` queued triangles: phase 1 (records) then phase 2 (functions)
+        auto flush = [&](int cnt) {
+            if (lane < cnt) {
+                const int pk = queue[(head + lane) & 63];
+                make_record<T, MODE>(nb, pk & 0xffff, pk >> 16, a.kind, a.pm1, a.rc, inv_rc, a.eta, recs + lane * REC_STRIDE);
+            }
+            __syncwarp();
+            for (int t = grp; t < cnt; t += ngrp) {
+                const T *r = recs + t * REC_STRIDE + cls_off;
+                const Q4<T> r0 = ld4<T>(r), r1 = (MODE != MODE_G) ? ld4<T>(r + 4) : Q4<T>{0, 0, 0, 0},
+                            r2 = (MODE != MODE_G) ? ld4<T>(r + 8) : Q4<T>{0, 0, 0, 0}, r3 = ld4<T>(r + 12);
+                Q4<T> u0{0, 0, 0, 0}, u1{0, 0, 0, 0};
+                if (MODE != MODE_G) {
+                    u0 = ld4<T>(recs + t * REC_STRIDE + REC_TAIL);
+                    u1 = ld4<T>(recs + t * REC_STRIDE + REC_TAIL + 4);
+                }
+                // fields: centre 0 (r0.a r0.b r0.c r0.d r1.a) centre 1 (r1.b r1.c r1.d r2.a r2.b) centre 2 (r2.c r2.d r3.a r3.b r3.c) V0 r3.d
+#pragma unroll
+                for (int i = 0; i < FPL; ++i) {
+                    T L0 = r0.a, A0x = r0.b, B0x = r0.c, A0y = r0.d, B0y = r1.a;
+                    T L1 = r1.b, A1x = r1.c, B1x = r1.d, A1y = r2.a, B1y = r2.b;
+                    T L2 = r2.c, A2x = r2.d, B2x = r3.a, A2y = r3.b, B2y = r3.c;
+                    T V0 = r3.d;
+                    if (!a.pm1) {  // general lambda: record holds |c|, sgn E dc, dE -- finish base/log here
+                        const T l = lam[i];
+                        const T b0 = M<T>::max_(M<T>::fma_(l, L0, T(1)), T(0));
+                        const T b1 = M<T>::max_(M<T>::fma_(l, L1, T(1)), T(0));
+                        const T b2 = M<T>::max_(M<T>::fma_(l, L2, T(1)), T(0));
+                        L0 = M<T>::max_(M<T>::log2_fast(b0), -M<T>::big());
+                        L1 = M<T>::max_(M<T>::log2_fast(b1), -M<T>::big());
+                        L2 = M<T>::max_(M<T>::log2_fast(b2), -M<T>::big());
+                        A0x *= l; A0y *= l; A1x *= l; A1y *= l; A2x *= l; A2y *= l;
+                        B0x *= b0; B0y *= b0; B1x *= b1; B1y *= b1; B2x *= b2; B2y *= b2;
+                        V0 *= b0;
+                    }
+                    const T q0 = M<T>::exp2_fast(zm1[i] * L0);
+                    val[i] = M<T>::fma_(q0, V0, val[i]);
+                    if (MODE != MODE_G) {
+                        const T q1 = M<T>::exp2_fast(zm1[i] * L1);
+                        const T q2 = M<T>::exp2_fast(zm1[i] * L2);
+                        const T zt = zeta[i];
+                        T sa = q0 * M<T>::fma_(zt, A0x, B0x);
+                        T sb = q0 * M<T>::fma_(zt, A0y, B0y);
+                        sa = M<T>::fma_(q1, M<T>::fma_(zt, A1x, B1x), sa);
+                        sb = M<T>::fma_(q1, M<T>::fma_(zt, A1y, B1y), sb);
+                        sa = M<T>::fma_(q2, M<T>::fma_(zt, A2x, B2x), sa);
+                        sb = M<T>::fma_(q2, M<T>::fma_(zt, A2y, B2y), sb);
+                        gx[i] = M<T>::fma_(sa, u0.a, gx[i]); gx[i] = M<T>::fma_(sb, u0.d, gx[i]);
+                        gy[i] = M<T>::fma_(sa, u0.b, gy[i]); gy[i] = M<T>::fma_(sb, u1.a, gy[i]);
+                        gz[i] = M<T>::fma_(sa, u0.c, gz[i]); gz[i] = M<T>::fma_(sb, u1.b, gz[i]);
+                    }
+                }
+            }
+            __syncwarp();
+        };
+
+        for (int tj = 0; tj + 1 < nn; ++tj) {
+            const T ujx = nb.ux[tj], ujy = nb.uy[tj], ujz = nb.uz[tj];
+            for (int kb = tj + 1; kb < nn; kb += 32) {
+                const int tk = kb + lane;
+                bool ok = false;
+                if (tk < nn) {
+                    const T wx = ujx - nb.ux[tk], wy = ujy - nb.uy[tk], wz = ujz - nb.uz[tk];
+                    const T z = M<T>::sqrt_(wx * wx + wy * wy + wz * wz);
+                    ok = (z < a.rc) && (z > T(0));  // the third side of the triangle (symm_funcs.py:34-50)
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 63] = tj | (tk << 16);
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= ANG_BATCH) {
+                    flush(ANG_BATCH);
+                    head = (head + ANG_BATCH) & 63;
+                    qn -= ANG_BATCH;
+                }
+            }
+        }
+        if (qn > 0) flush(qn);
+
+        // combine the triangle groups, then lanes < G own their functions' totals
+#pragma unroll
+        for (int i = 0; i < FPL; ++i) {
+            for (int o = G; o < 32; o <<= 1) {
+                val[i] += __shfl_xor_sync(0xffffffffu, val[i], o);
+                if (MODE != MODE_G) {
+                    gx[i] += __shfl_xor_sync(0xffffffffu, gx[i], o);
+                    gy[i] += __shfl_xor_sync(0xffffffffu, gy[i], o);
+                    gz[i] += __shfl_xor_sync(0xffffffffu, gz[i], o);
+                }
+            }
+        }
+        T fx = 0, fy = 0, fz = 0;
+        if (grp == 0) {
+#pragma unroll
+            for (int i = 0; i < FPL; ++i) {
+                if (col[i] < 0) continue;
+                const int64_t o = row * a.nf + col[i];
+                const T cf = coef[i];
+                if (MODE == MODE_G || MODE == MODE_DG) a.G[o] = cf * val[i];
+                if (MODE == MODE_DG) {
+                    const T dx = -cf * gx[i], dy = -cf * gy[i], dz = -cf * gz[i];
+                    a.dG[3 * o] = dx; a.dG[3 * o + 1] = dy; a.dG[3 * o + 2] = dz;
+                    bad |= !(isfinite(dx) && isfinite(dy) && isfinite(dz));
+                }
+                if (MODE == MODE_FORCE) {
+                    const T wv = a.w[o] * cf;  // F = -sum_f w dG = +sum_f w coef g
+                    fx = M<T>::fma_(wv, gx[i], fx); fy = M<T>::fma_(wv, gy[i], fy); fz = M<T>::fma_(wv, gz[i], fz);
+                }
+            }
+        }
+        if (MODE == MODE_FORCE) {
+            fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+            if (lane == 0) { a.force[3 * row] += fx; a.force[3 * row + 1] += fy; a.force[3 * row + 2] += fz; }
+        }
+        __syncwarp();
+    }
+    if (MODE == MODE_DG && bad) atomicOr(a.flag, NNMD_FLAG_NAN_DG);
+}
+
+// =============================================================================================
+// K5 normalise, K4c contraction
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_kernel(const T *G, int64_t n_rows, int nf, T *ghat,
+                                                        uint32_t *__restrict__ flag) {
+    const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    bool bad = false;
+    for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < n_rows; row += int64_t(gridDim.x) * wpb) {
+        const T *g = G + row * nf;
+        T ss = 0;
+        for (int f = lane; f < nf; f += 32) { const T v = g[f]; ss = M<T>::fma_(v, v, ss); }
+        ss = warp_sum(ss);
+        const T nrm = M<T>::sqrt_(ss);
+        for (int f = lane; f < nf; f += 32) {
+            const T v = g[f] / nrm;  // 0/0 -> NaN for an atom without neighbours, like calculate_sf.py:101
+            ghat[row * nf + f] = v;
+            bad |= !(v == v);
+        }
+    }
+    if (bad) atomicOr(flag, NNMD_FLAG_NAN_G);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) contract_kernel(const T *__restrict__ dE, const T *__restrict__ dG, int64_t n_rows,
+                                                       int nf, T *__restrict__ force) {
+    const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < n_rows; row += int64_t(gridDim.x) * wpb) {
+        const T *w = dE + row * nf;
+        const T *g = dG + row * nf * 3;
+        T acc[3] = {0, 0, 0};
+        // 96 contiguous elements per step: lane l covers component (l % 3) in every step
+        for (int e0 = 0; e0 < 3 * nf; e0 += 96) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int e = e0 + 32 * k + lane;
+                if (e < 3 * nf) {
+                    const T p = w[e / 3] * g[e];
+                    const int c = e % 3;
+                    acc[0] += c == 0 ? p : T(0); acc[1] += c == 1 ? p : T(0); acc[2] += c == 2 ? p : T(0);
+                }
+            }
+        }
+        const T fx = warp_sum(acc[0]), fy = warp_sum(acc[1]), fz = warp_sum(acc[2]);
+        if (lane == 0) { force[3 * row] = -fx; force[3 * row + 1] = -fy; force[3 * row + 2] = -fz; }
+    }
+}
+
+// =============================================================================================
+// launch helpers
+// =============================================================================================
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+template <typename T, int MODE>
+static int launch_radial(const nnmd_sf_plan *p, RadArgs<T> a, cudaStream_t st) {
+    int wpb = 8;
+    while (wpb > 1 && size_t(wpb) * 5 * a.cap * sizeof(T) > 160 * 1024) wpb >>= 1;
+    const size_t smem = size_t(wpb) * 5 * a.cap * sizeof(T);
+    if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "radial: neighbour row of %d entries exceeds shared memory", a.cap);
+    auto kern = radial_kernel<T, MODE>;
+    NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int64_t blocks = (a.n_rows + wpb - 1) / wpb;
+    blocks = std::min<int64_t>(blocks, int64_t(sm_count()) * 8);
+    ProfScope prof(PROF_RADIAL, st);
+    kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
+    NNMD_LAUNCH_CHECK("radial_kernel");
+    (void)p;
+    return NNMD_OK;
+}
+
+template <typename T, int FPL, int MODE>
+static int launch_angular_t(AngArgs<T> a, cudaStream_t st) {
+    const size_t per_warp = size_t(ANG_BATCH) * REC_STRIDE * sizeof(T) + size_t(NB_FIELDS) * a.cap * sizeof(T) + 64 * sizeof(int);
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    const size_t smem = per_warp * wpb;
+    if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "angular: neighbour row of %d entries exceeds shared memory", a.cap);
+    auto kern = angular_kernel<T, FPL, MODE>;
+    NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int occ = 1;
+    NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+    if (occ < 1) occ = 1;
+    int64_t blocks = (a.n_rows + wpb - 1) / wpb;
+    blocks = std::min<int64_t>(blocks, int64_t(sm_count()) * occ);  // persistent: one resident wave, rows strided
+    ProfScope prof(PROF_ANGULAR, st);
+    kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
+    NNMD_LAUNCH_CHECK("angular_kernel");
+    return NNMD_OK;
+}
+
+template <typename T, int MODE>
+static int launch_angular(const AngGroup &g, AngArgs<T> a, cudaStream_t st) {
+    a.kind = g.kind; a.pm1 = g.pm1; a.lanes = g.lanes; a.log_lanes = ilog2(g.lanes);
+    a.rc = T(g.rc); a.eta = T(g.eta);
+    a.zeta = (const T *)g.d_zeta; a.lam = (const T *)g.d_lam; a.coef = (const T *)g.d_coef; a.col = g.d_col;
+    switch (g.fpl) {
+        case 1: return launch_angular_t<T, 1, MODE>(a, st);
+        case 2: return launch_angular_t<T, 2, MODE>(a, st);
+        case 4: return launch_angular_t<T, 4, MODE>(a, st);
+    }
+    return set_err(NNMD_ERR_INVALID, "internal: bad fpl %d", g.fpl);
+}
+
+template <typename T, int MODE>
+static int sf_run(const nnmd_sf_plan *p, const T *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
+                  const int64_t *offsets, const int32_t *idx, int64_t max_row, T *G, T *dG, const T *w, T *force,
+                  uint32_t *flag, cudaStream_t st) {
+    const int64_t n_rows = n_frames * n_centres;
+    if (n_rows == 0) return NNMD_OK;
+    int cap = int((std::max<int64_t>(max_row, 1) + 3) & ~int64_t(3));
+    if (cap >= 32768) return set_err(NNMD_ERR_CAPACITY, "neighbour row of %lld entries is not supported", (long long)max_row);
+    if (p->rad.n > 0) {
+        RadArgs<T> a;
+        a.posw = posw; a.n_rows = n_rows; a.n_atoms = n_atoms; a.n_centres = n_centres; a.offsets = offsets; a.idx = idx;
+        a.cap = cap; a.n = p->rad.n; a.rc_max = T(p->rad.rc_max);
+        a.rc = (const T *)p->rad.d_rc; a.eta = (const T *)p->rad.d_eta; a.rs = (const T *)p->rad.d_rs; a.col = p->rad.d_col;
+        a.nf = p->nf; a.G = G; a.dG = dG; a.w = w; a.force = force; a.flag = flag;
+        int r = launch_radial<T, MODE>(p, a, st);
+        if (r) return r;
+    }
+    for (const AngGroup &g : p->groups) {
+        AngArgs<T> a;
+        a.posw = posw; a.n_rows = n_rows; a.n_atoms = n_atoms; a.n_centres = n_centres; a.offsets = offsets; a.idx = idx;
+        a.cap = cap; a.nf = p->nf; a.G = G; a.dG = dG; a.w = w; a.force = force; a.flag = flag;
+        int r = launch_angular<T, MODE>(g, a, st);
+        if (r) return r;
+    }
+    return NNMD_OK;
+}
+
+}  // namespace nnmd
+
+using namespace nnmd;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, const double *params, nnmd_sf_plan **out) {
+    if (!out) return set_err(NNMD_ERR_INVALID, "plan: null output");
+    *out = nullptr;
+    if (dtype != NNMD_F32 && dtype != NNMD_F64) return set_err(NNMD_ERR_INVALID, "plan: bad dtype %d", dtype);
+    if (nf <= 0 || !kinds || !params) return set_err(NNMD_ERR_INVALID, "plan: empty symmetry-function table");
+    for (int f = 0; f < nf; ++f) {
+        const int k = kinds[f];
+        if (k != NNMD_G1 && k != NNMD_G2 && k != NNMD_G4 && k != NNMD_G5)
+            return set_err(NNMD_ERR_INVALID, "Unknown symmetry function number: %d", k);
+        if (!(params[4 * f] > 0.0)) return set_err(NNMD_ERR_INVALID, "plan: function %d has a non-positive cutoff", f);
+    }
+    nnmd_sf_plan *p = new (std::nothrow) nnmd_sf_plan();
+    if (!p) return set_err(NNMD_ERR_INVALID, "plan: out of host memory");
+    p->dtype = dtype; p->nf = nf; p->rc_max = 0;
+    std::vector<double> rrc, reta, rrs;
+    std::vector<int> rcol;
+    std::map<std::tuple<int, double, double>, std::vector<int>> groups;
+    std::vector<std::tuple<int, double, double>> order;  // first-appearance order keeps launches deterministic
+    for (int f = 0; f < nf; ++f) {
+        p->rc_max = std::max(p->rc_max, params[4 * f]);
+        if (kinds[f] == NNMD_G1 || kinds[f] == NNMD_G2) {
+            rrc.push_back(params[4 * f]);
+            reta.push_back(kinds[f] == NNMD_G2 ? params[4 * f + 1] : 0.0);
+            rrs.push_back(kinds[f] == NNMD_G2 ? params[4 * f + 2] : 0.0);
+            rcol.push_back(f);
+            p->rad.rc_max = std::max(p->rad.rc_max, params[4 * f]);
+        } else {
+            auto key = std::make_tuple(int(kinds[f]), params[4 * f], params[4 * f + 1]);
+            if (!groups.count(key)) order.push_back(key);
+            groups[key].push_back(f);
+        }
+    }
+    p->rad.n = int(rcol.size());
+    int r = NNMD_OK;
+    if (p->rad.n > 0) {
+        if (!r) r = upload_real(dtype, rrc, &p->rad.d_rc);
+        if (!r) r = upload_real(dtype, reta, &p->rad.d_eta);
+        if (!r) r = upload_real(dtype, rrs, &p->rad.d_rs);
+        if (!r) r = upload_int(rcol, &p->rad.d_col);
+    }
+    for (auto &key : order) {
+        if (r) break;
+        r = build_group(dtype, std::get<0>(key), std::get<1>(key), std::get<2>(key), groups[key], params, p->groups);
+    }
+    if (r) { nnmd_sf_plan_destroy(p); return r; }
+    *out = p;
+    return NNMD_OK;
+}
+
+extern "C" void nnmd_sf_plan_destroy(nnmd_sf_plan *p) {
+    if (!p) return;
+    cudaFree(p->rad.d_rc); cudaFree(p->rad.d_eta); cudaFree(p->rad.d_rs); cudaFree(p->rad.d_col);
+    for (AngGroup &g : p->groups) { cudaFree(g.d_zeta); cudaFree(g.d_lam); cudaFree(g.d_coef); cudaFree(g.d_col); }
+    delete p;
+}
+
+extern "C" double nnmd_sf_plan_rc_max(const nnmd_sf_plan *p) { return p ? p->rc_max : 0.0; }
+
+static int sf_args_ok(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
+                      const int64_t *offsets, const int32_t *idx, int64_t max_row) {
+    if (!plan) return set_err(NNMD_ERR_INVALID, "sf: null plan");
+    if (n_frames < 0 || n_atoms < 0 || n_centres < 0 || n_centres > n_atoms || max_row < 0)
+        return set_err(NNMD_ERR_INVALID, "sf: bad sizes");
+    if (n_frames * n_centres > 0 && (!posw || !offsets)) return set_err(NNMD_ERR_INVALID, "sf: null pointer");
+    if (max_row > 0 && !idx) return set_err(NNMD_ERR_INVALID, "sf: null neighbour indices");
+    return NNMD_OK;
+}
+
+extern "C" int nnmd_sf_eval(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms,
+                            int64_t n_centres, const int64_t *offsets, const int32_t *idx, int64_t max_row, void *G,
+                            void *dG, uint32_t *flag, void *stream) {
+    int r = sf_args_ok(plan, posw, n_frames, n_atoms, n_centres, offsets, idx, max_row);
+    if (r) return r;
+    if (n_frames * n_centres > 0 && (!G || !flag)) return set_err(NNMD_ERR_INVALID, "sf_eval: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->dtype == NNMD_F32) {
+        if (dG) return sf_run<float, MODE_DG>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, (float *)G, (float *)dG, nullptr, nullptr, flag, st);
+        return sf_run<float, MODE_G>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, (float *)G, nullptr, nullptr, nullptr, flag, st);
+    }
+    if (dG) return sf_run<double, MODE_DG>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, (double *)G, (double *)dG, nullptr, nullptr, flag, st);
+    return sf_run<double, MODE_G>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, (double *)G, nullptr, nullptr, nullptr, flag, st);
+}
+
+extern "C" int nnmd_sf_force(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms,
+                             int64_t n_centres, const int64_t *offsets, const int32_t *idx, int64_t max_row,
+                             const void *w, void *force, void *virial, void *stream) {
+    int r = sf_args_ok(plan, posw, n_frames, n_atoms, n_centres, offsets, idx, max_row);
+    if (r) return r;
+    if (virial) return set_err(NNMD_ERR_INVALID, "sf_force: virial output is not implemented yet");
+    const int64_t n_rows = n_frames * n_centres;
+    if (n_rows > 0 && (!w || !force)) return set_err(NNMD_ERR_INVALID, "sf_force: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = plan->dtype == NNMD_F32 ? 4 : 8;
+    if (n_rows > 0) NNMD_CUDA_CHECK(cudaMemsetAsync(force, 0, size_t(n_rows) * 3 * es, st));
+    if (plan->dtype == NNMD_F32)
+        return sf_run<float, MODE_FORCE>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, nullptr, (const float *)w, (float *)force, nullptr, st);
+    return sf_run<double, MODE_FORCE>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, nullptr, (const double *)w, (double *)force, nullptr, st);
+}
+
+extern "C" int nnmd_sf_normalize(int dtype, const void *G, int64_t n_rows, int nf, void *ghat, uint32_t *flag, void *stream) {
+    if (dtype != NNMD_F32 && dtype != NNMD_F64) return set_err(NNMD_ERR_INVALID, "normalize: bad dtype %d", dtype);
+    if (n_rows < 0 || nf <= 0) return set_err(NNMD_ERR_INVALID, "normalize: bad sizes");
+    if (n_rows == 0) return NNMD_OK;
+    if (!G || !ghat || !flag) return set_err(NNMD_ERR_INVALID, "normalize: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpb = 8;
+    int64_t blocks = std::min<int64_t>((n_rows + wpb - 1) / wpb, int64_t(sm_count()) * 16);
+    ProfScope prof(PROF_NORMALIZE, st);
+    if (dtype == NNMD_F32) normalize_kernel<float><<<unsigned(blocks), wpb * 32, 0, st>>>((const float *)G, n_rows, nf, (float *)ghat, flag);
+    else normalize_kernel<double><<<unsigned(blocks), wpb * 32, 0, st>>>((const double *)G, n_rows, nf, (double *)ghat, flag);
+    NNMD_LAUNCH_CHECK("normalize_kernel");
+    return NNMD_OK;
+}
+
+extern "C" int nnmd_force_contract(int dtype, const void *dE, const void *dG, int64_t n_rows, int nf, void *force, void *stream) {
+    if (dtype != NNMD_F32 && dtype != NNMD_F64) return set_err(NNMD_ERR_INVALID, "contract: bad dtype %d", dtype);
+    if (n_rows < 0 || nf <= 0) return set_err(NNMD_ERR_INVALID, "contract: bad sizes");
+    if (n_rows == 0) return NNMD_OK;
+    if (!dE || !dG || !force) return set_err(NNMD_ERR_INVALID, "contract: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpb = 8;
+    int64_t blocks = std::min<int64_t>((n_rows + wpb - 1) / wpb, int64_t(sm_count()) * 16);
+    ProfScope prof(PROF_CONTRACT, st);
+    if (dtype == NNMD_F32) contract_kernel<float><<<unsigned(blocks), wpb * 32, 0, st>>>((const float *)dE, (const float *)dG, n_rows, nf, (float *)force);
+    else contract_kernel<double><<<unsigned(blocks), wpb * 32, 0, st>>>((const double *)dE, (const double *)dG, n_rows, nf, (double *)force);
+    NNMD_LAUNCH_CHECK("contract_kernel");
+    return NNMD_OK;
+}

@@ -1,0 +1,45 @@
+// sf_plan.h -- host-side description of one species' symmetry-function table (nnmd_sf_plan).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace nnmd {
+
+constexpr int ANG_MAX_FPL = 4;    // angular functions per lane (template values 1, 2, 4)
+constexpr int REC_STRIDE = 44;    // shared-memory record stride in reals (44 mod 32 = 12: conflict-free 16 B accesses)
+constexpr int REC_CLASS = 16;     // reals per lambda-class block
+constexpr int REC_TAIL = 32;      // offset of the unit vectors
+constexpr int ANG_BATCH = 32;     // triangles staged per batch
+constexpr int NB_FIELDS = 9;      // per-neighbour staged reals: ux uy uz d 1/d fc fc' psi psi'
+
+// One launch of the angular kernel: functions that share (kind, rc, eta).
+struct AngGroup {
+    int kind;           // NNMD_G4 | NNMD_G5
+    double rc, eta;
+    int pm1;            // all lambda in {+1,-1}: logs precomputed per class in the triangle record
+    int fpl;            // functions per lane
+    int lanes;          // G: lanes per triangle (power of two <= 32)
+    int n_slots;        // lanes * fpl table entries
+    // device tables in the working dtype, n_slots entries each (slot = lane*fpl + i); col = -1 marks padding
+    void *d_zeta = nullptr, *d_lam = nullptr, *d_coef = nullptr;
+    int *d_col = nullptr;
+    std::vector<int> cols;  // host copy (tests / debugging)
+};
+
+struct RadialTab {
+    int n = 0;          // number of G1/G2 functions
+    double rc_max = 0;
+    void *d_rc = nullptr, *d_eta = nullptr, *d_rs = nullptr;  // working dtype; G1 rows carry eta = 0, rs = 0
+    int *d_col = nullptr;
+};
+
+}  // namespace nnmd
+
+struct nnmd_sf_plan {
+    int dtype;
+    int nf;
+    double rc_max;
+    nnmd::RadialTab rad;
+    std::vector<nnmd::AngGroup> groups;
+};

@@ -1,0 +1,133 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the box, gloo in CPU tests).
+
+Two ways the path shards:
+  * spatial  -- one large structure is cut into x-slabs; every rank owns the atoms of its slab and imports a HALO
+    of width rc from the slabs next to it.  Because every contributing triplet is a closed triangle
+    (SURVEY 7.2), G_a, dG[a] and the reference-semantic force of an owned atom depend only on atoms within rc
+    of it: ONE exchange of positions per step, no reverse (force) communication.  Wrap-only PBC
+    means no halo crosses a periodic face.
+  * frames   -- training sets shard the frame axis; the only collective is the all-reduce of the flat MLP
+    gradient buffer (`allreduce_gradients`).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as td
+
+from .features.symm_funcs import map_positions_pbc
+
+
+def _world():
+    if td.is_available() and td.is_initialized():
+        return td.get_rank(), td.get_world_size()
+    return 0, 1
+
+
+@dataclass
+class SlabShard:
+    """Ownership and halo plan of one rank for an x-slab decomposition."""
+
+    rank: int
+    world: int
+    rc: float
+    n_global: int
+    owned_idx: torch.Tensor                     # (n_owned,) global atom indices, ascending
+    owned_pos: torch.Tensor                     # (n_owned, 3) ORIGINAL (unwrapped) positions
+    send_idx: list = field(default_factory=list)  # per peer: indices into `owned_*` to send (None: nothing)
+    edges: torch.Tensor | None = None           # (world+1,) slab boundaries on the wrapped x axis
+
+    @property
+    def n_owned(self) -> int:
+        return int(self.owned_idx.numel())
+
+    @staticmethod
+    def slab_edges(x_wrapped: torch.Tensor, world: int) -> torch.Tensor:
+        """Equal-count boundaries on the wrapped x coordinate: edges[0] = -inf, edges[world] = +inf."""
+        xs = torch.sort(x_wrapped.double()).values
+        n = xs.numel()
+        inner = [float(xs[(k * n) // world]) for k in range(1, world)]
+        return torch.tensor([-float("inf")] + inner + [float("inf")], dtype=torch.float64)
+
+    @classmethod
+    def from_global(cls, pos: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, rc: float, rank: int, world: int):
+        """Domain decomposition of a structure every rank can see (synthetic benchmarks, file-based inputs).
+
+        Ownership is decided on the WRAPPED x coordinate (the coordinate the kernels measure distances in);
+        the positions that travel are the original ones, so every rank's K0 reproduces the single-GPU wrap bit for bit.
+        """
+        pos = pos.detach().cpu()
+        xw = map_positions_pbc(pos, cell.detach().cpu().to(pos.dtype), pbc.detach().cpu().to(pos.dtype))[:, 0].double()
+        edges = cls.slab_edges(xw, world)
+        lo, hi = edges[rank], edges[rank + 1]
+        mine = torch.nonzero((xw >= lo) & (xw < hi)).flatten()
+        send = []
+        for peer in range(world):
+            if peer == rank:
+                send.append(None)
+                continue
+            plo, phi = edges[peer] - rc, edges[peer + 1] + rc
+            sel = torch.nonzero((xw[mine] >= plo) & (xw[mine] < phi)).flatten()
+            send.append(sel if sel.numel() else None)
+        return cls(rank, world, float(rc), pos.shape[0], mine, pos[mine].contiguous(), send, edges)
+
+    def exchange_halo(self, device=None) -> torch.Tensor:
+        """Positions this rank computes on: owned atoms first, then the halo atoms received from the peers.
+
+        world == 1: just the owned positions on `device`.  Otherwise one count all-gather plus one batched
+        send/recv round (NCCL on GPUs; gloo when the tensors live on the CPU).
+        """
+        device = torch.device(device) if device is not None else self.owned_pos.device
+        own = self.owned_pos.to(device)
+        if self.world == 1:
+            return own
+        counts = torch.tensor([0 if s is None else int(s.numel()) for s in self.send_idx], dtype=torch.int64, device=device)
+        all_counts = [torch.empty_like(counts) for _ in range(self.world)]
+        td.all_gather(all_counts, counts)
+        recv_counts = [int(all_counts[peer][self.rank]) for peer in range(self.world)]
+        ops, recv_bufs, keep = [], [], []
+        for peer in range(self.world):
+            if peer == self.rank:
+                continue
+            if self.send_idx[peer] is not None:
+                buf = own.index_select(0, self.send_idx[peer].to(device)).contiguous()
+                keep.append(buf)
+                ops.append(td.P2POp(td.isend, buf, peer))
+            if recv_counts[peer] > 0:
+                rb = torch.empty((recv_counts[peer], 3), dtype=own.dtype, device=device)
+                recv_bufs.append(rb)
+                ops.append(td.P2POp(td.irecv, rb, peer))
+        if ops:
+            for req in td.batch_isend_irecv(ops):
+                req.wait()
+        return torch.cat([own] + recv_bufs, dim=0) if recv_bufs else own
+
+
+def shard_frames(n_frames: int, rank: int | None = None, world: int | None = None) -> range:
+    """Contiguous block of frame indices owned by `rank` (training / descriptor-cache sharding)."""
+    if rank is None or world is None:
+        rank, world = _world()
+    lo = (n_frames * rank) // world
+    hi = (n_frames * (rank + 1)) // world
+    return range(lo, hi)
+
+
+def allreduce_gradients(params, average: bool = True) -> None:
+    """One all-reduce of the flat gradient buffer of all atomic networks (<= ~30k floats for the shipped nets:
+    latency-bound, so everything goes in a single message)."""
+    rank, world = _world()
+    if world == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    td.all_reduce(flat, op=td.ReduceOp.SUM)
+    if average:
+        flat /= world
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

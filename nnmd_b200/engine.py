@@ -1,0 +1,85 @@
+"""Positions -> (descriptors) -> per-atom energy -> force, entirely on the GPU kernels (K0..K6).
+
+This is the evaluation pipeline behind `BPNN.predict` and `bench.py`.  Force semantics are the reference's
+(nnmd/nn/bpnn.py:347-354):  F[a] = - sum_f (dE/dg_hat[a,f]) * dG[a,f,:]  with dG the un-normalised
+summed gradient of calculate_sf.
+
+Two data flows over the same kernels:
+  materialize : K1 -> K2/K3 (+K4a: dG written once to HBM) -> K5 -> K6 -> K4c (contract against dG)
+  fused       : K1 -> K2/K3 (values only) -> K5 -> K6 -> K4b (re-walks the triangles, contracts on the fly;
+                no (N,F,3) tensor ever exists -- for structures whose dG would not fit)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from .features.calculate_sf import SfPlan, get_plan, normalize, raise_on_flag, raw_descriptors
+from .neighbor import NeighborList, build_from_wrapped, wrap_positions
+
+
+@dataclass
+class EvalResult:
+    energy: torch.Tensor          # (n_frames,) total energy per frame
+    e_atoms: torch.Tensor         # (n_frames, n_centres)
+    forces: torch.Tensor          # (n_frames, n_centres, 3)
+    g: torch.Tensor               # (n_frames, n_centres, F) normalised descriptors
+    nlist: NeighborList
+    flag: torch.Tensor
+
+
+def force_contract(dE: torch.Tensor, dG: torch.Tensor) -> torch.Tensor:
+    """K4c: F[a,:] = - sum_f dE[a,f] dG[a,f,:]   (einsum "ijk,ijkl->ijl" of bpnn.py:353)."""
+    lib = _lib.load()
+    nf = dE.shape[-1]
+    dE2 = dE.detach().reshape(-1, nf).contiguous()
+    dG2 = dG.detach().reshape(-1, nf, 3).contiguous()
+    out = torch.empty((dE2.shape[0], 3), dtype=dE.dtype, device=dE.device)
+    with torch.cuda.device(dE.device):
+        _lib.check(lib.nnmd_force_contract(_lib.dtype_code(dE.dtype), _lib.ptr(dE2), _lib.ptr(dG2), dE2.shape[0], nf,
+                                           _lib.ptr(out), _lib.stream_ptr()))
+    return out.view(*dE.shape[:-1], 3)
+
+
+def fused_force(plan: SfPlan, nl: NeighborList, w: torch.Tensor) -> torch.Tensor:
+    """K4b: forces from dE/dg_hat without a materialised dG."""
+    lib = _lib.load()
+    w2 = w.detach().reshape(-1, plan.nf).contiguous()
+    out = torch.empty((nl.n_rows, 3), dtype=w.dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(lib.nnmd_sf_force(plan.handle, _lib.ptr(nl.posw), nl.n_frames, nl.n_atoms, nl.n_centres,
+                                     _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(w2), _lib.ptr(out),
+                                     None, _lib.stream_ptr()))
+    return out
+
+
+def energy_forces(cart: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, symm_funcs_data: dict, net,
+                  mode: str = "materialize", mlp_precision: str = "exact", n_centres: int | None = None,
+                  check: bool = True) -> EvalResult:
+    """Evaluate one species: cart (B,N,3) on the GPU -> energies and reference-semantic forces."""
+    _lib.require_cuda()
+    if cart.dim() == 2:
+        cart = cart.unsqueeze(0)
+    B, N, _ = cart.shape
+    plan = get_plan(symm_funcs_data, cart.dtype, cart.device)
+    posw = wrap_positions(cart, cell, pbc)
+    nl = build_from_wrapped(posw, B, N, plan.rc_max, n_centres)
+    nc = nl.n_centres
+    if mode == "materialize":
+        G, dG, flag = raw_descriptors(plan, nl, with_grad=True)
+    elif mode == "fused":
+        G, dG, flag = raw_descriptors(plan, nl, with_grad=False)
+    else:
+        raise ValueError(f"unknown mode {mode!r}")
+    g = normalize(G, flag, out=G)
+    e, dE = net.energy_and_grad(g, need_grad=True, precision=mlp_precision)
+    if mode == "materialize":
+        f = force_contract(dE, dG)
+    else:
+        f = fused_force(plan, nl, dE)
+    if check:
+        raise_on_flag(flag)
+    e_atoms = e.view(B, nc)
+    return EvalResult(e_atoms.sum(dim=1), e_atoms, f.view(B, nc, 3), g.view(B, nc, plan.nf), nl, flag)

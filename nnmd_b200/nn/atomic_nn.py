@@ -1,0 +1,72 @@
+"""Per-species atomic network (reference: nnmd/nn/atomic_nn.py:5-48).
+
+Linear -> sigmoid -> ... -> Linear, one output per atom.  Parameters live in `self.model` (an nn.Sequential of
+nn.Linear) so `state_dict()` keys are `model.{i}.weight|bias` and the reference's shipped weights
+(samples/*/models_*/atomic_nn_*.pt) load unchanged.
+
+Two execution paths:
+  * `energy_and_grad(x)`  -- K6 (csrc/mlp.cu): e and dE/dx in one fused CUDA pass, no autograd graph; used by
+    `BPNN.predict` and the evaluation engine.
+  * `forward(x)`          -- differentiable torch ops (needed while the training step differentiates through
+    dE/dx); same arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+
+class AtomicNN(nn.Module):
+    def __init__(self, input_size: int, hidden_sizes, output_size: int = 1, activation=torch.sigmoid):
+        super().__init__()
+        if isinstance(hidden_sizes, list):
+            widths = [input_size] + list(hidden_sizes) + [output_size]
+        elif isinstance(hidden_sizes, int):
+            widths = [input_size, hidden_sizes, output_size]
+        else:
+            raise ValueError("hidden_sizes must be a list or an integer")
+        self.model = nn.Sequential(*[nn.Linear(a, b) for a, b in zip(widths[:-1], widths[1:])])
+        self.activation = activation
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        last = len(self.model) - 1
+        for i, layer in enumerate(self.model):
+            x = layer(x)
+            if i != last:
+                x = self.activation(x)
+        return x
+
+    # ---- CUDA inference path ------------------------------------------------------------------------------
+    def layer_sizes(self) -> list[int]:
+        return [self.model[0].in_features] + [m.out_features for m in self.model]
+
+    def energy_and_grad(self, x: torch.Tensor, need_grad: bool = True, precision: str = "exact"):
+        """K6: per-atom energies e (..., 1) and dE/dx (..., F) for x (..., F) on the GPU; no autograd graph."""
+        if self.activation is not torch.sigmoid:
+            raise NotImplementedError("the CUDA atomic network implements the reference's sigmoid activation only")
+        _lib.require_cuda()
+        lib = _lib.load()
+        if not x.is_cuda:
+            raise _lib.NnmdError("AtomicNN.energy_and_grad needs CUDA tensors")
+        sizes = self.layer_sizes()
+        dtype = x.dtype
+        x2 = x.detach().reshape(-1, sizes[0]).contiguous()
+        n_rows = x2.shape[0]
+        ws = [m.weight.detach().to(device=x.device, dtype=dtype).contiguous() for m in self.model]
+        bs = [m.bias.detach().to(device=x.device, dtype=dtype).contiguous() for m in self.model]
+        L = len(ws)
+        e = torch.empty(n_rows, dtype=dtype, device=x.device)
+        dE = torch.empty_like(x2) if need_grad else None
+        c_sizes = (ctypes.c_int32 * (L + 1))(*sizes)
+        c_w = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+        c_b = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
+        prec = {"exact": _lib.MLP_EXACT, "tf32": _lib.MLP_TF32}[precision]
+        with torch.cuda.device(x.device):
+            _lib.check(lib.nnmd_mlp_energy_grad(_lib.dtype_code(dtype), prec, L, c_sizes, c_w, c_b, _lib.ptr(x2), n_rows,
+                                                _lib.ptr(e), _lib.ptr(dE), _lib.stream_ptr()))
+        e = e.view(*x.shape[:-1], 1)
+        return e, (dE.view_as(x) if need_grad else None)

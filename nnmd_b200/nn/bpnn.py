@@ -1,0 +1,238 @@
+"""Behler-Parrinello network: one atomic MLP per species, trained on energies and forces
+(reference: nnmd/nn/bpnn.py:45-565).  Public surface, config keys, optimizer settings, loss, log format and
+checkpoint layout follow the reference; evaluation (`predict`) runs on the CUDA kernels K0..K6.
+
+Deviations from the reference, all of them places where the reference raises as shipped:
+  * `predict(cartesians, cell, symm_func_params, pbc=None)`: the reference forgets `pbc` and raises TypeError
+    (bpnn.py:529-531).  Here pbc defaults to `self.pbc` when `config` received one, else all-False for a
+    zero-determinant cell and all-True otherwise.
+  * `fit` works without the DEBUG environment variable and without installed package metadata.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.utils.data import DataLoader
+
+from .._util._logger import Logger
+from ..engine import force_contract
+from ..features import calculate_sf
+from .atomic_nn import AtomicNN
+from .dataset import TrainAtomicDataset
+
+torch.manual_seed(0)  # the reference seeds at import (bpnn.py:18); sample runs depend on it
+DEBUG = os.environ.get("DEBUG", False)
+
+if DEBUG:
+    from tqdm import tqdm
+else:
+    def tqdm(iterable, **_kwargs):
+        return iterable
+
+
+class RMSELoss(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.mse = torch.nn.MSELoss()
+
+    def forward(self, yhat, y):
+        return torch.sqrt(self.mse(yhat, y))
+
+
+available_optimizers = {"adam": torch.optim.Adam, "adamw": torch.optim.AdamW}
+available_losses = {"mse": torch.nn.MSELoss, "mae": torch.nn.L1Loss, "rmse": RMSELoss}
+
+
+def _package_version() -> str:
+    try:
+        from importlib.metadata import version
+        return version("nnmd")
+    except Exception:
+        return "0.2.0.dev0+b200"
+
+
+class BPNN(torch.nn.Module):
+    """High-dimensional NN potential: per-species AtomicNN, shared optimizer (reference: bpnn.py:45-62)."""
+
+    def __init__(self, dtype=torch.float32, use_cuda: bool = True) -> None:
+        super().__init__()
+        self.dtype = dtype
+        self.use_cuda = use_cuda
+        self.device = torch.device("cuda") if self.use_cuda else torch.device("cpu")
+        self.pbc = None
+
+    # ------------------------------------------------------------------------------------------ configuration
+    def config(self, neural_net_data: dict):
+        """reference: bpnn.py:106-194 (Xavier-uniform weights, zero biases, Adam(0.8,0.9999)/AdamW(0.9,0.999) + amsgrad)."""
+        self.neural_net_data = neural_net_data
+        self.species = neural_net_data["atom_species"]
+        self.input_sizes = neural_net_data["input_sizes"]
+        self.hidden_sizes = neural_net_data["hidden_sizes"]
+        self.learning_rate = neural_net_data["learning_rate"]
+        self.l2_regularization = neural_net_data["l2_regularization"]
+        self.e_loss_coeff = neural_net_data["e_loss_coeff"]
+        self.f_loss_coeff = neural_net_data["f_loss_coeff"]
+        if "pbc" in neural_net_data:
+            self.pbc = neural_net_data["pbc"]
+
+        self.atomic_nets = []
+        for i, spec in enumerate(self.species):
+            net = AtomicNN(input_size=self.input_sizes[i], hidden_sizes=self.hidden_sizes[i], output_size=1)
+            net = net.to(self.device)
+            if neural_net_data["load_models"]:
+                net.load_state_dict(torch.load(f"{neural_net_data['path']}/atomic_nn_{spec}.pt", map_location=self.device))
+            else:
+                for layer in net.model:
+                    if isinstance(layer, torch.nn.Linear):
+                        torch.nn.init.xavier_uniform_(layer.weight)
+                        torch.nn.init.constant_(layer.bias, 0)
+            self.atomic_nets.append(net)
+
+        self.criterion = torch.nn.MSELoss()
+
+        params = [p for net in self.atomic_nets for p in net.parameters()]
+        name = neural_net_data["optimizer"]
+        if name is None:
+            name = "adam"
+            print("Optimizer is not specified, using default: Adam")
+        elif name not in available_optimizers:
+            raise ValueError(f"Optimizer {name} is not available. "
+                             f"Available optimizers: {list(available_optimizers.keys())}")
+        betas = (0.9, 0.999) if name == "adamw" else (0.8, 0.9999)
+        self.optim = available_optimizers[name](params=params, lr=self.learning_rate,
+                                                weight_decay=self.l2_regularization, betas=betas, amsgrad=True)
+
+    # ------------------------------------------------------------------------------------------------- loss
+    def _loss(self, e_nn, energies, f_nn, forces):
+        """e_coeff * MSE(E) + f_coeff / 3 * MSE(F)   (reference: bpnn.py:196-215)."""
+        E_loss = self.e_loss_coeff * self.criterion(e_nn, energies)
+        F_loss = self.f_loss_coeff / 3 * self.criterion(f_nn, forces)
+        return E_loss + F_loss, E_loss, F_loss
+
+    def _energies_forces(self, g: dict, dG: dict):
+        """Per-species MLP, dE/dg (graph kept for the force loss) and the force contraction (bpnn.py:342-364)."""
+        e_nn, f_nn = [], []
+        for i, spec in enumerate(self.species):
+            e_spec = self.atomic_nets[i](g[spec])
+            dE = torch.autograd.grad(e_spec.sum(), g[spec], create_graph=True)[0]
+            e_nn.append(e_spec)
+            f_nn.append(-torch.einsum("ijk,ijkl->ijl", dE, dG[spec]))
+        return torch.cat(e_nn, dim=0), torch.cat(f_nn, dim=0)
+
+    # ------------------------------------------------------------------------------------------------ loops
+    def _run_epoch(self, loader, train: bool, desc: str):
+        for net in self.atomic_nets:
+            net.train(train)
+        tot = torch.zeros(3, device=self.device)
+        for g, dG, energy, forces in tqdm(loader, desc=desc, total=len(loader)):
+            if train:
+                self.optim.zero_grad(set_to_none=True)
+            e_nn, f_nn = self._energies_forces(g, dG)
+            energy = energy.to(device=self.device)
+            forces = forces.to(device=self.device)
+            loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), energy, f_nn, forces)
+            if train:
+                loss.backward()
+                self.optim.step()
+            tot += torch.stack([e_loss.detach(), f_loss.detach(), loss.detach()])
+        tot /= len(loader)
+        return tot[0], tot[1], tot[2]
+
+    def _train_loop(self, epoch: int, train_loader: DataLoader):
+        """reference: bpnn.py:308-377; returns epoch means (E loss, F loss, total)."""
+        return self._run_epoch(train_loader, True, f"Epoch {epoch + 1}, Training")
+
+    def _validate(self, epoch: int, val_loader: DataLoader):
+        """reference: bpnn.py:379-444."""
+        return self._run_epoch(val_loader, False, f"Epoch {epoch + 1}, Validation")
+
+    def _test(self, test_loader: DataLoader):
+        """reference: bpnn.py:446-505."""
+        return self._run_epoch(test_loader, False, "Testing")
+
+    def _describe_training(self, n_train, n_val, n_test, batch_size, epochs):
+        """Log header, same lines as the reference (bpnn.py:64-104; samples/*/plot_errors.py parse the log)."""
+        log = self.net_log.info
+        log(f"NNMD v{_package_version()}\n")
+        log("---Neural network parameters---")
+        log(f"device:                             {self.device}")
+        log(f"training epochs:                    {epochs}")
+        log(f"batch size:                         {batch_size}")
+        log(f"optimizer:                          {self.optim.__class__.__name__}")
+        log(f"loss function:                      {self.criterion.__class__.__name__}")
+        log(f"energies loss function coefficient: {self.e_loss_coeff}")
+        log(f"forces loss function coefficient:   {self.f_loss_coeff}")
+        log(f"learning rate:                      {self.learning_rate}")
+        log(f"scheduler:                          {self.sched.__class__.__name__}")
+        log(f"L2 regularization coefficient:      {self.l2_regularization}\n\n")
+        log("----Atomic NNs parameters----")
+        log(f"input sizes (number of descriptors): {self.input_sizes}")
+        log(f"hidden sizes:                        {self.hidden_sizes}\n\n")
+        log("---Dataset parameters---")
+        log(f"Training sample size:   {n_train}")
+        log(f"Validation sample size: {n_val}")
+        log(f"Test sample size:       {n_test}\n\n")
+
+    def fit(self, train_dataset: TrainAtomicDataset, val_dataset: TrainAtomicDataset, test_dataset: TrainAtomicDataset):
+        """reference: bpnn.py:217-306 (ExponentialLR gamma 0.99, net.log, per-epoch train/validation lines)."""
+        batch_size = self.neural_net_data["batch_size"]
+        epochs = self.neural_net_data["epochs"]
+        train_loader = DataLoader(train_dataset, batch_size=batch_size, shuffle=True)
+        val_loader = DataLoader(val_dataset, batch_size=batch_size, shuffle=True)
+        test_loader = DataLoader(test_dataset, batch_size=batch_size, shuffle=True)
+        self.sched = torch.optim.lr_scheduler.ExponentialLR(self.optim, gamma=0.99)
+        self.net_log = Logger.get_logger("Net training info", "net.log")
+        self._describe_training(len(train_dataset), len(val_dataset), len(test_dataset), batch_size, epochs)
+        curr_lr = self.optim.param_groups[0]["lr"]
+        line = "{loss} E = {e_loss:e}, {loss} F = {f_loss:e}, {loss} total = {total:e} eV"
+        name = self.criterion.__class__.__name__
+        for epoch in range(epochs):
+            e_loss, f_loss, loss = self._train_loop(epoch, train_loader)
+            self.net_log.info(f"Epoch {epoch + 1}: training:   "
+                              + line.format(e_loss=e_loss.item(), f_loss=f_loss.item(), loss=name, total=loss.item()))
+            e_loss, f_loss, loss = self._validate(epoch, val_loader)
+            self.net_log.info(f"Epoch {epoch + 1}: validation: "
+                              + line.format(e_loss=e_loss.item(), f_loss=f_loss.item(), loss=name, total=loss.item()))
+            self.sched.step()
+            if self.optim.param_groups[0]["lr"] != curr_lr:
+                curr_lr = self.optim.param_groups[0]["lr"]
+                self.net_log.info(f"Learning rate changed to {curr_lr}")
+        e_loss, f_loss, loss = self._test(test_loader)
+        self.net_log.info("Testing: " + line.format(e_loss=e_loss.item(), f_loss=f_loss.item(), loss=loss.item(),
+                                                    total=loss.item()))
+
+    # ---------------------------------------------------------------------------------------------- predict
+    def _default_pbc(self, cell: torch.Tensor) -> torch.Tensor:
+        if self.pbc is not None:
+            return torch.as_tensor(self.pbc, dtype=self.dtype)
+        has_cell = bool(torch.det(cell.detach().to("cpu", torch.float64)) != 0)
+        return torch.full((3,), 1.0 if has_cell else 0.0, dtype=self.dtype)
+
+    def predict(self, cartesians: dict, cell: torch.Tensor, symm_func_params: dict, pbc=None):
+        """Energies and forces for frames of atoms (reference: bpnn.py:507-554), on K0..K6.
+
+        cartesians: {species: (B,N,3) or (N,3)}; returns (E per frame squeezed, F squeezed) like the reference:
+        species are concatenated along dim 0 exactly as bpnn.py:546-552 does.
+        """
+        for net in self.atomic_nets:
+            net.eval()
+        pbc_t = self._default_pbc(cell) if pbc is None else torch.as_tensor(pbc)
+        e_nn = f_nn = None
+        for i, spec in enumerate(self.species):
+            cart = cartesians[spec].to(device=self.device)
+            if cart.dim() == 2:
+                cart = cart.unsqueeze(0)
+            cartesians[spec] = cart
+            g, dg = calculate_sf(cart, cell, pbc_t.to(cart.dtype), symm_func_params[spec], disable_tqdm=True)
+            e_spec, dE = self.atomic_nets[i].energy_and_grad(g, need_grad=True)
+            f_spec = force_contract(dE, dg)
+            e_spec, f_spec = e_spec.squeeze(0), f_spec.squeeze(0)  # the reference squeezes g/dg before the net
+            e_nn = e_spec if e_nn is None else torch.cat((e_nn, e_spec), dim=0)
+            f_nn = f_spec if f_nn is None else torch.cat((f_nn, f_spec), dim=0)
+        return e_nn.sum(1).squeeze(), f_nn.squeeze()
+
+    def save_model(self, path: str):
+        """One state_dict per species at <path>/atomic_nn_<spec>.pt (reference: bpnn.py:556-565)."""
+        for spec, net in zip(self.neural_net_data["atom_species"], self.atomic_nets):
+            torch.save(net.state_dict(), f"{path}/atomic_nn_{spec}.pt")

@@ -1,0 +1,81 @@
+"""CPU-side checks: the C-ABI library builds for sm_100a, loads, and exports every symbol include/nnmd_b200.h declares;
+host logic (plan validation, calculate_params, dense helpers) behaves like the reference.  No compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    from nnmd_b200 import _lib
+    lib = _lib.load()
+    with open(os.path.join(ROOT, "include", "nnmd_b200.h")) as fh:
+        header = fh.read()
+    declared = set(re.findall(r"\b(nnmd_[a-z0-9_]+)\s*\(", header))
+    declared.discard("nnmd_sf_plan")
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    assert lib.nnmd_abi_version() == 1
+
+
+def test_compute_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from nnmd_b200 import _lib
+    from nnmd_b200.features import calculate_sf
+    with pytest.raises(_lib.NnmdError, match="no CPU fallback"):
+        calculate_sf(torch.zeros(1, 3, 3), torch.zeros(3, 3), torch.zeros(3), {"features": [1], "params": [[3.0]]})
+
+
+def test_calculate_params_matches_reference_vectors(golden_dir):
+    from nnmd_b200.features import calculate_params
+    d = np.load(os.path.join(golden_dir, "calculate_params.npz"))
+    n = 0
+    for key in d.files:
+        if not key.startswith("args_"):
+            continue
+        args = [float(a) if "." in a else int(a) for a in key[5:].split("_")]
+        rows = calculate_params(*args)
+        arr = np.full((len(rows), 4), np.nan)
+        for i, r in enumerate(rows):
+            arr[i, :len(r)] = [float(x) for x in r]
+        assert np.array_equal(arr, d[key], equal_nan=True), key
+        n += 1
+    assert n == 4
+    with pytest.raises(ZeroDivisionError):
+        calculate_params(6.0, 0, 1, 0, 0, 0)
+
+
+def test_dense_helpers_match_oracle():
+    """g*_function(distances, ...) helpers (kept as thin torch code for the plotting samples)."""
+    from nnmd_b200 import features as F
+    from oracle import dense_oracle as O2
+    torch.manual_seed(0)
+    pos = torch.rand(2, 12, 3, dtype=torch.float64) * 5
+    cell = torch.tensor([[5.0, 0, 0], [0.5, 5, 0], [0, 0, 5]], dtype=torch.float64)
+    pbc = torch.tensor([1.0, 1, 0], dtype=torch.float64)
+    d = F.calculate_distances(pos - 2.0, cell, pbc)
+    assert torch.allclose(d, O2.distance_matrix(pos - 2.0, cell, pbc), atol=1e-14)
+    assert torch.allclose(F.f_cutoff(d, 3.0), O2.cutoff_fn(d, 3.0))
+    assert torch.allclose(F.g1_function(d, 3.0), O2._radial(d, 1, [3.0]))
+    assert torch.allclose(F.g2_function(d, 3.0, 0.7, 1.1), O2._radial(d, 2, [3.0, 0.7, 1.1]))
+    assert torch.allclose(F.g4_function(d, 3.0, 0.1, 2.5, -1), O2._angular(d, 4, [3.0, 0.1, 2.5, -1], "exact"))
+    assert torch.allclose(F.g5_function(d, 3.0, 0.1, 3, 1), O2._angular(d, 5, [3.0, 0.1, 3, 1], "exact"))
+    assert [m.value for m in F.SymmetryFunction] == [1, 2, 4, 5]
+
+
+def test_atomic_nn_state_dict_layout():
+    from nnmd_b200.nn import AtomicNN
+    net = AtomicNN(14, [64, 64])
+    assert list(net.state_dict().keys()) == [f"model.{i}.{k}" for i in range(3) for k in ("weight", "bias")]
+    assert AtomicNN(5, 7).layer_sizes() == [5, 7, 1]
+    with pytest.raises(ValueError, match="hidden_sizes must be a list or an integer"):
+        AtomicNN(3, (4, 4))
+    x = torch.rand(2, 5, 14)
+    assert net(x).shape == (2, 5, 1)

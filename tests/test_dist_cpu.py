@@ -1,0 +1,69 @@
+"""world_size-2 gloo tests of the multi-GPU host logic (spatial slab sharding with halo exchange, frame sharding,
+gradient all-reduce).  CPU only: the kernels are not involved, the checker is the O(N) oracle's pair set."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from nnmd_b200 import dist
+    from nnmd_b200.workloads import fcc_cell
+    pos, cell, pbc = fcc_cell(6, dtype=torch.float64)
+    pos = pos - 3.0  # some atoms start outside the cell: ownership must follow the WRAPPED coordinate
+    shard = dist.SlabShard.from_global(pos, cell, pbc, rc=6.0, rank=rank, world=world)
+    local = shard.exchange_halo("cpu")
+    # gradient all-reduce
+    p = torch.nn.Parameter(torch.zeros(5))
+    p.grad = torch.full((5,), float(rank + 1))
+    dist.allreduce_gradients([p])
+    frames = list(dist.shard_frames(11))
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), owned=shard.owned_idx.numpy(), local=local.numpy(),
+             grad=p.grad.numpy(), frames=np.asarray(frames))
+    td.destroy_process_group()
+
+
+def test_slab_shard_halo_and_allreduce(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from nnmd_b200.features.symm_funcs import map_positions_pbc
+    from nnmd_b200.workloads import fcc_cell
+    from oracle import nl_oracle as O3
+    pos, cell, pbc = fcc_cell(6, dtype=torch.float64)
+    pos = pos - 3.0
+    n = pos.shape[0]
+    pairs = O3.pairs(pos, cell, pbc, 6.0)
+    parts = [np.load(os.path.join(str(tmp_path), f"r{r}.npz")) for r in range(world)]
+    owned = [set(p["owned"].tolist()) for p in parts]
+    assert owned[0].isdisjoint(owned[1]) and len(owned[0] | owned[1]) == n
+    assert abs(len(owned[0]) - len(owned[1])) <= 1
+    for r, p in enumerate(parts):
+        local = torch.from_numpy(p["local"])
+        n_own = len(p["owned"])
+        # owned atoms come first, in ascending global order, with their ORIGINAL positions
+        assert torch.equal(local[:n_own], pos[torch.from_numpy(p["owned"])])
+        # every neighbour (inside rc, reference pair set) of an owned atom is present locally
+        have = {tuple(np.round(v, 9)) for v in p["local"]}
+        need = {int(j) for i, j in pairs if int(i) in owned[r]}
+        for j in need:
+            assert tuple(np.round(pos[j].numpy(), 9)) in have
+        # the halo is a strict subset of the other rank's atoms (no duplicates of owned atoms)
+        assert local.shape[0] < n and local.shape[0] - n_own > 0
+        assert np.allclose(p["grad"], 1.5)
+    assert sorted(parts[0]["frames"].tolist() + parts[1]["frames"].tolist()) == list(range(11))
+    # slabs are cut on the wrapped coordinate
+    xw = map_positions_pbc(pos, cell, pbc)[:, 0]
+    assert xw[list(owned[0])].max() <= xw[list(owned[1])].min()

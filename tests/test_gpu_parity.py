@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracles and the reference-generated
+golden fixtures.  Run on the B200 box with `-m gpu`.
+
+Tolerances (BASELINE.json north_star): fp64 mode 1e-10 relative against the exact oracles (O2/O3); against the
+reference itself the angular columns can only agree to its own complex64 round-off (<= 5e-7), radial
+columns to 1e-10.  fp32 mode: 1e-5 relative for descriptors/energies, 1e-4 absolute for forces.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import SF_CASES, col_relerr, load_case, relerr
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _inputs(d, dtype):
+    return (torch.tensor(d["cart"], dtype=dtype, device=DEV), torch.tensor(d["cell"], dtype=dtype, device=DEV),
+            torch.tensor(d["pbc"], dtype=dtype, device=DEV))
+
+
+@pytest.mark.parametrize("case", SF_CASES)
+@pytest.mark.parametrize("tag,dtype", [("f64", torch.float64), ("f32", torch.float32)])
+def test_pair_sets_bit_exact(case, tag, dtype):
+    from nnmd_b200.neighbor import build_neighbor_list
+    d, _ = load_case(case)
+    cart, cell, pbc = _inputs(d, dtype)
+    nl = build_neighbor_list(cart, cell, pbc, float(d["rc_pairs"]))
+    got = nl.pairs().cpu().numpy()
+    ref = d[f"pairs_{tag}"].astype(np.int64)
+    assert got.shape == ref.shape, (got.shape, ref.shape, float(d[f"pairs_margin_{tag}"]))
+    assert (got == ref).all()
+    assert nl.total == ref.shape[0]
+    # rows ascending, counts consistent
+    cnt = nl.counts().cpu().numpy().reshape(-1)
+    assert cnt.sum() == ref.shape[0] and cnt.max() == nl.max_row
+
+
+@pytest.mark.parametrize("case", SF_CASES)
+def test_wrap_matches_reference_arithmetic(case):
+    from nnmd_b200.neighbor import wrap_positions
+    from oracle import dense_oracle as O2
+    d, _ = load_case(case)
+    for dtype, tol in ((torch.float64, 1e-14), (torch.float32, 2e-6)):
+        cart, cell, pbc = _inputs(d, dtype)
+        got = wrap_positions(cart, cell, pbc)[:, :3].cpu().view_as(cart)
+        ref = O2.wrap_positions(cart.cpu(), cell.cpu(), pbc.cpu())
+        assert float((got - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("case", SF_CASES)
+def test_descriptors_fp64(case):
+    """fp64 mode: 1e-10 against the exact oracles, <= 5e-7 against the reference's complex64-limited angular columns."""
+    from nnmd_b200.features import calculate_sf
+    from oracle import nl_oracle as O3
+    d, sfd = load_case(case)
+    cart, cell, pbc = _inputs(d, torch.float64)
+    g, dg = calculate_sf(cart, cell, pbc, sfd, disable_tqdm=True)
+    assert g.shape == d["g_f64"].shape and dg.shape == d["dg_f64"].shape
+    assert g.dtype == torch.float64 and g.is_cuda and not g.requires_grad
+    g3, dg3 = O3.descriptors(cart.cpu(), cell.cpu(), pbc.cpu(), sfd)
+    assert relerr(g.cpu(), g3) < 1e-10
+    assert col_relerr(dg.cpu(), dg3, 2) < 1e-10
+    # against the reference's own output
+    assert relerr(g.cpu(), d["g_f64"]) < 5e-7
+    assert col_relerr(dg.cpu(), d["dg_f64"], 2) < 5e-7
+    rad = [i for i, k in enumerate(sfd["features"]) if k in (1, 2)]
+    if rad:
+        assert col_relerr(dg.cpu()[:, :, rad], d["dg_f64"][:, :, rad], 2) < 1e-10
+    if len(rad) == len(sfd["features"]):
+        assert relerr(g.cpu(), d["g_f64"]) < 1e-10
+
+
+@pytest.mark.parametrize("case", SF_CASES)
+def test_descriptors_fp32(case):
+    """fp32 mode against the reference run in fp32 and against the fp64 truth: 1e-5 relative."""
+    from nnmd_b200.features import calculate_sf
+    d, sfd = load_case(case)
+    cart, cell, pbc = _inputs(d, torch.float32)
+    g, dg = calculate_sf(cart, cell, pbc, sfd, disable_tqdm=True)
+    assert g.dtype == torch.float32
+    e_g_ref32, e_dg_ref32 = relerr(g.cpu(), d["g_f32"]), col_relerr(dg.cpu(), d["dg_f32"], 2)
+    e_g_true, e_dg_true = relerr(g.cpu(), d["g_f64"]), col_relerr(dg.cpu(), d["dg_f64"], 2)
+    print(f"{case}: fp32 g vs ref32 {e_g_ref32:.2e} vs fp64 {e_g_true:.2e}; dg vs ref32 {e_dg_ref32:.2e} vs fp64 {e_dg_true:.2e}")
+    assert e_g_true < 1e-5 and e_g_ref32 < 1e-5
+    # the reference's own fp32 gradients carry ~1e-5 of round-off (its autograd runs through fp32 complex pow)
+    assert e_dg_true < 1e-5
+    assert e_dg_ref32 < 3e-5
+
+
+def test_cpu_input_roundtrip_and_seed_side_effect():
+    from nnmd_b200.features import calculate_sf
+    d, sfd = load_case("sf_lj_trimer")
+    cart = torch.tensor(d["cart"], dtype=torch.float64)
+    g, dg = calculate_sf(cart, torch.tensor(d["cell"]), torch.tensor(d["pbc"]), sfd)
+    assert not g.is_cuda and relerr(g, d["g_f64"]) < 1e-10 and relerr(dg, d["dg_f64"]) < 1e-10
+    assert cart.requires_grad is False
+    a = torch.rand(3)
+    torch.manual_seed(42)
+    assert torch.equal(a, torch.rand(3))  # calculate_sf reseeds with 42 like calculate_sf.py:115
+
+
+def test_isolated_atom_raises_like_reference():
+    from nnmd_b200.features import calculate_sf
+    cart = torch.tensor([[[0.0, 0, 0], [1.0, 0, 0], [50.0, 0, 0]]], dtype=torch.float64, device=DEV)
+    z = torch.zeros(3, 3, dtype=torch.float64, device=DEV)
+    with pytest.raises(ValueError, match="NaN values in the symmetry functions"):
+        calculate_sf(cart, z, torch.zeros(3, dtype=torch.float64, device=DEV), {"features": [1], "params": [[3.0]]})
+
+
+def test_unknown_function_and_bad_arity():
+    from nnmd_b200.features import calculate_sf
+    cart = torch.rand(1, 4, 3, device=DEV)
+    z = torch.zeros(3, 3, device=DEV)
+    with pytest.raises(ValueError):
+        calculate_sf(cart, z, torch.zeros(3, device=DEV), {"features": [3], "params": [[3.0, 1]]})
+    with pytest.raises(TypeError):
+        calculate_sf(cart, z, torch.zeros(3, device=DEV), {"features": [2], "params": [[3.0, 1.0]]})
+
+
+def test_general_lambda_and_many_functions():
+    """lambda outside {+1,-1} takes the general record path; > 32 functions per group takes FPL 2/4."""
+    from nnmd_b200.features import calculate_sf
+    from oracle import nl_oracle as O3
+    d, _ = load_case("sf_cluster")
+    cart, cell, pbc = _inputs(d, torch.float64)
+    rng = np.random.default_rng(5)
+    params = [[3.0, 0.1, float(z), float(l)] for z, l in zip(rng.uniform(1, 8, 70), rng.choice([1.0, -1.0], 70))]
+    params += [[2.8, 0.2, 2.0, 0.5], [2.8, 0.2, 3.5, -0.7], [3.0, 0.1, 1.0, -1.0]]
+    feats = [4] * 40 + [5] * 30 + [4, 5, 4]
+    sfd = {"features": feats, "params": params}
+    g, dg = calculate_sf(cart, cell, pbc, sfd)
+    g3, dg3 = O3.descriptors(cart.cpu(), cell.cpu(), pbc.cpu(), sfd)
+    assert relerr(g.cpu(), g3) < 1e-10
+    assert col_relerr(dg.cpu(), dg3, 2) < 1e-10
+    g32, dg32 = calculate_sf(cart.float(), cell.float(), pbc.float(), sfd)
+    assert relerr(g32.cpu(), g3) < 1e-5
+    assert col_relerr(dg32.cpu(), dg3, 2) < 2e-5
+
+
+@pytest.mark.parametrize("dtype,tol_e,tol_f", [(torch.float64, 1e-10, 1e-10), (torch.float32, 1e-5, 1e-4)])
+def test_mlp_energy_force_against_reference(dtype, tol_e, tol_f):
+    """K6 + K4c against quantities the reference computed (tests/golden/train_step.npz)."""
+    import os
+    from helpers import GOLDEN
+    from nnmd_b200.engine import force_contract
+    from nnmd_b200.nn import AtomicNN
+    from oracle import dense_oracle as O2
+    d = np.load(os.path.join(GOLDEN, "train_step.npz"))
+    F = d["g"].shape[-1]
+    net = AtomicNN(F, [int(v) for v in d["cfg_hidden"]]).to(DEV)
+    net.load_state_dict({k[3:]: torch.tensor(d[k]) for k in d.files if k.startswith("w0_")})
+    g = torch.tensor(d["g"], dtype=dtype, device=DEV)
+    dg = torch.tensor(d["dg"], dtype=dtype, device=DEV)
+    e, dE = net.energy_and_grad(g)
+    f = force_contract(dE, dg)
+    if dtype == torch.float64:  # fp64 truth from the oracle with the same (fp32-valued) inputs
+        Ws = [torch.tensor(d[f"w0_model.{i}.weight"], dtype=dtype) for i in range(3)]
+        bs = [torch.tensor(d[f"w0_model.{i}.bias"], dtype=dtype) for i in range(3)]
+        e_o, dE_o, f_o = O2.energy_force(g.cpu(), dg.cpu(), Ws, bs)
+        assert relerr(e.cpu(), e_o) < tol_e and relerr(dE.cpu(), dE_o) < tol_e and relerr(f.cpu(), f_o) < tol_f
+    assert relerr(e.cpu(), d["e_atoms"]) < 1e-5
+    assert relerr(dE.cpu(), d["dE"]) < 2e-5
+    assert float((f.cpu() - torch.tensor(d["f_nn"])).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["materialize", "fused"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_engine_energy_forces(mode, dtype):
+    """positions -> E, F through K0..K6 in both data flows against the oracle chain."""
+    from nnmd_b200.engine import energy_forces
+    from nnmd_b200.nn import AtomicNN
+    from oracle import dense_oracle as O2
+    from oracle import nl_oracle as O3
+    d, sfd = load_case("sf_fcc108")
+    cart, cell, pbc = _inputs(d, dtype)
+    torch.manual_seed(4)
+    net = AtomicNN(len(sfd["features"]), [24, 12]).to(DEV)
+    res = energy_forces(cart, cell, pbc, sfd, net, mode=mode)
+    g3, dg3 = O3.descriptors(cart.double().cpu(), cell.double().cpu(), pbc.double().cpu(), sfd)
+    Ws = [m.weight.detach().double().cpu() for m in net.model]
+    bs = [m.bias.detach().double().cpu() for m in net.model]
+    e_o, dE_o, f_o = O2.energy_force(g3, dg3, Ws, bs)
+    tol_e, tol_f = (1e-10, 1e-10) if dtype == torch.float64 else (1e-5, 1e-4)
+    assert relerr(res.e_atoms.cpu(), e_o.squeeze(-1)) < tol_e
+    assert relerr(res.energy.cpu(), e_o.sum(dim=(1, 2))) < tol_e
+    ferr = float((res.forces.cpu().double() - f_o).abs().max())
+    assert ferr < tol_f * max(1.0, float(f_o.abs().max())), ferr
+
+
+def test_large_cell_properties():
+    """Sizes the dense oracle cannot reach: translation invariance of dG, fused == materialised forces,
+    neighbour counts of the bulk fcc shell structure, and agreement with the O(N) C oracle on a sample."""
+    from nnmd_b200.engine import energy_forces
+    from nnmd_b200.features import calculate_params
+    from nnmd_b200.features.calculate_sf import get_plan, raw_descriptors
+    from nnmd_b200.neighbor import build_neighbor_list
+    from nnmd_b200.nn import AtomicNN
+    from oracle import nl_oracle as O3
+    ncell, a = 12, 3.615
+    base = torch.tensor([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]], dtype=torch.float64)
+    grid = torch.stack(torch.meshgrid(*[torch.arange(ncell, dtype=torch.float64)] * 3, indexing="ij"), -1).reshape(-1, 1, 3)
+    gen = torch.Generator().manual_seed(0)
+    pos = ((grid + base).reshape(-1, 3) * a + 0.05 * torch.randn(4 * ncell**3, 3, generator=gen, dtype=torch.float64))
+    cell = torch.eye(3, dtype=torch.float64) * ncell * a
+    pbc = torch.ones(3, dtype=torch.float64)
+    ang = calculate_params(6.0, 0, 32, 0, 64, 0)[32:]
+    rad = [[6.0, 4.0, float(rs)] for rs in np.linspace(0.5, 5.5, 32)]
+    sfd = {"features": [2] * 32 + [4] * 64, "params": rad + ang}
+    cart = pos[None].to(DEV)
+    nl = build_neighbor_list(cart, cell.to(DEV), pbc.to(DEV), 6.0)
+    cnt = nl.counts().cpu()
+    assert int(cnt.max()) <= 90 and int(cnt.median()) == 78          # bulk fcc: 78 neighbours inside 6 A
+    pairs = nl.pairs()
+    assert bool((pairs[:, 1] != pairs[:, 2]).all())
+    # symmetric pair set: (i,j) present <=> (j,i) present
+    key = pairs[:, 1] * nl.n_atoms + pairs[:, 2]
+    key_t = pairs[:, 2] * nl.n_atoms + pairs[:, 1]
+    assert torch.equal(torch.sort(key).values, torch.sort(key_t).values)
+    plan = get_plan(sfd, torch.float64, cart.device)
+    G, dG, flag = raw_descriptors(plan, nl)
+    assert int(flag.item()) == 0
+    # translation invariance of every function: sum_a dG[a,f,:] = 0
+    tot = dG.sum(dim=0).abs().max().item()
+    assert tot < 1e-9 * dG.abs().max().item() * dG.shape[0] ** 0.5
+    # O(N) CPU oracle on the same cell
+    G3, dG3, cnt3 = O3.raw_descriptors(pos[None], cell, pbc, sfd)
+    assert torch.equal(cnt3.reshape(-1).to(torch.int64), cnt.reshape(-1))
+    assert relerr(G.cpu(), G3[0]) < 1e-10 and col_relerr(dG.cpu(), dG3[0], 1) < 1e-10
+    # fused and materialised data flows agree
+    torch.manual_seed(1)
+    net = AtomicNN(96, [32, 16]).to(DEV)
+    r1 = energy_forces(cart.float(), cell.float().to(DEV), pbc.float().to(DEV), sfd, net, mode="materialize")
+    r2 = energy_forces(cart.float(), cell.float().to(DEV), pbc.float().to(DEV), sfd, net, mode="fused")
+    assert torch.equal(r1.e_atoms, r2.e_atoms)
+    assert float((r1.forces - r2.forces).abs().max()) < 1e-4 * max(1.0, float(r1.forces.abs().max()))
+    # fp32 descriptors of the bench table against the fp64 truth
+    G32, dG32, _ = raw_descriptors(get_plan(sfd, torch.float32, cart.device), build_neighbor_list(cart.float(), cell.float().to(DEV), pbc.float().to(DEV), 6.0))
+    print("bench-table fp32 errors:", relerr(G32.cpu(), G3[0]), col_relerr(dG32.cpu(), dG3[0], 1))
+    assert col_relerr(G32.cpu(), G3[0], 1) < 1e-5
+    assert col_relerr(dG32.cpu(), dG3[0], 1) < 2e-5
+
+
+def test_predict_api_shapes_and_values():
+    from nnmd_b200.nn import BPNN
+    from oracle import dense_oracle as O2
+    from oracle import nl_oracle as O3
+    d, sfd = load_case("sf_cu111_json")
+    net = BPNN(dtype=torch.float32)
+    torch.manual_seed(2)
+    net.config(dict(atom_species=["Cu"], input_sizes=[len(sfd["features"])], hidden_sizes=[[16, 8]], learning_rate=0.01,
+                    l2_regularization=0.0, e_loss_coeff=1.0, f_loss_coeff=1.0, load_models=False, path="",
+                    optimizer="adam", batch_size=2, epochs=1))
+    cart = torch.tensor(d["cart"], dtype=torch.float32)
+    cell = torch.tensor(d["cell"], dtype=torch.float32)
+    E, F = net.predict({"Cu": cart.clone()}, cell, {"Cu": sfd}, pbc=d["pbc"])
+    assert E.shape == (cart.shape[0],) and F.shape == cart.shape
+    g3, dg3 = O3.descriptors(cart.double(), cell.double(), torch.tensor(d["pbc"]), sfd)
+    Ws = [m.weight.detach().double().cpu() for m in net.atomic_nets[0].model]
+    bs = [m.bias.detach().double().cpu() for m in net.atomic_nets[0].model]
+    e_o, _, f_o = O2.energy_force(g3, dg3, Ws, bs)
+    assert relerr(E.cpu(), e_o.sum(dim=(1, 2))) < 1e-5
+    assert float((F.cpu().double() - f_o).abs().max()) < 1e-4
+    # single frame, 2-D input: scalar energy, (N,3) forces
+    E1, F1 = net.predict({"Cu": cart[0].clone()}, cell, {"Cu": sfd}, pbc=d["pbc"])
+    assert E1.dim() == 0 and F1.shape == cart[0].shape
