@@ -75,18 +75,29 @@ def test_descriptors_fp64(case):
 
 @pytest.mark.parametrize("case", SF_CASES)
 def test_descriptors_fp32(case):
-    """fp32 mode against the reference run in fp32 and against the fp64 truth: 1e-5 relative."""
+    """fp32 mode: 1e-5 relative against (a) the reference run in fp32 and (b) the fp64 truth evaluated on the SAME
+    fp32-wrapped positions.  (The fp64 fixture computed from fp64 inputs is not a fair fp32 target: the fp32 wrap
+    arithmetic pos @ inv(cell) @ cell alone moves dG by up to 5e-5 -- the reference's own fp32 run differs from its
+    fp64 run by that much; printed below for the record.)"""
     from nnmd_b200.features import calculate_sf
+    from nnmd_b200.neighbor import wrap_positions
+    from oracle import nl_oracle as O3
     d, sfd = load_case(case)
     cart, cell, pbc = _inputs(d, torch.float32)
     g, dg = calculate_sf(cart, cell, pbc, sfd, disable_tqdm=True)
     assert g.dtype == torch.float32
     e_g_ref32, e_dg_ref32 = relerr(g.cpu(), d["g_f32"]), col_relerr(dg.cpu(), d["dg_f32"], 2)
-    e_g_true, e_dg_true = relerr(g.cpu(), d["g_f64"]), col_relerr(dg.cpu(), d["dg_f64"], 2)
-    print(f"{case}: fp32 g vs ref32 {e_g_ref32:.2e} vs fp64 {e_g_true:.2e}; dg vs ref32 {e_dg_ref32:.2e} vs fp64 {e_dg_true:.2e}")
+    posw = wrap_positions(cart, cell, pbc)[:, :3].cpu().double().view(cart.shape)
+    z3 = torch.zeros(3, 3, dtype=torch.float64)
+    g_t, dg_t = O3.descriptors(posw, z3, torch.zeros(3, dtype=torch.float64), sfd)
+    e_g_true, e_dg_true = relerr(g.cpu(), g_t), col_relerr(dg.cpu(), dg_t, 2)
+    print(f"{case}: fp32 g vs ref32 {e_g_ref32:.2e} vs fp64-on-same-positions {e_g_true:.2e}; dg vs ref32 {e_dg_ref32:.2e} "
+          f"vs fp64-on-same-positions {e_dg_true:.2e}; (vs fp64 fixture: g {relerr(g.cpu(), d['g_f64']):.2e} "
+          f"dg {col_relerr(dg.cpu(), d['dg_f64'], 2):.2e})")
     assert e_g_true < 1e-5 and e_g_ref32 < 1e-5
-    # the reference's own fp32 gradients carry ~1e-5 of round-off (its autograd runs through fp32 complex pow)
     assert e_dg_true < 1e-5
+    # two fp32 runs whose wrapped positions differ by an ulp (torch matmul vs K0): the ill-conditioned columns of the
+    # auto-parameter set (SURVEY Q10) move by more than either run's own error
     assert e_dg_ref32 < 3e-5
 
 
@@ -212,7 +223,7 @@ def test_large_cell_properties():
     cart = pos[None].to(DEV)
     nl = build_neighbor_list(cart, cell.to(DEV), pbc.to(DEV), 6.0)
     cnt = nl.counts().cpu()
-    assert int(cnt.max()) <= 90 and int(cnt.median()) == 78          # bulk fcc: 78 neighbours inside 6 A
+    assert int(cnt.max()) <= 90 and int(torch.mode(cnt.reshape(-1)).values) == 78  # bulk fcc: 78 neighbours inside 6 A
     pairs = nl.pairs()
     assert bool((pairs[:, 1] != pairs[:, 2]).all())
     # symmetric pair set: (i,j) present <=> (j,i) present
@@ -236,11 +247,18 @@ def test_large_cell_properties():
     r2 = energy_forces(cart.float(), cell.float().to(DEV), pbc.float().to(DEV), sfd, net, mode="fused")
     assert torch.equal(r1.e_atoms, r2.e_atoms)
     assert float((r1.forces - r2.forces).abs().max()) < 1e-4 * max(1.0, float(r1.forces.abs().max()))
-    # fp32 descriptors of the bench table against the fp64 truth
-    G32, dG32, _ = raw_descriptors(get_plan(sfd, torch.float32, cart.device), build_neighbor_list(cart.float(), cell.float().to(DEV), pbc.float().to(DEV), 6.0))
-    print("bench-table fp32 errors:", relerr(G32.cpu(), G3[0]), col_relerr(dG32.cpu(), dG3[0], 1))
-    assert col_relerr(G32.cpu(), G3[0], 1) < 1e-5
-    assert col_relerr(dG32.cpu(), dG3[0], 1) < 2e-5
+    # fp32 descriptors of the bench table against the fp64 truth ON THE SAME fp32-wrapped positions (at 43 A a float
+    # position carries 4e-6 A of rounding, which the eta=4 Gaussians amplify to 1e-4 relative: conditioning of the
+    # fp32 input, shared with the reference's own fp32 mode, not kernel error)
+    nl32 = build_neighbor_list(cart.float(), cell.float().to(DEV), pbc.float().to(DEV), 6.0)
+    G32, dG32, _ = raw_descriptors(get_plan(sfd, torch.float32, cart.device), nl32)
+    p32 = nl32.posw[:, :3].double().cpu()[None]
+    z3 = torch.zeros(3, 3, dtype=torch.float64)
+    G3s, dG3s, _ = O3.raw_descriptors(p32, z3, torch.zeros(3, dtype=torch.float64), sfd)
+    eg, edg = col_relerr(G32.cpu(), G3s[0], 1), col_relerr(dG32.cpu(), dG3s[0], 1)
+    print("bench-table fp32 column errors: G", eg, "dG", edg, "(vs fp64 inputs:", relerr(G32.cpu(), G3[0]), ")")
+    assert eg < 1e-5
+    assert edg < 1e-5
 
 
 def test_predict_api_shapes_and_values():
@@ -263,6 +281,8 @@ def test_predict_api_shapes_and_values():
     e_o, _, f_o = O2.energy_force(g3, dg3, Ws, bs)
     assert relerr(E.cpu(), e_o.sum(dim=(1, 2))) < 1e-5
     assert float((F.cpu().double() - f_o).abs().max()) < 1e-4
-    # single frame, 2-D input: scalar energy, (N,3) forces
+    # single frame, 2-D input: the reference squeezes the batch axis BEFORE the network (bpnn.py:532-533), so
+    # e_nn.sum(1).squeeze() is the per-atom energy vector (nnmd/md/calculator.py:69 sums it) and F is (N,3)
     E1, F1 = net.predict({"Cu": cart[0].clone()}, cell, {"Cu": sfd}, pbc=d["pbc"])
-    assert E1.dim() == 0 and F1.shape == cart[0].shape
+    assert E1.shape == (cart.shape[1],) and F1.shape == cart[0].shape
+    assert abs(float(E1.sum() - E[0])) < 1e-4 * abs(float(E[0])) and torch.allclose(F1, F[0], atol=1e-6)
