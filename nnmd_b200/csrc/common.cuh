@@ -81,6 +81,10 @@ template <> struct M<float> {
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
         return r;
     }
+    // SFU forms used once per triangle in the fp32 kernels (each within a few ulp; error budget in DESIGN.md)
+    static __device__ __forceinline__ float rsqrt_fast(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float cospi_fast(float x) { return __cosf(x * 3.14159265358979323846f); }
+    static __device__ __forceinline__ float exp_fast(float x) { return exp2_fast(x * 1.4426950408889634f); }
     static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
     static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
@@ -97,6 +101,9 @@ template <> struct M<double> {
     static __device__ __forceinline__ double log2_(double x) { return log2(x); }
     static __device__ __forceinline__ double exp2_fast(double x) { return exp2(x); }
     static __device__ __forceinline__ double log2_fast(double x) { return log2(x); }
+    static __device__ __forceinline__ double rsqrt_fast(double x) { return 1.0 / sqrt(x); }
+    static __device__ __forceinline__ double cospi_fast(double x) { return cospi(x); }
+    static __device__ __forceinline__ double exp_fast(double x) { return exp(x); }
     static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
     static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }

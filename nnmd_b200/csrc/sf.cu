@@ -121,21 +121,41 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
     return NNMD_OK;
 }
 
+template <typename T>
+__device__ __forceinline__ void st4(T *p, T a, T b, T c, T d);
+template <> __device__ __forceinline__ void st4<float>(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void st4<double>(double *p, double a, double b, double c, double d) {
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(c, d);
+}
+template <typename T> struct Q4 { T a, b, c, d; };
+template <typename T> __device__ __forceinline__ Q4<T> ld4(const T *p);
+template <> __device__ __forceinline__ Q4<float> ld4<float>(const float *p) {
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    return {v.x, v.y, v.z, v.w};
+}
+template <> __device__ __forceinline__ Q4<double> ld4<double>(const double *p) {
+    const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
+    return {u.x, u.y, v.x, v.y};
+}
+
 // =============================================================================================
 // shared-memory staging of one neighbour row (phase 0, used by K2 and K3)
 // =============================================================================================
+// Per neighbour: u4 = (ux, uy, uz, d) as one 16 B (fp32) / 32 B (fp64) entry, then 1/d, fc, fc', psi, psi' as SoA.
 template <typename T>
 struct NbView {
-    T *ux, *uy, *uz, *d, *invd, *fc, *dfc, *psi, *dpsi;
+    T *u4, *invd, *fc, *dfc, *psi, *dpsi;
     __device__ __forceinline__ void bind(T *base, int cap) {
-        ux = base; uy = ux + cap; uz = uy + cap; d = uz + cap; invd = d + cap;
-        fc = invd + cap; dfc = fc + cap; psi = dfc + cap; dpsi = psi + cap;
+        u4 = base; invd = u4 + 4 * cap; fc = invd + cap; dfc = fc + cap; psi = dfc + cap; dpsi = psi + cap;
     }
 };
 
-// Gathers the neighbours of centre `gi` that lie inside rc into shared memory; returns their number.
-// ANG: also stage fc, fc', psi, psi' for the group's (rc, eta).
-template <typename T, bool ANG>
+// Gathers the neighbours of a centre that lie inside rc into shared memory; returns their number.
+// FULL: also stage fc, fc', psi = exp(-eta d^2) fc, psi' for the given (rc, eta).
+template <typename T, bool FULL>
 __device__ __forceinline__ int stage_row(const T *__restrict__ posw, const int32_t *__restrict__ idx, int64_t o0,
                                          int64_t o1, T xa, T ya, T za, T rc, T inv_rc, T eta, NbView<T> nb, int cap) {
     const int lane = lane_id();
@@ -156,9 +176,9 @@ __device__ __forceinline__ int stage_row(const T *__restrict__ posw, const int32
         if (keep) {
             const int p = nn + __popc(m & ((1u << lane) - 1u));
             if (p < cap) {
-                nb.ux[p] = ux; nb.uy[p] = uy; nb.uz[p] = uz; nb.d[p] = d;
+                st4<T>(nb.u4 + 4 * p, ux, uy, uz, d);
                 nb.invd[p] = M<T>::rcp(d);
-                if (ANG) {
+                if (FULL) {
                     T s, c;
                     M<T>::sincospi_(d * inv_rc, &s, &c);
                     const T fc = T(0.5) * (c + T(1));
@@ -199,21 +219,25 @@ struct RadArgs {
     uint32_t *flag;
 };
 
-template <typename T, int MODE>
+// One warp per centre atom, lanes over radial functions, the staged row broadcast from shared memory.
+// UNI: every radial function has the same cutoff, so fc and fc' are staged once per neighbour and the
+// per-function work is one exponential and a handful of FMAs.
+template <typename T, int MODE, bool UNI>
 __global__ void __launch_bounds__(256) radial_kernel(RadArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    T *base = reinterpret_cast<T *>(smem_raw) + size_t(warp) * 5 * a.cap;
+    T *base = reinterpret_cast<T *>(smem_raw) + size_t(warp) * NB_FIELDS * a.cap;
     NbView<T> nb;
     nb.bind(base, a.cap);
+    const T inv_rc_max = M<T>::rcp(a.rc_max);
     bool bad = false;
     for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
         const int64_t frame = row / a.n_centres;
         const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
         T xa, ya, za;
         load_pos<T>(a.posw, gi, xa, ya, za);
-        const int nn = stage_row<T, false>(a.posw, a.idx, a.offsets[row], a.offsets[row + 1], xa, ya, za, a.rc_max,
-                                           T(0), T(0), nb, a.cap);
+        const int nn = stage_row<T, UNI>(a.posw, a.idx, a.offsets[row], a.offsets[row + 1], xa, ya, za, a.rc_max,
+                                         inv_rc_max, T(0), nb, a.cap);
         T fx = 0, fy = 0, fz = 0;  // MODE_FORCE partial sums
         for (int f0 = 0; f0 < a.n; f0 += 32) {
             const int f = f0 + lane;
@@ -223,23 +247,28 @@ __global__ void __launch_bounds__(256) radial_kernel(RadArgs<T> a) {
             T val = 0, gx = 0, gy = 0, gz = 0;
             if (act) {
                 for (int t = 0; t < nn; ++t) {
-                    const T d = nb.d[t];
-                    if (d < rc) {
+                    const Q4<T> u = ld4<T>(nb.u4 + 4 * t);
+                    const T d = u.d;
+                    T fc, dfc;
+                    if (UNI) {
+                        fc = nb.fc[t]; dfc = nb.dfc[t];
+                    } else {
+                        if (!(d < rc)) continue;
                         T s, c;
                         M<T>::sincospi_(d * inv_rc, &s, &c);
-                        const T fc = T(0.5) * (c + T(1));
-                        const T dfc = T(-0.5) * M<T>::pi() * inv_rc * s;
-                        const T dr = d - rs;
-                        const T ex = M<T>::exp_(-eta * dr * dr);  // G1: eta = 0 -> 1
-                        val += ex * fc;
-                        if (MODE != MODE_G) {
-                            const T dphi = ex * (dfc - T(2) * eta * dr * fc);
-                            // own-atom gradient plus the identical term inside every neighbour's G_j
-                            const T sc = T(-2) * dphi * nb.invd[t];
-                            gx = M<T>::fma_(sc, nb.ux[t], gx);
-                            gy = M<T>::fma_(sc, nb.uy[t], gy);
-                            gz = M<T>::fma_(sc, nb.uz[t], gz);
-                        }
+                        fc = T(0.5) * (c + T(1));
+                        dfc = T(-0.5) * M<T>::pi() * inv_rc * s;
+                    }
+                    const T dr = d - rs;
+                    const T ex = M<T>::exp_fast(-eta * dr * dr);  // G1: eta = 0 -> 1
+                    val = M<T>::fma_(ex, fc, val);
+                    if (MODE != MODE_G) {
+                        const T dphi = ex * (dfc - T(2) * eta * dr * fc);
+                        // own-atom gradient plus the identical term inside every neighbour's G_j
+                        const T sc = T(-2) * dphi * nb.invd[t];
+                        gx = M<T>::fma_(sc, u.a, gx);
+                        gy = M<T>::fma_(sc, u.b, gy);
+                        gz = M<T>::fma_(sc, u.c, gz);
                     }
                 }
                 const int col = a.col[f];
@@ -285,25 +314,15 @@ struct AngArgs {
     uint32_t *flag;
 };
 
-template <typename T>
-__device__ __forceinline__ void st4(T *p, T a, T b, T c, T d);
-template <> __device__ __forceinline__ void st4<float>(float *p, float a, float b, float c, float d) {
-    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
-}
-template <> __device__ __forceinline__ void st4<double>(double *p, double a, double b, double c, double d) {
-    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
-    *reinterpret_cast<double2 *>(p + 2) = make_double2(c, d);
-}
-template <typename T> struct Q4 { T a, b, c, d; };
-template <typename T> __device__ __forceinline__ Q4<T> ld4(const T *p);
-template <> __device__ __forceinline__ Q4<float> ld4<float>(const float *p) {
-    const float4 v = *reinterpret_cast<const float4 *>(p);
-    return {v.x, v.y, v.z, v.w};
-}
-template <> __device__ __forceinline__ Q4<double> ld4<double>(const double *p) {
-    const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
-    return {u.x, u.y, v.x, v.y};
-}
+// Triangle record (REC_STRIDE reals in shared memory), one block of 16 per lambda class (+ then -):
+//   [ L0  L1  L2  V0 | A0x A0y B0x B0y | A1x A1y B1x B1y | A2x A2y B2x B2y ]
+//   L_X = log2(1 +- |c_X|), V0 = (1 +- |c_0|) E_0, A_X = +-sgn(c_X) E_X dc_X/d(x,y), B_X = (1 +- |c_X|) dE_X/d(x,y)
+// so that for a function (zeta, lambda = +-1), with q_X = 2^((zeta-1) L_X):
+//   G += q_0 V0 ;  dS/dx = sum_X q_X (zeta A_Xx + B_Xx) ;  dS/dy likewise
+// tail at REC_TAIL: [ ujx ukx ujy uky | ujz ukz . . ] unit vectors towards j and k, interleaved so that
+// (dS/dx, dS/dy) * (uj_c, uk_c) is one packed FMA per component.
+// General lambda: block 0 holds [ |c_0| |c_1| |c_2| E_0 | sgn E dc pairs, dE pairs ] and the lane finishes base, log, lambda.
+constexpr int RL = 0, RV = 3, RA = 4;  // field offsets inside a class block: L_X at RL+X, V0 at RV, centre X quad at RA+4X
 
 // cosine at a centre with adjacent sides (p, q), opposite side r (squares given), thresholds of symm_funcs.py:193-197
 template <typename T>
@@ -312,19 +331,20 @@ __device__ __forceinline__ T cos_law(T p2, T q2, T r2, T p, T q, T ip, T iq, boo
     return live ? (p2 + q2 - r2) * (T(0.5) * ip * iq) : T(0);
 }
 
-// phase 1: one lane reduces one closed triangle (tj < tk) to its record
+// phase 1: one lane reduces one closed triangle (tj < tk) to its record.
+// fp32 uses the SFU approximations (rsqrt, cos, ex2, lg2: each a few ulp, see DESIGN.md "fp32 error budget");
+// fp64 uses the accurate library routines.
 template <typename T, int MODE>
 __device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk, int kind, int pm1, T rc, T inv_rc, T eta,
                                             T *__restrict__ rec) {
-    const T x = nb.d[tj], y = nb.d[tk], ix = nb.invd[tj], iy = nb.invd[tk];
-    const T ujx = nb.ux[tj], ujy = nb.uy[tj], ujz = nb.uz[tj];
-    const T ukx = nb.ux[tk], uky = nb.uy[tk], ukz = nb.uz[tk];
-    const T wx = ujx - ukx, wy = ujy - uky, wz = ujz - ukz;
+    const Q4<T> uj = ld4<T>(nb.u4 + 4 * tj), uk = ld4<T>(nb.u4 + 4 * tk);
+    const T x = uj.d, y = uk.d, ix = nb.invd[tj], iy = nb.invd[tk];
+    const T wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
     const T z2 = wx * wx + wy * wy + wz * wz;
-    const T z = M<T>::sqrt_(z2), iz = M<T>::rcp(z);
+    const T iz = M<T>::rsqrt_fast(z2), z = z2 * iz;
     const T x2 = x * x, y2 = y * y;
-    const T fz = T(0.5) * (M<T>::cospi_(z * inv_rc) + T(1));
-    const T psz = M<T>::exp_(-eta * z2) * fz;
+    const T fz = T(0.5) * (M<T>::cospi_fast(z * inv_rc) + T(1));
+    const T psz = M<T>::exp_fast(-eta * z2) * fz;
     const T psx = nb.psi[tj], psy = nb.psi[tk], dpsx = nb.dpsi[tj], dpsy = nb.dpsi[tk];
 
     T c[3], dcx[3], dcy[3], E[3], Ex[3], Ey[3];
@@ -346,7 +366,6 @@ __device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk,
         E[1] = psx * psz * fcy;  Ex[1] = dpsx * psz * fcy;  Ey[1] = psx * psz * dfcy;
         E[2] = psy * psz * fcx;  Ex[2] = psy * psz * dfcx;  Ey[2] = dpsy * psz * fcx;
     }
-    // class blocks: [L0 Ax0 Bx0 Ay0 | By0 L1 Ax1 Bx1 | Ay1 By1 L2 Ax2 | Bx2 Ay2 By2 V0]
     T blk[2][REC_CLASS];
 #pragma unroll
     for (int X = 0; X < 3; ++X) {
@@ -357,18 +376,24 @@ __device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk,
         const T ex = on ? Ex[X] : T(0), ey = on ? Ey[X] : T(0);
         if (pm1) {
             const T bp = T(1) + ac, bm = M<T>::max_(T(1) - ac, T(0));
-            const T lp = on ? M<T>::log2_(bp) : T(0);
-            const T lm = on ? M<T>::max_(M<T>::log2_(bm), -M<T>::big()) : T(0);
-            blk[0][5 * X + 0] = lp;  blk[0][5 * X + 1] = ax;   blk[0][5 * X + 2] = bp * ex;
-            blk[0][5 * X + 3] = ay;  blk[0][5 * X + 4] = bp * ey;
-            blk[1][5 * X + 0] = lm;  blk[1][5 * X + 1] = -ax;  blk[1][5 * X + 2] = bm * ex;
-            blk[1][5 * X + 3] = -ay; blk[1][5 * X + 4] = bm * ey;
-            if (X == 0) { blk[0][15] = on ? bp * E[0] : T(0); blk[1][15] = on ? bm * E[0] : T(0); }
+            blk[0][RL + X] = on ? M<T>::log2_fast(bp) : T(0);
+            blk[1][RL + X] = on ? M<T>::max_(M<T>::log2_fast(bm), -M<T>::big()) : T(0);
+            blk[0][RA + 4 * X + 0] = ax;       blk[0][RA + 4 * X + 1] = ay;
+            blk[0][RA + 4 * X + 2] = bp * ex;  blk[0][RA + 4 * X + 3] = bp * ey;
+            blk[1][RA + 4 * X + 0] = -ax;      blk[1][RA + 4 * X + 1] = -ay;
+            blk[1][RA + 4 * X + 2] = bm * ex;  blk[1][RA + 4 * X + 3] = bm * ey;
+            if (X == 0) { blk[0][RV] = on ? bp * E[0] : T(0); blk[1][RV] = on ? bm * E[0] : T(0); }
         } else {  // general lambda: the lane finishes base, log and the lambda factors itself
-            blk[0][5 * X + 0] = on ? ac : T(0);  blk[0][5 * X + 1] = ax;  blk[0][5 * X + 2] = ex;
-            blk[0][5 * X + 3] = ay;              blk[0][5 * X + 4] = ey;
-            if (X == 0) blk[0][15] = on ? E[0] : T(0);
+            blk[0][RL + X] = on ? ac : T(0);
+            blk[0][RA + 4 * X + 0] = ax;  blk[0][RA + 4 * X + 1] = ay;
+            blk[0][RA + 4 * X + 2] = ex;  blk[0][RA + 4 * X + 3] = ey;
+            if (X == 0) blk[0][RV] = on ? E[0] : T(0);
         }
+    }
+    if (MODE == MODE_G) {
+        st4<T>(rec, blk[0][0], blk[0][1], blk[0][2], blk[0][3]);
+        if (pm1) st4<T>(rec + REC_CLASS, blk[1][0], blk[1][1], blk[1][2], blk[1][3]);
+        return;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) st4<T>(rec + 4 * q, blk[0][4 * q], blk[0][4 * q + 1], blk[0][4 * q + 2], blk[0][4 * q + 3]);
@@ -377,9 +402,117 @@ __device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk,
         for (int q = 0; q < 4; ++q)
             st4<T>(rec + REC_CLASS + 4 * q, blk[1][4 * q], blk[1][4 * q + 1], blk[1][4 * q + 2], blk[1][4 * q + 3]);
     }
-    if (MODE != MODE_G) {
-        st4<T>(rec + REC_TAIL, ujx * ix, ujy * ix, ujz * ix, ukx * iy);
-        st4<T>(rec + REC_TAIL + 4, uky * iy, ukz * iy, T(0), T(0));
+    st4<T>(rec + REC_TAIL, uj.a * ix, uk.a * iy, uj.b * ix, uk.b * iy);
+    st4<T>(rec + REC_TAIL + 4, uj.c * ix, uk.c * iy, T(0), T(0));
+}
+
+// Per-lane accumulators of phase 2.  g*[i] hold the (towards-j, towards-k) partial sums of one component.
+template <typename T, int FPL>
+struct AngAcc {
+    T val[FPL];
+    T gxa[FPL], gxb[FPL], gya[FPL], gyb[FPL], gza[FPL], gzb[FPL];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < FPL; ++i) val[i] = gxa[i] = gxb[i] = gya[i] = gyb[i] = gza[i] = gzb[i] = T(0);
+    }
+};
+
+// phase 2, generic arithmetic (fp64, and fp32 with a general lambda)
+template <typename T, int FPL, int MODE>
+__device__ __forceinline__ void phase2_generic(const T *__restrict__ recs, int cnt, int grp, int ngrp, int cls_off, int pm1,
+                                               const T (&zeta)[FPL], const T (&zm1)[FPL], const T (&lam)[FPL],
+                                               AngAcc<T, FPL> &acc) {
+    for (int t = grp; t < cnt; t += ngrp) {
+        const T *r = recs + t * REC_STRIDE + cls_off;
+        const Q4<T> l = ld4<T>(r);
+        Q4<T> c0{0, 0, 0, 0}, c1{0, 0, 0, 0}, c2{0, 0, 0, 0}, ua{0, 0, 0, 0}, ub{0, 0, 0, 0};
+        if (MODE != MODE_G) {
+            c0 = ld4<T>(r + RA); c1 = ld4<T>(r + RA + 4); c2 = ld4<T>(r + RA + 8);
+            ua = ld4<T>(recs + t * REC_STRIDE + REC_TAIL);
+            ub = ld4<T>(recs + t * REC_STRIDE + REC_TAIL + 4);
+        }
+#pragma unroll
+        for (int i = 0; i < FPL; ++i) {
+            T L0 = l.a, L1 = l.b, L2 = l.c, V0 = l.d;
+            T A0x = c0.a, A0y = c0.b, B0x = c0.c, B0y = c0.d;
+            T A1x = c1.a, A1y = c1.b, B1x = c1.c, B1y = c1.d;
+            T A2x = c2.a, A2y = c2.b, B2x = c2.c, B2y = c2.d;
+            if (!pm1) {  // record holds |c|, sgn E dc, dE: finish base, log and the lambda factors here
+                const T lm = lam[i];
+                const T b0 = M<T>::max_(M<T>::fma_(lm, L0, T(1)), T(0));
+                const T b1 = M<T>::max_(M<T>::fma_(lm, L1, T(1)), T(0));
+                const T b2 = M<T>::max_(M<T>::fma_(lm, L2, T(1)), T(0));
+                L0 = M<T>::max_(M<T>::log2_fast(b0), -M<T>::big());
+                L1 = M<T>::max_(M<T>::log2_fast(b1), -M<T>::big());
+                L2 = M<T>::max_(M<T>::log2_fast(b2), -M<T>::big());
+                A0x *= lm; A0y *= lm; A1x *= lm; A1y *= lm; A2x *= lm; A2y *= lm;
+                B0x *= b0; B0y *= b0; B1x *= b1; B1y *= b1; B2x *= b2; B2y *= b2;
+                V0 *= b0;
+            }
+            const T q0 = M<T>::exp2_fast(zm1[i] * L0);
+            acc.val[i] = M<T>::fma_(q0, V0, acc.val[i]);
+            if (MODE != MODE_G) {
+                const T q1 = M<T>::exp2_fast(zm1[i] * L1);
+                const T q2 = M<T>::exp2_fast(zm1[i] * L2);
+                const T zt = zeta[i];
+                T sa = q0 * M<T>::fma_(zt, A0x, B0x);
+                T sb = q0 * M<T>::fma_(zt, A0y, B0y);
+                sa = M<T>::fma_(q1, M<T>::fma_(zt, A1x, B1x), sa);
+                sb = M<T>::fma_(q1, M<T>::fma_(zt, A1y, B1y), sb);
+                sa = M<T>::fma_(q2, M<T>::fma_(zt, A2x, B2x), sa);
+                sb = M<T>::fma_(q2, M<T>::fma_(zt, A2y, B2y), sb);
+                acc.gxa[i] = M<T>::fma_(sa, ua.a, acc.gxa[i]); acc.gxb[i] = M<T>::fma_(sb, ua.b, acc.gxb[i]);
+                acc.gya[i] = M<T>::fma_(sa, ua.c, acc.gya[i]); acc.gyb[i] = M<T>::fma_(sb, ua.d, acc.gyb[i]);
+                acc.gza[i] = M<T>::fma_(sa, ub.a, acc.gza[i]); acc.gzb[i] = M<T>::fma_(sb, ub.b, acc.gzb[i]);
+            }
+        }
+    }
+}
+
+// phase 2, fp32 with lambda = +-1: packed FP32 (fma.rn.f32x2, sm_100) on everything that comes in (x,y) pairs.
+// Per function and triangle: 2 issue slots for the three exponents, 3 ex2, 3 packed FMAs for zeta*A+B, 3 packed FMAs
+// for q*(...), 1 for the value, 3 packed FMAs for the direction vectors: 15 issue slots / 22 FMA-pipe cycles
+// (the scalar form needs 25 issue slots).
+template <int FPL, int MODE>
+__device__ __forceinline__ void phase2_packed(const float *__restrict__ recs, int cnt, int grp, int ngrp, int cls_off,
+                                              const float (&zeta)[FPL], const float (&zm1)[FPL], AngAcc<float, FPL> &acc) {
+    for (int t = grp; t < cnt; t += ngrp) {
+        const float *r = recs + t * REC_STRIDE + cls_off;
+        const float4 l = *reinterpret_cast<const float4 *>(r);
+        float4 c0, c1, c2, ua, ub;
+        if (MODE != MODE_G) {
+            c0 = *reinterpret_cast<const float4 *>(r + RA);
+            c1 = *reinterpret_cast<const float4 *>(r + RA + 4);
+            c2 = *reinterpret_cast<const float4 *>(r + RA + 8);
+            ua = *reinterpret_cast<const float4 *>(recs + t * REC_STRIDE + REC_TAIL);
+            ub = *reinterpret_cast<const float4 *>(recs + t * REC_STRIDE + REC_TAIL + 4);
+        }
+#pragma unroll
+        for (int i = 0; i < FPL; ++i) {
+            if (MODE == MODE_G) {
+                const float q0 = M<float>::exp2_fast(zm1[i] * l.x);
+                acc.val[i] = fmaf(q0, l.w, acc.val[i]);
+            } else {
+                const float2 zm = make_float2(zm1[i], zm1[i]), zz = make_float2(zeta[i], zeta[i]);
+                const float2 e01 = __fmul2_rn(zm, make_float2(l.x, l.y));
+                const float q0 = M<float>::exp2_fast(e01.x), q1 = M<float>::exp2_fast(e01.y);
+                const float q2 = M<float>::exp2_fast(zm1[i] * l.z);
+                const float2 t0 = __ffma2_rn(zz, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w));
+                const float2 t1 = __ffma2_rn(zz, make_float2(c1.x, c1.y), make_float2(c1.z, c1.w));
+                const float2 t2 = __ffma2_rn(zz, make_float2(c2.x, c2.y), make_float2(c2.z, c2.w));
+                acc.val[i] = fmaf(q0, l.w, acc.val[i]);
+                // FFMA2 takes a scalar register as a broadcast operand, so q_X * (t_Xx, t_Xy) is one instruction
+                float2 s = __fmul2_rn(make_float2(q0, q0), t0);
+                s = __ffma2_rn(make_float2(q1, q1), t1, s);
+                s = __ffma2_rn(make_float2(q2, q2), t2, s);
+                float2 gx = make_float2(acc.gxa[i], acc.gxb[i]), gy = make_float2(acc.gya[i], acc.gyb[i]),
+                       gz = make_float2(acc.gza[i], acc.gzb[i]);
+                gx = __ffma2_rn(s, make_float2(ua.x, ua.y), gx);
+                gy = __ffma2_rn(s, make_float2(ua.z, ua.w), gy);
+                gz = __ffma2_rn(s, make_float2(ub.x, ub.y), gz);
+                acc.gxa[i] = gx.x; acc.gxb[i] = gx.y; acc.gya[i] = gy.x; acc.gyb[i] = gy.y; acc.gza[i] = gz.x; acc.gzb[i] = gz.y;
+            }
+        }
     }
 }
 
@@ -396,7 +529,7 @@ __global__ void __launch_bounds__(128) angular_kernel(AngArgs<T> a) {
     int *queue = reinterpret_cast<int *>(recs + ANG_BATCH * REC_STRIDE + size_t(NB_FIELDS) * a.cap);
 
     const int G = a.lanes, grp = lane >> a.log_lanes, fl = lane & (G - 1), ngrp = 32 >> a.log_lanes;
-    const T inv_rc = M<T>::rcp(a.rc);
+    const T inv_rc = M<T>::rcp(a.rc), rc2 = a.rc * a.rc;
     // this lane's functions
     T zeta[FPL], zm1[FPL], lam[FPL], coef[FPL];
     int col[FPL];
@@ -415,81 +548,41 @@ __global__ void __launch_bounds__(128) angular_kernel(AngArgs<T> a) {
         load_pos<T>(a.posw, gi, xa, ya, za);
         const int nn = stage_row<T, true>(a.posw, a.idx, a.offsets[row], a.offsets[row + 1], xa, ya, za, a.rc, inv_rc,
                                           a.eta, nb, a.cap);
-        T val[FPL], gx[FPL], gy[FPL], gz[FPL];
-#pragma unroll
-        for (int i = 0; i < FPL; ++i) val[i] = gx[i] = gy[i] = gz[i] = T(0);
+        AngAcc<T, FPL> acc;
+        acc.clear();
 
         int head = 0, qn = 0;  // ring buffer of closed (tj,tk) pairs, warp-uniform
         // process `cnt` queued triangles: phase 1 (records) then phase 2 (functions)
         auto flush = [&](int cnt) {
+            __syncwarp();
             if (lane < cnt) {
                 const int pk = queue[(head + lane) & 63];
                 make_record<T, MODE>(nb, pk & 0xffff, pk >> 16, a.kind, a.pm1, a.rc, inv_rc, a.eta, recs + lane * REC_STRIDE);
             }
             __syncwarp();
-            for (int t = grp; t < cnt; t += ngrp) {
-                const T *r = recs + t * REC_STRIDE + cls_off;
-                const Q4<T> r0 = ld4<T>(r), r1 = (MODE != MODE_G) ? ld4<T>(r + 4) : Q4<T>{0, 0, 0, 0},
-                            r2 = (MODE != MODE_G) ? ld4<T>(r + 8) : Q4<T>{0, 0, 0, 0}, r3 = ld4<T>(r + 12);
-                Q4<T> u0{0, 0, 0, 0}, u1{0, 0, 0, 0};
-                if (MODE != MODE_G) {
-                    u0 = ld4<T>(recs + t * REC_STRIDE + REC_TAIL);
-                    u1 = ld4<T>(recs + t * REC_STRIDE + REC_TAIL + 4);
-                }
-                // fields: centre 0 (r0.a r0.b r0.c r0.d r1.a) centre 1 (r1.b r1.c r1.d r2.a r2.b) centre 2 (r2.c r2.d r3.a r3.b r3.c) V0 r3.d
-#pragma unroll
-                for (int i = 0; i < FPL; ++i) {
-                    T L0 = r0.a, A0x = r0.b, B0x = r0.c, A0y = r0.d, B0y = r1.a;
-                    T L1 = r1.b, A1x = r1.c, B1x = r1.d, A1y = r2.a, B1y = r2.b;
-                    T L2 = r2.c, A2x = r2.d, B2x = r3.a, A2y = r3.b, B2y = r3.c;
-                    T V0 = r3.d;
-                    if (!a.pm1) {  // general lambda: record holds |c|, sgn E dc, dE -- finish base/log here
-                        const T l = lam[i];
-                        const T b0 = M<T>::max_(M<T>::fma_(l, L0, T(1)), T(0));
-                        const T b1 = M<T>::max_(M<T>::fma_(l, L1, T(1)), T(0));
-                        const T b2 = M<T>::max_(M<T>::fma_(l, L2, T(1)), T(0));
-                        L0 = M<T>::max_(M<T>::log2_fast(b0), -M<T>::big());
-                        L1 = M<T>::max_(M<T>::log2_fast(b1), -M<T>::big());
-                        L2 = M<T>::max_(M<T>::log2_fast(b2), -M<T>::big());
-                        A0x *= l; A0y *= l; A1x *= l; A1y *= l; A2x *= l; A2y *= l;
-                        B0x *= b0; B0y *= b0; B1x *= b1; B1y *= b1; B2x *= b2; B2y *= b2;
-                        V0 *= b0;
-                    }
-                    const T q0 = M<T>::exp2_fast(zm1[i] * L0);
-                    val[i] = M<T>::fma_(q0, V0, val[i]);
-                    if (MODE != MODE_G) {
-                        const T q1 = M<T>::exp2_fast(zm1[i] * L1);
-                        const T q2 = M<T>::exp2_fast(zm1[i] * L2);
-                        const T zt = zeta[i];
-                        T sa = q0 * M<T>::fma_(zt, A0x, B0x);
-                        T sb = q0 * M<T>::fma_(zt, A0y, B0y);
-                        sa = M<T>::fma_(q1, M<T>::fma_(zt, A1x, B1x), sa);
-                        sb = M<T>::fma_(q1, M<T>::fma_(zt, A1y, B1y), sb);
-                        sa = M<T>::fma_(q2, M<T>::fma_(zt, A2x, B2x), sa);
-                        sb = M<T>::fma_(q2, M<T>::fma_(zt, A2y, B2y), sb);
-                        gx[i] = M<T>::fma_(sa, u0.a, gx[i]); gx[i] = M<T>::fma_(sb, u0.d, gx[i]);
-                        gy[i] = M<T>::fma_(sa, u0.b, gy[i]); gy[i] = M<T>::fma_(sb, u1.a, gy[i]);
-                        gz[i] = M<T>::fma_(sa, u0.c, gz[i]); gz[i] = M<T>::fma_(sb, u1.b, gz[i]);
-                    }
-                }
+            if constexpr (sizeof(T) == 4) {
+                if (a.pm1) phase2_packed<FPL, MODE>(recs, cnt, grp, ngrp, cls_off, zeta, zm1, acc);
+                else phase2_generic<T, FPL, MODE>(recs, cnt, grp, ngrp, cls_off, a.pm1, zeta, zm1, lam, acc);
+            } else {
+                phase2_generic<T, FPL, MODE>(recs, cnt, grp, ngrp, cls_off, a.pm1, zeta, zm1, lam, acc);
             }
             __syncwarp();
         };
 
         for (int tj = 0; tj + 1 < nn; ++tj) {
-            const T ujx = nb.ux[tj], ujy = nb.uy[tj], ujz = nb.uz[tj];
+            const Q4<T> uj = ld4<T>(nb.u4 + 4 * tj);
             for (int kb = tj + 1; kb < nn; kb += 32) {
                 const int tk = kb + lane;
                 bool ok = false;
                 if (tk < nn) {
-                    const T wx = ujx - nb.ux[tk], wy = ujy - nb.uy[tk], wz = ujz - nb.uz[tk];
-                    const T z = M<T>::sqrt_(wx * wx + wy * wy + wz * wz);
-                    ok = (z < a.rc) && (z > T(0));  // the third side of the triangle (symm_funcs.py:34-50)
+                    const Q4<T> uk = ld4<T>(nb.u4 + 4 * tk);
+                    const T wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
+                    const T z2 = wx * wx + wy * wy + wz * wz;
+                    ok = (z2 < rc2) && (z2 > T(0));  // the third side of the triangle (symm_funcs.py:34-50)
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 if (ok) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 63] = tj | (tk << 16);
                 qn += __popc(m);
-                __syncwarp();
                 if (qn >= ANG_BATCH) {
                     flush(ANG_BATCH);
                     head = (head + ANG_BATCH) & 63;
@@ -500,8 +593,10 @@ __global__ void __launch_bounds__(128) angular_kernel(AngArgs<T> a) {
         if (qn > 0) flush(qn);
 
         // combine the triangle groups, then lanes < G own their functions' totals
+        T val[FPL], gx[FPL], gy[FPL], gz[FPL];
 #pragma unroll
         for (int i = 0; i < FPL; ++i) {
+            val[i] = acc.val[i]; gx[i] = acc.gxa[i] + acc.gxb[i]; gy[i] = acc.gya[i] + acc.gyb[i]; gz[i] = acc.gza[i] + acc.gzb[i];
             for (int o = G; o < 32; o <<= 1) {
                 val[i] += __shfl_xor_sync(0xffffffffu, val[i], o);
                 if (MODE != MODE_G) {
@@ -592,21 +687,25 @@ __global__ void __launch_bounds__(256) contract_kernel(const T *__restrict__ dE,
 // =============================================================================================
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-template <typename T, int MODE>
-static int launch_radial(const nnmd_sf_plan *p, RadArgs<T> a, cudaStream_t st) {
+template <typename T, int MODE, bool UNI>
+static int launch_radial_t(RadArgs<T> a, cudaStream_t st) {
     int wpb = 8;
-    while (wpb > 1 && size_t(wpb) * 5 * a.cap * sizeof(T) > 160 * 1024) wpb >>= 1;
-    const size_t smem = size_t(wpb) * 5 * a.cap * sizeof(T);
+    while (wpb > 1 && size_t(wpb) * NB_FIELDS * a.cap * sizeof(T) > 160 * 1024) wpb >>= 1;
+    const size_t smem = size_t(wpb) * NB_FIELDS * a.cap * sizeof(T);
     if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "radial: neighbour row of %d entries exceeds shared memory", a.cap);
-    auto kern = radial_kernel<T, MODE>;
+    auto kern = radial_kernel<T, MODE, UNI>;
     NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int64_t blocks = (a.n_rows + wpb - 1) / wpb;
     blocks = std::min<int64_t>(blocks, int64_t(sm_count()) * 8);
     ProfScope prof(PROF_RADIAL, st);
     kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
     NNMD_LAUNCH_CHECK("radial_kernel");
-    (void)p;
     return NNMD_OK;
+}
+
+template <typename T, int MODE>
+static int launch_radial(const nnmd_sf_plan *p, RadArgs<T> a, cudaStream_t st) {
+    return p->rad.uniform_rc ? launch_radial_t<T, MODE, true>(a, st) : launch_radial_t<T, MODE, false>(a, st);
 }
 
 template <typename T, int FPL, int MODE>
@@ -709,6 +808,8 @@ extern "C" int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, cons
         }
     }
     p->rad.n = int(rcol.size());
+    p->rad.uniform_rc = 1;
+    for (double v : rrc) if (v != p->rad.rc_max) p->rad.uniform_rc = 0;
     int r = NNMD_OK;
     if (p->rad.n > 0) {
         if (!r) r = upload_real(dtype, rrc, &p->rad.d_rc);

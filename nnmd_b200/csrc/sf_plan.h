@@ -9,7 +9,7 @@ namespace nnmd {
 constexpr int ANG_MAX_FPL = 4;    // angular functions per lane (template values 1, 2, 4)
 constexpr int REC_STRIDE = 44;    // shared-memory record stride in reals (44 mod 32 = 12: conflict-free 16 B accesses)
 constexpr int REC_CLASS = 16;     // reals per lambda-class block
-constexpr int REC_TAIL = 32;      // offset of the unit vectors
+constexpr int REC_TAIL = 32;      // offset of the interleaved unit vectors
 constexpr int ANG_BATCH = 32;     // triangles staged per batch
 constexpr int NB_FIELDS = 9;      // per-neighbour staged reals: ux uy uz d 1/d fc fc' psi psi'
 
@@ -29,6 +29,7 @@ struct AngGroup {
 
 struct RadialTab {
     int n = 0;          // number of G1/G2 functions
+    int uniform_rc = 0; // every radial function has the same cutoff: fc is staged once per neighbour
     double rc_max = 0;
     void *d_rc = nullptr, *d_eta = nullptr, *d_rs = nullptr;  // working dtype; G1 rows carry eta = 0, rs = 0
     int *d_col = nullptr;
