@@ -74,6 +74,9 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = _build.LIB
+    override = os.environ.get("NNMD_B200_LIB")  # tuning / debugging: load a differently built library
+    if override:
+        path, build_if_missing = override, False
     if build_if_missing:
         try:
             path = _build.build()

@@ -24,6 +24,7 @@
 // The inner loop is bound by the FP32 FMA pipe and the SFU (ex2), not by HBM: see DESIGN.md.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <new>
 #include <tuple>
@@ -84,6 +85,10 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
         int fpl = 1;
         auto slots_for = [&](int l) { return int((plus.size() + l - 1) / l + (minus.size() + l - 1) / l); };
         while (fpl < ANG_MAX_FPL && slots_for(fpl) > 32) fpl <<= 1;
+        if (const char *env = getenv("NNMD_ANG_FPL")) {  // tuning knob: force more functions per lane
+            const int want = atoi(env);
+            while (fpl < want && fpl < ANG_MAX_FPL) fpl <<= 1;
+        }
         if (slots_for(fpl) > 32) return set_err(NNMD_ERR_INVALID, "internal: angular group does not fit a warp");
         AngGroup g;
         g.kind = kind; g.rc = rc; g.eta = eta; g.pm1 = pm1 ? 1 : 0; g.fpl = fpl;
@@ -110,6 +115,20 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
         };
         place(plus, 1.0);
         place(minus, -1.0);
+        // zeta ladder (what calculate_params emits): when every lane's two functions are separated by the same
+        // step (to within the 6-decimal rounding of the table, <= 2e-6), the second power is the first one times
+        // 2^(step * L), and 2^(step * L) does not depend on the lane: it moves into the triangle record.
+        const char *no_ladder = getenv("NNMD_NO_LADDER");  // tuning knob
+        if (pm1 && fpl == 2 && !(no_ladder && no_ladder[0] == '1')) {
+            double sum = 0, lo = 1e300, hi = -1e300;
+            int n = 0;
+            for (int l = 0; l < g.lanes; ++l)
+                if (col[2 * l] >= 0 && col[2 * l + 1] >= 0) {
+                    const double d = zeta[2 * l + 1] - zeta[2 * l];
+                    sum += d; lo = std::min(lo, d); hi = std::max(hi, d); ++n;
+                }
+            if (n > 0 && hi - lo <= 2e-6) { g.ladder = 1; g.ladder_step = sum / n; }
+        }
         int r;
         if ((r = upload_real(dtype, zeta, &g.d_zeta))) return r;
         if ((r = upload_real(dtype, lam, &g.d_lam))) return r;
@@ -303,8 +322,8 @@ struct AngArgs {
     const int64_t *offsets;
     const int32_t *idx;
     int cap;
-    int kind, pm1, lanes, log_lanes;
-    T rc, eta;
+    int kind, pm1, lanes, log_lanes, ladder;
+    T rc, eta, step;
     const T *zeta, *lam, *coef;
     const int *col;
     int nf;
@@ -314,15 +333,15 @@ struct AngArgs {
     uint32_t *flag;
 };
 
-// Triangle record (REC_STRIDE reals in shared memory), one block of 16 per lambda class (+ then -):
-//   [ L0  L1  L2  V0 | A0x A0y B0x B0y | A1x A1y B1x B1y | A2x A2y B2x B2y ]
+// Triangle record (REC_STRIDE reals in shared memory), one block of REC_CLASS per lambda class (+ then -):
+//   [ L0  L1  L2  V0 | A0x A0y B0x B0y | A1x A1y B1x B1y | A2x A2y B2x B2y | R0 R1 R2 . ]   R_X = 2^(step L_X), ladder only
 //   L_X = log2(1 +- |c_X|), V0 = (1 +- |c_0|) E_0, A_X = +-sgn(c_X) E_X dc_X/d(x,y), B_X = (1 +- |c_X|) dE_X/d(x,y)
 // so that for a function (zeta, lambda = +-1), with q_X = 2^((zeta-1) L_X):
 //   G += q_0 V0 ;  dS/dx = sum_X q_X (zeta A_Xx + B_Xx) ;  dS/dy likewise
 // tail at REC_TAIL: [ ujx ukx ujy uky | ujz ukz . . ] unit vectors towards j and k, interleaved so that
 // (dS/dx, dS/dy) * (uj_c, uk_c) is one packed FMA per component.
 // General lambda: block 0 holds [ |c_0| |c_1| |c_2| E_0 | sgn E dc pairs, dE pairs ] and the lane finishes base, log, lambda.
-constexpr int RL = 0, RV = 3, RA = 4;  // field offsets inside a class block: L_X at RL+X, V0 at RV, centre X quad at RA+4X
+constexpr int RL = 0, RV = 3, RA = 4, RR = 16;  // offsets inside a class block: L_X at RL+X, V0 at RV, centre X quad at RA+4X, R_X at RR+X
 
 // cosine at a centre with adjacent sides (p, q), opposite side r (squares given), thresholds of symm_funcs.py:193-197
 template <typename T>
@@ -335,8 +354,8 @@ __device__ __forceinline__ T cos_law(T p2, T q2, T r2, T p, T q, T ip, T iq, boo
 // fp32 uses the SFU approximations (rsqrt, cos, ex2, lg2: each a few ulp, see DESIGN.md "fp32 error budget");
 // fp64 uses the accurate library routines.
 template <typename T, int MODE>
-__device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk, int kind, int pm1, T rc, T inv_rc, T eta,
-                                            T *__restrict__ rec) {
+__device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk, int kind, int pm1, int ladder, T step,
+                                            T rc, T inv_rc, T eta, T *__restrict__ rec) {
     const Q4<T> uj = ld4<T>(nb.u4 + 4 * tj), uk = ld4<T>(nb.u4 + 4 * tk);
     const T x = uj.d, y = uk.d, ix = nb.invd[tj], iy = nb.invd[tk];
     const T wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
@@ -367,6 +386,7 @@ __device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk,
         E[2] = psy * psz * fcx;  Ex[2] = psy * psz * dfcx;  Ey[2] = dpsy * psz * fcx;
     }
     T blk[2][REC_CLASS];
+    blk[0][RR + 3] = blk[1][RR + 3] = T(0);
 #pragma unroll
     for (int X = 0; X < 3; ++X) {
         const T ac = M<T>::abs_(c[X]);
@@ -378,6 +398,10 @@ __device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk,
             const T bp = T(1) + ac, bm = M<T>::max_(T(1) - ac, T(0));
             blk[0][RL + X] = on ? M<T>::log2_fast(bp) : T(0);
             blk[1][RL + X] = on ? M<T>::max_(M<T>::log2_fast(bm), -M<T>::big()) : T(0);
+            if (ladder) {
+                blk[0][RR + X] = M<T>::exp2_fast(step * blk[0][RL + X]);
+                blk[1][RR + X] = M<T>::exp2_fast(step * blk[1][RL + X]);
+            }
             blk[0][RA + 4 * X + 0] = ax;       blk[0][RA + 4 * X + 1] = ay;
             blk[0][RA + 4 * X + 2] = bp * ex;  blk[0][RA + 4 * X + 3] = bp * ey;
             blk[1][RA + 4 * X + 0] = -ax;      blk[1][RA + 4 * X + 1] = -ay;
@@ -389,6 +413,10 @@ __device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk,
             blk[0][RA + 4 * X + 2] = ex;  blk[0][RA + 4 * X + 3] = ey;
             if (X == 0) blk[0][RV] = on ? E[0] : T(0);
         }
+    }
+    if (ladder) {
+        st4<T>(rec + RR, blk[0][RR], blk[0][RR + 1], blk[0][RR + 2], T(0));
+        st4<T>(rec + REC_CLASS + RR, blk[1][RR], blk[1][RR + 1], blk[1][RR + 2], T(0));
     }
     if (MODE == MODE_G) {
         st4<T>(rec, blk[0][0], blk[0][1], blk[0][2], blk[0][3]);
@@ -516,8 +544,56 @@ __device__ __forceinline__ void phase2_packed(const float *__restrict__ recs, in
     }
 }
 
+#ifndef NNMD_ANG_MINB
+#define NNMD_ANG_MINB 4  // resident CTAs per SM the register allocation must allow
+#endif
+// phase 2, fp32, lambda = +-1, two functions per lane on a zeta ladder: the lane's second power is the first one
+// times the record's R_X = 2^(step L_X), so the SFU issues 3 ex2 per triangle instead of 6.
+template <int MODE>
+__device__ __forceinline__ void phase2_ladder(const float *__restrict__ recs, int cnt, int grp, int ngrp, int cls_off,
+                                              const float (&zeta)[2], const float (&zm1)[2], AngAcc<float, 2> &acc) {
+    for (int t = grp; t < cnt; t += ngrp) {
+        const float *r = recs + t * REC_STRIDE + cls_off;
+        const float4 l = *reinterpret_cast<const float4 *>(r);
+        const float4 rr = *reinterpret_cast<const float4 *>(r + RR);
+        const float2 zm = make_float2(zm1[0], zm1[0]);
+        const float2 e01 = __fmul2_rn(zm, make_float2(l.x, l.y));
+        float2 qa01, qb01;
+        qa01.x = M<float>::exp2_fast(e01.x); qa01.y = M<float>::exp2_fast(e01.y);
+        const float qa2 = M<float>::exp2_fast(zm1[0] * l.z);
+        qb01 = __fmul2_rn(qa01, make_float2(rr.x, rr.y));
+        const float qb2 = qa2 * rr.z;
+        acc.val[0] = fmaf(qa01.x, l.w, acc.val[0]);
+        acc.val[1] = fmaf(qb01.x, l.w, acc.val[1]);
+        if (MODE != MODE_G) {
+            const float4 c0 = *reinterpret_cast<const float4 *>(r + RA);
+            const float4 c1 = *reinterpret_cast<const float4 *>(r + RA + 4);
+            const float4 c2 = *reinterpret_cast<const float4 *>(r + RA + 8);
+            const float4 ua = *reinterpret_cast<const float4 *>(recs + t * REC_STRIDE + REC_TAIL);
+            const float4 ub = *reinterpret_cast<const float4 *>(recs + t * REC_STRIDE + REC_TAIL + 4);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float q0 = i ? qb01.x : qa01.x, q1 = i ? qb01.y : qa01.y, q2 = i ? qb2 : qa2;
+                const float2 zz = make_float2(zeta[i], zeta[i]);
+                const float2 t0 = __ffma2_rn(zz, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w));
+                const float2 t1 = __ffma2_rn(zz, make_float2(c1.x, c1.y), make_float2(c1.z, c1.w));
+                const float2 t2 = __ffma2_rn(zz, make_float2(c2.x, c2.y), make_float2(c2.z, c2.w));
+                float2 s = __fmul2_rn(make_float2(q0, q0), t0);
+                s = __ffma2_rn(make_float2(q1, q1), t1, s);
+                s = __ffma2_rn(make_float2(q2, q2), t2, s);
+                float2 gx = make_float2(acc.gxa[i], acc.gxb[i]), gy = make_float2(acc.gya[i], acc.gyb[i]),
+                       gz = make_float2(acc.gza[i], acc.gzb[i]);
+                gx = __ffma2_rn(s, make_float2(ua.x, ua.y), gx);
+                gy = __ffma2_rn(s, make_float2(ua.z, ua.w), gy);
+                gz = __ffma2_rn(s, make_float2(ub.x, ub.y), gz);
+                acc.gxa[i] = gx.x; acc.gxb[i] = gx.y; acc.gya[i] = gy.x; acc.gyb[i] = gy.y; acc.gza[i] = gz.x; acc.gzb[i] = gz.y;
+            }
+        }
+    }
+}
+
 template <typename T, int FPL, int MODE>
-__global__ void __launch_bounds__(128) angular_kernel(AngArgs<T> a) {
+__global__ void __launch_bounds__(128, NNMD_ANG_MINB) angular_kernel(AngArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     // per-warp shared memory: records | neighbour fields | pair queue
@@ -557,10 +633,14 @@ __global__ void __launch_bounds__(128) angular_kernel(AngArgs<T> a) {
             __syncwarp();
             if (lane < cnt) {
                 const int pk = queue[(head + lane) & 63];
-                make_record<T, MODE>(nb, pk & 0xffff, pk >> 16, a.kind, a.pm1, a.rc, inv_rc, a.eta, recs + lane * REC_STRIDE);
+                make_record<T, MODE>(nb, pk & 0xffff, pk >> 16, a.kind, a.pm1, a.ladder, a.step, a.rc, inv_rc, a.eta,
+                                     recs + lane * REC_STRIDE);
             }
             __syncwarp();
             if constexpr (sizeof(T) == 4) {
+                if constexpr (FPL == 2) {
+                    if (a.ladder) { phase2_ladder<MODE>(recs, cnt, grp, ngrp, cls_off, zeta, zm1, acc); __syncwarp(); return; }
+                }
                 if (a.pm1) phase2_packed<FPL, MODE>(recs, cnt, grp, ngrp, cls_off, zeta, zm1, acc);
                 else phase2_generic<T, FPL, MODE>(recs, cnt, grp, ngrp, cls_off, a.pm1, zeta, zm1, lam, acc);
             } else {
@@ -731,7 +811,8 @@ static int launch_angular_t(AngArgs<T> a, cudaStream_t st) {
 template <typename T, int MODE>
 static int launch_angular(const AngGroup &g, AngArgs<T> a, cudaStream_t st) {
     a.kind = g.kind; a.pm1 = g.pm1; a.lanes = g.lanes; a.log_lanes = ilog2(g.lanes);
-    a.rc = T(g.rc); a.eta = T(g.eta);
+    a.ladder = (g.ladder && sizeof(T) == 4) ? 1 : 0;
+    a.rc = T(g.rc); a.eta = T(g.eta); a.step = T(g.ladder_step);
     a.zeta = (const T *)g.d_zeta; a.lam = (const T *)g.d_lam; a.coef = (const T *)g.d_coef; a.col = g.d_col;
     switch (g.fpl) {
         case 1: return launch_angular_t<T, 1, MODE>(a, st);

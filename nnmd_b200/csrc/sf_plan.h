@@ -7,9 +7,9 @@
 namespace nnmd {
 
 constexpr int ANG_MAX_FPL = 4;    // angular functions per lane (template values 1, 2, 4)
-constexpr int REC_STRIDE = 44;    // shared-memory record stride in reals (44 mod 32 = 12: conflict-free 16 B accesses)
-constexpr int REC_CLASS = 16;     // reals per lambda-class block
-constexpr int REC_TAIL = 32;      // offset of the interleaved unit vectors
+constexpr int REC_STRIDE = 52;    // shared-memory record stride in reals (52 mod 32 = 20: conflict-free 16 B accesses)
+constexpr int REC_CLASS = 20;     // reals per lambda-class block
+constexpr int REC_TAIL = 40;      // offset of the interleaved unit vectors
 constexpr int ANG_BATCH = 32;     // triangles staged per batch
 constexpr int NB_FIELDS = 9;      // per-neighbour staged reals: ux uy uz d 1/d fc fc' psi psi'
 
@@ -21,6 +21,8 @@ struct AngGroup {
     int fpl;            // functions per lane
     int lanes;          // G: lanes per triangle (power of two <= 32)
     int n_slots;        // lanes * fpl table entries
+    int ladder = 0;     // fpl == 2 and every lane's two zetas differ by the same step: q_b = q_a * 2^(step * L)
+    double ladder_step = 0;
     // device tables in the working dtype, n_slots entries each (slot = lane*fpl + i); col = -1 marks padding
     void *d_zeta = nullptr, *d_lam = nullptr, *d_coef = nullptr;
     int *d_col = nullptr;

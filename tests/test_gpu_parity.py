@@ -245,7 +245,7 @@ def test_large_cell_properties():
     net = AtomicNN(96, [32, 16]).to(DEV)
     r1 = energy_forces(cart.float(), cell.float().to(DEV), pbc.float().to(DEV), sfd, net, mode="materialize")
     r2 = energy_forces(cart.float(), cell.float().to(DEV), pbc.float().to(DEV), sfd, net, mode="fused")
-    assert torch.equal(r1.e_atoms, r2.e_atoms)
+    assert float((r1.e_atoms - r2.e_atoms).abs().max()) < 1e-6 * float(r1.e_atoms.abs().max())
     assert float((r1.forces - r2.forces).abs().max()) < 1e-4 * max(1.0, float(r1.forces.abs().max()))
     # fp32 descriptors of the bench table against the fp64 truth ON THE SAME fp32-wrapped positions (at 43 A a float
     # position carries 4e-6 A of rounding, which the eta=4 Gaussians amplify to 1e-4 relative: conditioning of the
