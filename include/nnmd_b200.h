@@ -53,8 +53,8 @@ int nnmd_device_sm_count(void);
 
 /* Instrumentation for bench.py: number of kernel launches issued by this library so far, and optional
  * CUDA-event timing per kernel class on the launching stream (classes: 0 nlist, 1 radial, 2 angular,
- * 3 normalize, 4 contract, 5 mlp, 6 wrap).  nnmd_profile_read synchronises the device and resets. */
-#define NNMD_PROF_NCLASS 7
+ * 3 normalize, 4 contract, 5 mlp, 6 wrap, 7 edge gather).  nnmd_profile_read synchronises the device and resets. */
+#define NNMD_PROF_NCLASS 8
 long long nnmd_launch_count(void);
 int nnmd_profile_enable(int on);
 int nnmd_profile_read(double *ms, long long *count);
@@ -78,14 +78,16 @@ int nnmd_wrap_positions(int dtype, const void *pos, int64_t n_total, const doubl
  * n_centres atoms of each frame (n_centres < n_atoms only for spatial shards that carry halo atoms).
  *
  *   step 1  nnmd_nlist_workspace_bytes -> size of `ws` (dev scratch, owned by the caller)
- *   step 2  nnmd_nlist_count : bins atoms, counts neighbours, writes offsets (int64, n_rows+1)
- *           and stats = {total pairs, longest row} (int64[2], dev)
+ *   step 2  nnmd_nlist_count : bins atoms, counts neighbours, writes offsets (int64, n_rows+1),
+ *           edge_offsets (int64, n_rows+1, optional: prefix sums of the per-row number of neighbours with a LARGER
+ *           global index -- every unordered pair has exactly one such "owner" row; used by the edge-centric
+ *           angular kernel) and stats = {total pairs, longest row, total owned edges} (int64[3], dev)
  *   step 3  caller reads stats (the one host sync of the build), allocates idx (int32, total)
  *   step 4  nnmd_nlist_fill  : writes the sorted rows
  * ------------------------------------------------------------------------------------- */
 int64_t nnmd_nlist_workspace_bytes(int64_t n_frames, int64_t n_atoms);
 int nnmd_nlist_count(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
-                     void *ws, int64_t *offsets, int64_t *stats, void *stream);
+                     void *ws, int64_t *offsets, int64_t *edge_offsets, int64_t *stats, void *stream);
 int nnmd_nlist_fill(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
                     const void *ws, const int64_t *offsets, int64_t max_row, int32_t *idx, void *stream);
 
@@ -111,8 +113,13 @@ double nnmd_sf_plan_rc_max(const nnmd_sf_plan *plan);
  *   flag dev uint32, OR-ed with NNMD_FLAG_NAN_DG
  * ------------------------------------------------------------------------------------- */
 int nnmd_sf_eval(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
-                 const int64_t *offsets, const int32_t *idx, int64_t max_row, void *G, void *dG, uint32_t *flag,
-                 void *stream);
+                 const int64_t *offsets, const int32_t *idx, int64_t max_row, const int64_t *edge_offsets,
+                 int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes, void *G, void *dG, uint32_t *flag, void *stream);
+
+/* Edge scratch of the edge-centric angular kernel (fp32 plans whose angular groups fill a warp with 2 functions per
+ * lane): bytes needed for n_edges owned edges, 0 when the plan does not use it.  Pass edge_ws = NULL to
+ * nnmd_sf_eval / nnmd_sf_force to force the vertex-centric kernel (no scratch, about twice the arithmetic). */
+int64_t nnmd_sf_edge_scratch_bytes(const nnmd_sf_plan *plan, int64_t n_edges);
 
 /* K5  L2 normalisation over the feature axis + NaN guard   replaces calculate_sf.py:100-109
  *   ghat may alias G */
@@ -127,8 +134,9 @@ int nnmd_sf_normalize(int dtype, const void *G, int64_t n_rows, int nf, void *gh
  *          (extension, the reference has no virial: SURVEY Q8)
  * ------------------------------------------------------------------------------------- */
 int nnmd_sf_force(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
-                  const int64_t *offsets, const int32_t *idx, int64_t max_row, const void *w, void *force,
-                  void *virial, void *stream);
+                  const int64_t *offsets, const int32_t *idx, int64_t max_row, const int64_t *edge_offsets,
+                  int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes, const void *w, void *force, void *virial,
+                  void *stream);
 
 /* K4c  force contraction against a materialised dG      replaces bpnn.py:353  einsum("ijk,ijkl->ijl")
  *   force[a,:] = -sum_f dE[a,f] * dG[a,f,:] */

@@ -33,7 +33,7 @@ _SIGNATURES = {
                                            ctypes.c_void_p]),
     "nnmd_nlist_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int64]),
     "nnmd_nlist_count": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
-                                        ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p]),
     "nnmd_nlist_fill": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                        ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
@@ -43,12 +43,15 @@ _SIGNATURES = {
     "nnmd_sf_plan_destroy": (None, [ctypes.c_void_p]),
     "nnmd_sf_plan_rc_max": (ctypes.c_double, [ctypes.c_void_p]),
     "nnmd_sf_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
-                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "nnmd_sf_edge_scratch_bytes": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int64]),
     "nnmd_sf_normalize": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p]),
     "nnmd_sf_force": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
-                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p]),
     "nnmd_force_contract": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p]),
@@ -115,7 +118,7 @@ def dtype_code(dtype: torch.dtype) -> int:
     raise TypeError(f"nnmd_b200 computes in float32 or float64, got {dtype}")
 
 
-PROF_CLASSES = ("nlist", "radial", "angular", "normalize", "contract", "mlp", "wrap")
+PROF_CLASSES = ("nlist", "radial", "angular", "normalize", "contract", "mlp", "wrap", "gather")
 
 
 def profile_enable(on: bool) -> None:

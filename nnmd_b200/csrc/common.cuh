@@ -35,7 +35,7 @@ int sm_count();
 // ---- launch counter and optional per-kernel-class CUDA-event timing (bench.py's roofline leg) ----------
 extern std::atomic<long long> g_launches;
 enum ProfClass { PROF_NLIST = 0, PROF_RADIAL = 1, PROF_ANGULAR = 2, PROF_NORMALIZE = 3, PROF_CONTRACT = 4, PROF_MLP = 5,
-                 PROF_WRAP = 6, PROF_NCLASS = 7 };
+                 PROF_WRAP = 6, PROF_GATHER = 7, PROF_NCLASS = 8 };
 void prof_begin(int cls, cudaStream_t st);
 void prof_end(int cls, cudaStream_t st);
 struct ProfScope {
@@ -111,6 +111,16 @@ template <> struct M<double> {
     static __device__ __forceinline__ double big() { return 1e300; }
     static __device__ __forceinline__ double pi() { return 3.14159265358979323846; }
 };
+
+// |u| with a fixed operation order and no FMA contraction: every kernel that decides "is this neighbour inside the
+// cutoff" gets bit-identical answers (the edge-centric kernels rely on it).
+template <typename T> __device__ __forceinline__ T norm3(T x, T y, T z);
+template <> __device__ __forceinline__ float norm3<float>(float x, float y, float z) {
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+template <> __device__ __forceinline__ double norm3<double>(double x, double y, double z) {
+    return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+}
 
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

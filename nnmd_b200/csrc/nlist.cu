@@ -29,7 +29,7 @@ struct GridHdr {
 struct WsLayout {
     int64_t cap;          // cell slots reserved per frame
     int64_t ncells_total; // n_frames * cap
-    int64_t off_cell_start, off_cursor, off_cell_of, off_order, off_spos, off_counts, off_scan, total;
+    int64_t off_cell_start, off_cursor, off_cell_of, off_order, off_spos, off_counts, off_ecounts, off_scan, total;
 };
 
 static inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
@@ -50,6 +50,7 @@ static WsLayout ws_layout(int64_t n_frames, int64_t n_atoms, int64_t n_centres) 
     L.off_order = o;      o = align256(o + 4 * n_total);
     L.off_spos = o;       o = align256(o + 32 * n_total);  // sized for double4
     L.off_counts = o;     o = align256(o + 4 * (n_rows + 1));
+    L.off_ecounts = o;    o = align256(o + 4 * (n_rows + 1));
     const int64_t longest = (L.ncells_total > n_rows ? L.ncells_total : n_rows) + 1;
     L.off_scan = o;       o = align256(o + 8 * (longest / 2048 + 2));
     L.total = o;
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
                                                          const int *__restrict__ cell_of,
                                                          const int *__restrict__ cell_start,
                                                          const int *__restrict__ order, T rc, int *__restrict__ counts,
+                                                         int *__restrict__ ecounts,
                                                          const int64_t *__restrict__ offsets, int max_row,
                                                          int32_t *__restrict__ idx,
                                                          unsigned long long *__restrict__ stats) {
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
         const int cz = c % ncz, cy = (c / ncz) % ncy, cx = c / (ncz * ncy);
         const int z0 = max(cz - 1, 0), z1 = min(cz + 1, ncz - 1);
         const int64_t fbase = frame * cap;
-        int n_found = 0;
+        int n_found = 0, n_gt = 0;  // n_gt: neighbours with a larger global index ("owned edges" of this centre)
         for (int ix = max(cx - 1, 0); ix <= min(cx + 1, ncx - 1); ++ix) {
             for (int iy = max(cy - 1, 0); iy <= min(cy + 1, ncy - 1); ++iy) {
                 // the z-run of cells is contiguous in the cell-sorted arrays
@@ -370,6 +372,8 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
                             const int p = n_found + __popc(m & ((1u << lane) - 1u));
                             if (p < max_row) buf[p] = order[s];
                         }
+                    } else {
+                        n_gt += __popc(__ballot_sync(0xffffffffu, ok && int64_t(order[s]) > gi));
                     }
                     n_found += __popc(m);
                 }
@@ -378,6 +382,7 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
         if (!FILL) {
             if (lane == 0) {
                 counts[row] = n_found;
+                ecounts[row] = n_gt;
                 atomicMax(&stats[1], (unsigned long long)n_found);
             }
         } else {
@@ -438,7 +443,7 @@ extern "C" int nnmd_wrap_positions(int dtype, const void *pos, int64_t n_total, 
 
 template <typename T>
 static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc, char *ws,
-                            int64_t *offsets, int64_t *stats, cudaStream_t st) {
+                            int64_t *offsets, int64_t *edge_offsets, int64_t *stats, cudaStream_t st) {
     const WsLayout L = ws_layout(n_frames, n_atoms, n_centres);
     const int64_t n_total = n_frames * n_atoms, n_rows = n_frames * n_centres;
     GridHdr *h = (GridHdr *)ws;
@@ -448,11 +453,13 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
     int *order = (int *)(ws + L.off_order);
     T *spos = (T *)(ws + L.off_spos);
     int *counts = (int *)(ws + L.off_counts);
+    int *ecounts = (int *)(ws + L.off_ecounts);
     long long *scratch = (long long *)(ws + L.off_scan);
 
-    NNMD_CUDA_CHECK(cudaMemsetAsync(stats, 0, 2 * sizeof(int64_t), st));
+    NNMD_CUDA_CHECK(cudaMemsetAsync(stats, 0, 3 * sizeof(int64_t), st));
     if (n_rows == 0 || n_total == 0) {
         NNMD_CUDA_CHECK(cudaMemsetAsync(offsets, 0, (n_rows + 1) * sizeof(int64_t), st));
+        if (edge_offsets) NNMD_CUDA_CHECK(cudaMemsetAsync(edge_offsets, 0, (n_rows + 1) * sizeof(int64_t), st));
         return NNMD_OK;
     }
     const int sms = sm_count();
@@ -482,7 +489,7 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
         int64_t blocks = (n_rows + wpb - 1) / wpb;
         if (blocks > int64_t(sms) * 16) blocks = int64_t(sms) * 16;
         nlist_rows_kernel<T, false><<<unsigned(blocks), wpb * 32, 0, st>>>(
-            posw, spos, n_rows, n_atoms, n_centres, L.cap, h, cell_of, cell_start, order, T(rc), counts, nullptr, 0,
+            posw, spos, n_rows, n_atoms, n_centres, L.cap, h, cell_of, cell_start, order, T(rc), counts, ecounts, nullptr, 0,
             nullptr, (unsigned long long *)stats);
         NNMD_LAUNCH_CHECK("nlist_rows_kernel<count>");
     }
@@ -490,6 +497,11 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
     if (rcode) return rcode;
     // stats[0] = total = offsets[n_rows]
     NNMD_CUDA_CHECK(cudaMemcpyAsync(stats, offsets + n_rows, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    if (edge_offsets) {
+        rcode = exclusive_scan<int64_t>(ecounts, n_rows, edge_offsets, scratch, st);
+        if (rcode) return rcode;
+        NNMD_CUDA_CHECK(cudaMemcpyAsync(stats + 2, edge_offsets + n_rows, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    }
     return NNMD_OK;
 }
 
@@ -515,7 +527,7 @@ static int nlist_fill_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int
     if (blocks > int64_t(sms) * 16) blocks = int64_t(sms) * 16;
     ProfScope prof(PROF_NLIST, st);
     kern<<<unsigned(blocks), wpb * 32, smem, st>>>(posw, spos, n_rows, n_atoms, n_centres, L.cap, h, cell_of, cell_start,
-                                                   order, T(rc), nullptr, offsets, int(max_row), idx, nullptr);
+                                                   order, T(rc), nullptr, nullptr, offsets, int(max_row), idx, nullptr);
     NNMD_LAUNCH_CHECK("nlist_rows_kernel<fill>");
     return NNMD_OK;
 }
@@ -533,13 +545,13 @@ static int nlist_args_ok(int dtype, const void *posw, int64_t n_frames, int64_t 
 }
 
 extern "C" int nnmd_nlist_count(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
-                                double rc, void *ws, int64_t *offsets, int64_t *stats, void *stream) {
+                                double rc, void *ws, int64_t *offsets, int64_t *edge_offsets, int64_t *stats, void *stream) {
     int r = nlist_args_ok(dtype, posw, n_frames, n_atoms, n_centres, rc, ws);
     if (r) return r;
     if (!offsets || !stats) return set_err(NNMD_ERR_INVALID, "nlist_count: null output");
     if (dtype == NNMD_F32)
-        return nlist_count_impl<float>((const float *)posw, n_frames, n_atoms, n_centres, rc, (char *)ws, offsets, stats, (cudaStream_t)stream);
-    return nlist_count_impl<double>((const double *)posw, n_frames, n_atoms, n_centres, rc, (char *)ws, offsets, stats, (cudaStream_t)stream);
+        return nlist_count_impl<float>((const float *)posw, n_frames, n_atoms, n_centres, rc, (char *)ws, offsets, edge_offsets, stats, (cudaStream_t)stream);
+    return nlist_count_impl<double>((const double *)posw, n_frames, n_atoms, n_centres, rc, (char *)ws, offsets, edge_offsets, stats, (cudaStream_t)stream);
 }
 
 extern "C" int nnmd_nlist_fill(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,

@@ -129,6 +129,8 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
                 }
             if (n > 0 && hi - lo <= 2e-6) { g.ladder = 1; g.ladder_step = sum / n; }
         }
+        const char *no_edge = getenv("NNMD_NO_EDGE");  // tuning knob
+        g.edge_path = (dtype == NNMD_F32 && pm1 && fpl == 2 && g.lanes == 32 && !(no_edge && no_edge[0] == '1')) ? 1 : 0;
         int r;
         if ((r = upload_real(dtype, zeta, &g.d_zeta))) return r;
         if ((r = upload_real(dtype, lam, &g.d_lam))) return r;
@@ -167,16 +169,20 @@ template <> __device__ __forceinline__ Q4<double> ld4<double>(const double *p) {
 template <typename T>
 struct NbView {
     T *u4, *invd, *fc, *dfc, *psi, *dpsi;
+    int *epos;  // edge slot of the neighbour inside the centre's owned-edge range, or -1 when the neighbour owns the edge
     __device__ __forceinline__ void bind(T *base, int cap) {
         u4 = base; invd = u4 + 4 * cap; fc = invd + cap; dfc = fc + cap; psi = dfc + cap; dpsi = psi + cap;
+        epos = reinterpret_cast<int *>(dpsi + cap);
     }
 };
 
 // Gathers the neighbours of a centre that lie inside rc into shared memory; returns their number.
 // FULL: also stage fc, fc', psi = exp(-eta d^2) fc, psi' for the given (rc, eta).
+// first_gt >= 0: also record each kept neighbour's edge slot (row position - first_gt; negative = owned by the neighbour).
 template <typename T, bool FULL>
 __device__ __forceinline__ int stage_row(const T *__restrict__ posw, const int32_t *__restrict__ idx, int64_t o0,
-                                         int64_t o1, T xa, T ya, T za, T rc, T inv_rc, T eta, NbView<T> nb, int cap) {
+                                         int64_t o1, T xa, T ya, T za, T rc, T inv_rc, T eta, NbView<T> nb, int cap,
+                                         int first_gt = -1) {
     const int lane = lane_id();
     int nn = 0;
     for (int64_t base = o0; base < o1; base += 32) {
@@ -188,7 +194,7 @@ __device__ __forceinline__ int stage_row(const T *__restrict__ posw, const int32
             T xj, yj, zj;
             load_pos<T>(posw, j, xj, yj, zj);
             ux = xj - xa; uy = yj - ya; uz = zj - za;
-            d = M<T>::sqrt_(ux * ux + uy * uy + uz * uz);
+            d = norm3<T>(ux, uy, uz);
             keep = (d < rc) && (d > T(0));
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -197,6 +203,7 @@ __device__ __forceinline__ int stage_row(const T *__restrict__ posw, const int32
             if (p < cap) {
                 st4<T>(nb.u4 + 4 * p, ux, uy, uz, d);
                 nb.invd[p] = M<T>::rcp(d);
+                if (first_gt >= 0) nb.epos[p] = int(e - o0) - first_gt;
                 if (FULL) {
                     T s, c;
                     M<T>::sincospi_(d * inv_rc, &s, &c);
@@ -714,6 +721,8 @@ __global__ void __launch_bounds__(128, NNMD_ANG_MINB) angular_kernel(AngArgs<T> 
     if (MODE == MODE_DG && bad) atomicOr(a.flag, NNMD_FLAG_NAN_DG);
 }
 
+#include "sf_edge.cuh"
+
 // =============================================================================================
 // K5 normalise, K4c contraction
 // =============================================================================================
@@ -824,7 +833,8 @@ static int launch_angular(const AngGroup &g, AngArgs<T> a, cudaStream_t st) {
 
 template <typename T, int MODE>
 static int sf_run(const nnmd_sf_plan *p, const T *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
-                  const int64_t *offsets, const int32_t *idx, int64_t max_row, T *G, T *dG, const T *w, T *force,
+                  const int64_t *offsets, const int32_t *idx, int64_t max_row, const int64_t *edge_offsets,
+                  int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes, T *G, T *dG, const T *w, T *force,
                   uint32_t *flag, cudaStream_t st) {
     const int64_t n_rows = n_frames * n_centres;
     if (n_rows == 0) return NNMD_OK;
@@ -839,7 +849,23 @@ static int sf_run(const nnmd_sf_plan *p, const T *posw, int64_t n_frames, int64_
         int r = launch_radial<T, MODE>(p, a, st);
         if (r) return r;
     }
+    const bool edge_ok = edge_offsets && edge_ws && p->edge_slots > 0 &&
+                         edge_ws_bytes >= n_edges * 2 * int64_t(p->edge_slots) * int64_t(sizeof(float));
     for (const AngGroup &g : p->groups) {
+        if constexpr (sizeof(T) == 4) {
+            if (g.edge_path && edge_ok) {
+                EdgeArgs e;
+                e.posw = posw; e.n_rows = n_rows; e.n_atoms = n_atoms; e.n_centres = n_centres; e.offsets = offsets; e.idx = idx;
+                e.edge_offsets = edge_offsets; e.cap = cap; e.kind = g.kind; e.ladder = g.ladder;
+                e.rc = float(g.rc); e.eta = float(g.eta); e.step = float(g.ladder_step);
+                e.zeta = (const float *)g.d_zeta; e.lam = (const float *)g.d_lam; e.coef = (const float *)g.d_coef; e.col = g.d_col;
+                e.nf = p->nf; e.nfa = p->edge_slots; e.ebase = g.edge_base; e.E = (float *)edge_ws;
+                e.G = G; e.dG = dG; e.w = w; e.force = force; e.flag = flag;
+                int r = launch_edge<MODE>(g, e, st);
+                if (r) return r;
+                continue;
+            }
+        }
         AngArgs<T> a;
         a.posw = posw; a.n_rows = n_rows; a.n_atoms = n_atoms; a.n_centres = n_centres; a.offsets = offsets; a.idx = idx;
         a.cap = cap; a.nf = p->nf; a.G = G; a.dG = dG; a.w = w; a.force = force; a.flag = flag;
@@ -903,6 +929,8 @@ extern "C" int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, cons
         r = build_group(dtype, std::get<0>(key), std::get<1>(key), std::get<2>(key), groups[key], params, p->groups);
     }
     if (r) { nnmd_sf_plan_destroy(p); return r; }
+    for (AngGroup &g : p->groups)
+        if (g.edge_path) { g.edge_base = p->edge_slots; p->edge_slots += g.n_slots; }
     *out = p;
     return NNMD_OK;
 }
@@ -926,23 +954,30 @@ static int sf_args_ok(const nnmd_sf_plan *plan, const void *posw, int64_t n_fram
     return NNMD_OK;
 }
 
+extern "C" int64_t nnmd_sf_edge_scratch_bytes(const nnmd_sf_plan *plan, int64_t n_edges) {
+    if (!plan || n_edges < 0 || plan->dtype != NNMD_F32) return 0;
+    return n_edges * 2 * int64_t(plan->edge_slots) * int64_t(sizeof(float));
+}
+
 extern "C" int nnmd_sf_eval(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms,
-                            int64_t n_centres, const int64_t *offsets, const int32_t *idx, int64_t max_row, void *G,
+                            int64_t n_centres, const int64_t *offsets, const int32_t *idx, int64_t max_row,
+                            const int64_t *edge_offsets, int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes, void *G,
                             void *dG, uint32_t *flag, void *stream) {
     int r = sf_args_ok(plan, posw, n_frames, n_atoms, n_centres, offsets, idx, max_row);
     if (r) return r;
     if (n_frames * n_centres > 0 && (!G || !flag)) return set_err(NNMD_ERR_INVALID, "sf_eval: null output");
     cudaStream_t st = (cudaStream_t)stream;
     if (plan->dtype == NNMD_F32) {
-        if (dG) return sf_run<float, MODE_DG>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, (float *)G, (float *)dG, nullptr, nullptr, flag, st);
-        return sf_run<float, MODE_G>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, (float *)G, nullptr, nullptr, nullptr, flag, st);
+        if (dG) return sf_run<float, MODE_DG>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, edge_offsets, n_edges, edge_ws, edge_ws_bytes, (float *)G, (float *)dG, nullptr, nullptr, flag, st);
+        return sf_run<float, MODE_G>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, edge_offsets, n_edges, edge_ws, edge_ws_bytes, (float *)G, nullptr, nullptr, nullptr, flag, st);
     }
-    if (dG) return sf_run<double, MODE_DG>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, (double *)G, (double *)dG, nullptr, nullptr, flag, st);
-    return sf_run<double, MODE_G>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, (double *)G, nullptr, nullptr, nullptr, flag, st);
+    if (dG) return sf_run<double, MODE_DG>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, 0, nullptr, 0, (double *)G, (double *)dG, nullptr, nullptr, flag, st);
+    return sf_run<double, MODE_G>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, 0, nullptr, 0, (double *)G, nullptr, nullptr, nullptr, flag, st);
 }
 
 extern "C" int nnmd_sf_force(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms,
                              int64_t n_centres, const int64_t *offsets, const int32_t *idx, int64_t max_row,
+                             const int64_t *edge_offsets, int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes,
                              const void *w, void *force, void *virial, void *stream) {
     int r = sf_args_ok(plan, posw, n_frames, n_atoms, n_centres, offsets, idx, max_row);
     if (r) return r;
@@ -953,8 +988,8 @@ extern "C" int nnmd_sf_force(const nnmd_sf_plan *plan, const void *posw, int64_t
     const size_t es = plan->dtype == NNMD_F32 ? 4 : 8;
     if (n_rows > 0) NNMD_CUDA_CHECK(cudaMemsetAsync(force, 0, size_t(n_rows) * 3 * es, st));
     if (plan->dtype == NNMD_F32)
-        return sf_run<float, MODE_FORCE>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, nullptr, (const float *)w, (float *)force, nullptr, st);
-    return sf_run<double, MODE_FORCE>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, nullptr, (const double *)w, (double *)force, nullptr, st);
+        return sf_run<float, MODE_FORCE>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, edge_offsets, n_edges, edge_ws, edge_ws_bytes, nullptr, nullptr, (const float *)w, (float *)force, nullptr, st);
+    return sf_run<double, MODE_FORCE>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, 0, nullptr, 0, nullptr, nullptr, (const double *)w, (double *)force, nullptr, st);
 }
 
 extern "C" int nnmd_sf_normalize(int dtype, const void *G, int64_t n_rows, int nf, void *ghat, uint32_t *flag, void *stream) {

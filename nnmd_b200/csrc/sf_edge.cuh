@@ -1,0 +1,393 @@
+// sf_edge.cuh -- edge-centric form of the angular kernel K3 (fp32, lambda = +-1, 2 functions per lane on 32 lanes).
+// Included by sf.cu after the shared staging helpers.
+//
+// Why: with S_f(a,j,k) = sum over the three centres of P_f(c_X) E_X (one closed triangle),
+//     dG[a,f] = -coef_f sum_{j in N(a)} Phi_f(a,j) u_aj ,   Phi_f(a,j) = sum_{k closes (a,j)} dS_f(a,j,k) / d d_aj ,
+// and Phi_f(a,j) = Phi_f(j,a).  The vertex-centric kernel evaluates both derivatives (d/dx and d/dy) of every triangle
+// from each of its three vertices; here every unordered edge is evaluated ONCE, by the endpoint with the smaller
+// global index (its "owner"), for one derivative only: 11 FMA-pipe cycles per (edge, third atom, function) instead
+// of 22, no direction-vector work in the inner loop.  Phi goes to HBM as an edge array and a second, bandwidth-bound
+// kernel gathers it from both endpoints.  The value G_a needs the centre-a term of every ordered pair (j,k): the
+// owner accumulates it in registers for its own edges and hands the other endpoint its share (Gamma) through the
+// same edge array.  Still gather-only and atomic-free: the summation order is fixed.
+//
+// Edge scratch layout: E[edge][2][nfa] floats, edge = edge_offsets[row] + slot among the row's neighbours with a
+// larger global index (rows are ascending, so those are a suffix), [0] = Phi, [1] = Gamma (share of the NON-owner),
+// function axis in lane order (slot 2*lane, 2*lane+1 of the group at ebase).
+#pragma once
+// (included inside namespace nnmd)
+
+struct EdgeArgs {
+    const float *posw;
+    int64_t n_rows, n_atoms, n_centres;
+    const int64_t *offsets;
+    const int32_t *idx;
+    const int64_t *edge_offsets;
+    int cap;
+    int kind, ladder;
+    float rc, eta, step;
+    const float *zeta, *lam, *coef;
+    const int *col;
+    int nf;     // row stride of G / dG / w
+    int nfa;    // function-axis length of the edge scratch
+    int ebase;  // first slot of this group
+    float *E;
+    float *G, *dG;
+    const float *w;
+    float *force;
+    uint32_t *flag;
+};
+
+// record: per lambda class (EREC_CLASS floats)  [ L0 L1 L2 eid | A0 A1 B0 B1 | A2 B2 V0a V0j | R0 R1 R2 . ]
+template <bool WITH_PHI, bool LADDER>
+__device__ __forceinline__ void make_record_edge(const NbView<float> &nb, int tj, int tk, int kind, float step,
+                                                 float inv_rc, float eta, int eid, float *__restrict__ rec) {
+    using MF = M<float>;
+    const Q4<float> uj = ld4<float>(nb.u4 + 4 * tj), uk = ld4<float>(nb.u4 + 4 * tk);
+    const float x = uj.d, y = uk.d, ix = nb.invd[tj], iy = nb.invd[tk];
+    const float wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
+    const float z2 = wx * wx + wy * wy + wz * wz;
+    const float iz = MF::rsqrt_fast(z2), z = z2 * iz;
+    const float x2 = x * x, y2 = y * y;
+    const float fz = 0.5f * (MF::cospi_fast(z * inv_rc) + 1.f);
+    const float psz = MF::exp_fast(-eta * z2) * fz;
+    const float psx = nb.psi[tj], psy = nb.psi[tk], dpsx = nb.dpsi[tj];
+    float c[3], dcx[3], E[3], Ex[3];
+    bool live[3];
+    c[0] = cos_law<float>(x2, y2, z2, x, y, ix, iy, live[0]);  // centre a : sides x, y   opposite z
+    c[1] = cos_law<float>(x2, z2, y2, x, z, ix, iz, live[1]);  // centre j : sides x, z   opposite y
+    c[2] = cos_law<float>(y2, z2, x2, y, z, iy, iz, live[2]);  // centre k : sides y, z   opposite x
+    dcx[0] = live[0] ? iy - c[0] * ix : 0.f;
+    dcx[1] = live[1] ? iz - c[1] * ix : 0.f;
+    dcx[2] = live[2] ? -x * iy * iz : 0.f;
+    if (kind == NNMD_G4) {
+        E[0] = E[1] = E[2] = psx * psy * psz;
+        Ex[0] = Ex[1] = Ex[2] = dpsx * psy * psz;
+    } else {  // G5 keeps fc of the opposite side
+        const float fcx = nb.fc[tj], fcy = nb.fc[tk], dfcx = nb.dfc[tj];
+        E[0] = psx * psy * fz;   Ex[0] = dpsx * psy * fz;
+        E[1] = psx * psz * fcy;  Ex[1] = dpsx * psz * fcy;
+        E[2] = psy * psz * fcx;  Ex[2] = psy * psz * dfcx;
+    }
+    float L[2][3], A[3], B[2][3], V[2][2];
+#pragma unroll
+    for (int X = 0; X < 3; ++X) {
+        const float ac = fabsf(c[X]);
+        const bool on = ac > 1e-3f;  // symm_funcs.py:210-211
+        const float sg = c[X] > 0.f ? 1.f : -1.f;
+        const float bp = 1.f + ac, bm = fmaxf(1.f - ac, 0.f);
+        L[0][X] = on ? MF::log2_fast(bp) : 0.f;
+        L[1][X] = on ? fmaxf(MF::log2_fast(bm), -MF::big()) : 0.f;
+        A[X] = on ? sg * E[X] * dcx[X] : 0.f;
+        B[0][X] = on ? bp * Ex[X] : 0.f;
+        B[1][X] = on ? bm * Ex[X] : 0.f;
+        if (X < 2) { V[0][X] = on ? bp * E[X] : 0.f; V[1][X] = on ? bm * E[X] : 0.f; }
+    }
+    const float eb = __int_as_float(eid);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        float *r = rec + s * EREC_CLASS;
+        const float sgn = s ? -1.f : 1.f;
+        st4<float>(r, L[s][0], L[s][1], L[s][2], eb);
+        if (WITH_PHI) st4<float>(r + 4, sgn * A[0], sgn * A[1], B[s][0], B[s][1]);
+        st4<float>(r + 8, sgn * A[2], B[s][2], V[s][0], V[s][1]);
+        if (LADDER) st4<float>(r + 12, MF::exp2_fast(step * L[s][0]), MF::exp2_fast(step * L[s][1]), MF::exp2_fast(step * L[s][2]), 0.f);
+    }
+}
+
+// K3e: one warp per centre atom, lanes over functions (2 per lane), edges owned by the centre only.
+// LADDER: the lane's second power is the first one times the record's R_X (zeta ladder, see build_group).
+template <bool WITH_PHI, bool LADDER>
+__global__ void __launch_bounds__(128, 4) angular_edge_kernel(EdgeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using MF = M<float>;
+    const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t per_warp = size_t(ANG_BATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
+    unsigned char *wbase = smem_raw + per_warp * warp;
+    float *recs = reinterpret_cast<float *>(wbase);
+    NbView<float> nb;
+    nb.bind(recs + ANG_BATCH * EREC_STRIDE, a.cap);
+    int *queue = reinterpret_cast<int *>(recs + ANG_BATCH * EREC_STRIDE + size_t(NB_FIELDS) * a.cap);
+    int *queue_eid = queue + 64;
+
+    const float inv_rc = MF::rcp(a.rc), rc2 = a.rc * a.rc;
+    const float zeta0 = a.zeta[2 * lane], zeta1 = a.zeta[2 * lane + 1];
+    const float zm10 = zeta0 - 1.f, zm11 = zeta1 - 1.f;
+    const int col0 = a.col[2 * lane], col1 = a.col[2 * lane + 1];
+    const int class_off = (a.lam[2 * lane] < 0.f) ? EREC_CLASS : 0;  // lambda class of this lane's two functions
+    const size_t nfa = size_t(a.nfa);
+    const int kind = a.kind;
+    const float eta = a.eta, step = a.step;
+
+    for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
+        const int64_t frame = row / a.n_centres;
+        const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
+        float xa, ya, za;
+        load_pos<float>(a.posw, gi, xa, ya, za);
+        const int64_t o0 = a.offsets[row], o1 = a.offsets[row + 1];
+        const int64_t e0 = a.edge_offsets[row], e1 = a.edge_offsets[row + 1];
+        const int first_gt = int((o1 - o0) - (e1 - e0));
+        const int nn = stage_row<float, true>(a.posw, a.idx, o0, o1, xa, ya, za, a.rc, inv_rc, eta, nb, a.cap, first_gt);
+
+        // phi*: two partial sums of Phi per function; vg*: (centre-a value of the row, Gamma of the current edge)
+        float2 phi0 = make_float2(0.f, 0.f), phi1 = phi0, vg0 = phi0, vg1 = phi0;
+        int cur_eid = -1;
+        int head = 0, qn = 0;
+
+        // process `cnt` queued (edge, third atom) pairs: phase 1 (records, one per lane) then phase 2 (functions)
+        auto flush = [&](int cnt) {
+            __syncwarp();
+            bool is_first = false;
+            if (lane < cnt) {
+                const int pk = queue[(head + lane) & 63];
+                is_first = (pk >> 30) & 1;
+                const int eid = is_first ? queue_eid[(head + lane) & 63] : -1;
+                make_record_edge<WITH_PHI, LADDER>(nb, pk & 0x7fff, (pk >> 15) & 0x7fff, kind, step, inv_rc, eta, eid,
+                                                   recs + lane * EREC_STRIDE);
+            }
+            const unsigned firsts = __ballot_sync(0xffffffffu, is_first);
+            __syncwarp();
+            int t = 0;
+            while (t < cnt) {
+                if ((firsts >> t) & 1u) {  // record t opens the next edge: retire the previous one (warp-uniform)
+                    if (cur_eid >= 0) {
+                        float *dst = a.E + (size_t(cur_eid) * 2) * nfa + a.ebase + 2 * lane;
+                        if (WITH_PHI) *reinterpret_cast<float2 *>(dst) = make_float2(phi0.x + phi0.y, phi1.x + phi1.y);
+                        *reinterpret_cast<float2 *>(dst + nfa) = make_float2(vg0.y, vg1.y);
+                    }
+                    cur_eid = __float_as_int(recs[t * EREC_STRIDE + 3]);
+                    phi0 = make_float2(0.f, 0.f); phi1 = phi0; vg0.y = 0.f; vg1.y = 0.f;
+                }
+                const unsigned rest = t < 31 ? (firsts & ~((2u << t) - 1u)) : 0u;
+                const int t_end = rest ? min(__ffs(rest) - 1, cnt) : cnt;
+                const float *r = recs + t * EREC_STRIDE + class_off;
+#pragma unroll 2
+                for (; t < t_end; ++t, r += EREC_STRIDE) {
+                    const float4 l = *reinterpret_cast<const float4 *>(r);       // L0 L1 L2 .
+                    const float4 c2 = *reinterpret_cast<const float4 *>(r + 8);  // A2 B2 V0a V0j
+                    const float2 e01 = __fmul2_rn(make_float2(zm10, zm10), make_float2(l.x, l.y));
+                    float2 qa, qb;
+                    qa.x = MF::exp2_fast(e01.x); qa.y = MF::exp2_fast(e01.y);
+                    const float qa2 = MF::exp2_fast(zm10 * l.z);
+                    float qb2;
+                    if (LADDER) {
+                        const float4 rr = *reinterpret_cast<const float4 *>(r + 12);  // R0 R1 R2 .
+                        qb = __fmul2_rn(qa, make_float2(rr.x, rr.y));
+                        qb2 = qa2 * rr.z;
+                    } else {
+                        const float2 f01 = __fmul2_rn(make_float2(zm11, zm11), make_float2(l.x, l.y));
+                        qb.x = MF::exp2_fast(f01.x); qb.y = MF::exp2_fast(f01.y);
+                        qb2 = MF::exp2_fast(zm11 * l.z);
+                    }
+                    if (WITH_PHI) {
+                        const float4 c1 = *reinterpret_cast<const float4 *>(r + 4);  // A0 A1 B0 B1
+                        const float2 ta = __ffma2_rn(make_float2(zeta0, zeta0), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w));
+                        const float2 tb = __ffma2_rn(make_float2(zeta1, zeta1), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w));
+                        const float ta2 = fmaf(zeta0, c2.x, c2.y), tb2 = fmaf(zeta1, c2.x, c2.y);
+                        phi0 = __ffma2_rn(qa, ta, phi0);
+                        phi1 = __ffma2_rn(qb, tb, phi1);
+                        phi0.x = fmaf(qa2, ta2, phi0.x);
+                        phi1.x = fmaf(qb2, tb2, phi1.x);
+                    }
+                    vg0 = __ffma2_rn(qa, make_float2(c2.z, c2.w), vg0);
+                    vg1 = __ffma2_rn(qb, make_float2(c2.z, c2.w), vg1);
+                }
+            }
+            __syncwarp();
+        };
+
+        for (int tj = 0; tj < nn; ++tj) {
+            const int ep = nb.epos[tj];
+            if (ep < 0) continue;  // the neighbour owns this edge (warp-uniform)
+            const int eid = int(e0 + ep);
+            const Q4<float> uj = ld4<float>(nb.u4 + 4 * tj);
+            int pushed = 0;
+            for (int kb = 0; kb < nn; kb += 32) {
+                const int tk = kb + lane;
+                bool ok = false;
+                if (tk < nn && tk != tj) {
+                    const Q4<float> uk = ld4<float>(nb.u4 + 4 * tk);
+                    const float wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
+                    const float z2 = wx * wx + wy * wy + wz * wz;
+                    ok = (z2 < rc2) && (z2 > 0.f);  // the third side of the triangle (symm_funcs.py:34-50)
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const int before = __popc(m & ((1u << lane) - 1u));
+                    const int slot = (head + qn + before) & 63;
+                    const int first = (pushed == 0 && before == 0) ? 1 : 0;
+                    queue[slot] = tj | (tk << 15) | (first << 30);
+                    if (first) queue_eid[slot] = eid;
+                }
+                const int c = __popc(m);
+                pushed += c;
+                qn += c;
+                if (qn >= ANG_BATCH) {
+                    flush(ANG_BATCH);
+                    head = (head + ANG_BATCH) & 63;
+                    qn -= ANG_BATCH;
+                }
+            }
+            if (pushed == 0) {  // an edge that closes no triangle still owns a (zero) slot the gather will read
+                float *dst = a.E + (size_t(eid) * 2) * nfa + a.ebase + 2 * lane;
+                if (WITH_PHI) *reinterpret_cast<float2 *>(dst) = make_float2(0.f, 0.f);
+                *reinterpret_cast<float2 *>(dst + nfa) = make_float2(0.f, 0.f);
+            }
+        }
+        if (qn > 0) flush(qn);
+        if (cur_eid >= 0) {
+            float *dst = a.E + (size_t(cur_eid) * 2) * nfa + a.ebase + 2 * lane;
+            if (WITH_PHI) *reinterpret_cast<float2 *>(dst) = make_float2(phi0.x + phi0.y, phi1.x + phi1.y);
+            *reinterpret_cast<float2 *>(dst + nfa) = make_float2(vg0.y, vg1.y);
+        }
+        // the centre's own share of its value (raw sum; scaled and completed by the gather kernel)
+        if (a.G) {
+            if (col0 >= 0) a.G[row * a.nf + col0] = vg0.x;
+            if (col1 >= 0) a.G[row * a.nf + col1] = vg1.x;
+        }
+        __syncwarp();
+    }
+}
+
+// K4e: gather Phi (and Gamma) over all edges of a centre.  HBM-bound: 8 B per lane per edge, coalesced 256 B rows.
+template <int MODE>
+__global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float *ubuf = reinterpret_cast<float *>(smem_raw) + size_t(warp) * 4 * a.cap;  // (ux/d, uy/d, uz/d, edge id bits)
+    float coef[2];
+    int col[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { coef[i] = a.coef[2 * lane + i]; col[i] = a.col[2 * lane + i]; }
+    const size_t nfa = size_t(a.nfa);
+    bool bad = false;
+    for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
+        const int64_t frame = row / a.n_centres;
+        const int64_t fbase = frame * a.n_atoms;
+        const int64_t gi = fbase + (row - frame * a.n_centres);
+        float xa, ya, za;
+        load_pos<float>(a.posw, gi, xa, ya, za);
+        const int64_t o0 = a.offsets[row], o1 = a.offsets[row + 1];
+        const int64_t e0 = a.edge_offsets[row], e1 = a.edge_offsets[row + 1];
+        const int first_gt = int((o1 - o0) - (e1 - e0));
+        // stage unit vectors and edge ids of the neighbours inside this group's cutoff
+        int nn = 0;
+        for (int64_t base = o0; base < o1; base += 32) {
+            const int64_t e = base + lane;
+            bool keep = false;
+            float ux = 0, uy = 0, uz = 0, d = 0;
+            int j = 0;
+            if (e < o1) {
+                j = __ldg(a.idx + e);
+                float xj, yj, zj;
+                load_pos<float>(a.posw, j, xj, yj, zj);
+                ux = xj - xa; uy = yj - ya; uz = zj - za;
+                d = norm3<float>(ux, uy, uz);  // the same expression as stage_row: both kernels see the same edge set
+                keep = (d < a.rc) && (d > 0.f);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int p = nn + __popc(m & ((1u << lane) - 1u));
+                int code;
+                const int ep = int(e - o0) - first_gt;
+                if (ep >= 0) {
+                    code = int(e0 + ep);  // owned: non-negative edge id
+                } else {
+                    // the neighbour owns the edge: find this centre in its (ascending) row
+                    const int64_t rj = frame * a.n_centres + (int64_t(j) - fbase);
+                    const int64_t p0 = a.offsets[rj], p1 = a.offsets[rj + 1];
+                    int64_t lo = p0, hi = p1;
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if (int64_t(__ldg(a.idx + mid)) < gi) lo = mid + 1; else hi = mid;
+                    }
+                    const int64_t q0 = a.edge_offsets[rj], q1 = a.edge_offsets[rj + 1];
+                    const int64_t fg = (p1 - p0) - (q1 - q0);
+                    code = ~int(q0 + (lo - p0) - fg);  // bitwise complement marks "not the owner"
+                }
+                if (p < a.cap) {
+                    const float inv = 1.0f / d;
+                    *reinterpret_cast<float4 *>(ubuf + 4 * p) = make_float4(ux * inv, uy * inv, uz * inv, __int_as_float(code));
+                }
+            }
+            nn += __popc(m);
+        }
+        __syncwarp();
+        nn = min(nn, a.cap);
+        float gx[2] = {0, 0}, gy[2] = {0, 0}, gz[2] = {0, 0}, gam[2] = {0, 0};
+#pragma unroll 4
+        for (int t = 0; t < nn; ++t) {
+            const float4 u = *reinterpret_cast<const float4 *>(ubuf + 4 * t);
+            const int code = __float_as_int(u.w);
+            const bool owner = code >= 0;
+            const size_t eid = size_t(owner ? code : ~code);
+            const float *src = a.E + (eid * 2) * nfa + a.ebase + 2 * lane;
+            if (MODE != MODE_G) {
+                const float2 ph = __ldg(reinterpret_cast<const float2 *>(src));
+                gx[0] = fmaf(ph.x, u.x, gx[0]); gy[0] = fmaf(ph.x, u.y, gy[0]); gz[0] = fmaf(ph.x, u.z, gz[0]);
+                gx[1] = fmaf(ph.y, u.x, gx[1]); gy[1] = fmaf(ph.y, u.y, gy[1]); gz[1] = fmaf(ph.y, u.z, gz[1]);
+            }
+            if (MODE != MODE_FORCE && !owner) {
+                const float2 ga = __ldg(reinterpret_cast<const float2 *>(src + nfa));
+                gam[0] += ga.x; gam[1] += ga.y;
+            }
+        }
+        float fx = 0, fy = 0, fz = 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (col[i] < 0) continue;
+            const int64_t o = row * a.nf + col[i];
+            if (MODE != MODE_FORCE) a.G[o] = 0.5f * coef[i] * (a.G[o] + gam[i]);  // ordered (j,k): both edges of a pair counted
+            if (MODE == MODE_DG) {
+                const float dx = -coef[i] * gx[i], dy = -coef[i] * gy[i], dz = -coef[i] * gz[i];
+                a.dG[3 * o] = dx; a.dG[3 * o + 1] = dy; a.dG[3 * o + 2] = dz;
+                bad |= !(isfinite(dx) && isfinite(dy) && isfinite(dz));
+            }
+            if (MODE == MODE_FORCE) {
+                const float wv = a.w[o] * coef[i];
+                fx = fmaf(wv, gx[i], fx); fy = fmaf(wv, gy[i], fy); fz = fmaf(wv, gz[i], fz);
+            }
+        }
+        if (MODE == MODE_FORCE) {
+            fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+            if (lane == 0) { a.force[3 * row] += fx; a.force[3 * row + 1] += fy; a.force[3 * row + 2] += fz; }
+        }
+        __syncwarp();
+    }
+    if (MODE == MODE_DG && bad) atomicOr(a.flag, NNMD_FLAG_NAN_DG);
+}
+
+template <int MODE>
+static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
+    constexpr bool WITH_PHI = MODE != MODE_G;
+    {
+        const size_t per_warp = size_t(ANG_BATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
+        int wpb = 4;
+        while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+        const size_t smem = per_warp * wpb;
+        if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "angular: neighbour row of %d entries exceeds shared memory", a.cap);
+        auto kern = a.ladder ? angular_edge_kernel<WITH_PHI, true> : angular_edge_kernel<WITH_PHI, false>;
+        NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        int occ = 1;
+        NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+        if (occ < 1) occ = 1;
+        int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * occ);
+        ProfScope prof(PROF_ANGULAR, st);
+        kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
+        NNMD_LAUNCH_CHECK("angular_edge_kernel");
+    }
+    {
+        int wpb = 8;
+        while (wpb > 1 && size_t(wpb) * 16 * a.cap > 160 * 1024) wpb >>= 1;
+        const size_t smem = size_t(wpb) * 16 * a.cap;
+        auto kern = edge_gather_kernel<MODE>;
+        NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * 16);
+        ProfScope prof(PROF_GATHER, st);
+        kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
+        NNMD_LAUNCH_CHECK("edge_gather_kernel");
+    }
+    (void)g;
+    return NNMD_OK;
+}
+

@@ -11,7 +11,9 @@ constexpr int REC_STRIDE = 52;    // shared-memory record stride in reals (52 mo
 constexpr int REC_CLASS = 20;     // reals per lambda-class block
 constexpr int REC_TAIL = 40;      // offset of the interleaved unit vectors
 constexpr int ANG_BATCH = 32;     // triangles staged per batch
-constexpr int NB_FIELDS = 9;      // per-neighbour staged reals: ux uy uz d 1/d fc fc' psi psi'
+constexpr int NB_FIELDS = 10;     // per-neighbour staged reals: ux uy uz d 1/d fc fc' psi psi' + edge slot (int)
+constexpr int EREC_STRIDE = 36;   // edge-centric record stride (36 mod 32 = 4: conflict-free 16 B accesses)
+constexpr int EREC_CLASS = 16;
 
 // One launch of the angular kernel: functions that share (kind, rc, eta).
 struct AngGroup {
@@ -23,6 +25,8 @@ struct AngGroup {
     int n_slots;        // lanes * fpl table entries
     int ladder = 0;     // fpl == 2 and every lane's two zetas differ by the same step: q_b = q_a * 2^(step * L)
     double ladder_step = 0;
+    int edge_path = 0;  // fp32, lambda = +-1, 2 functions per lane on all 32 lanes: eligible for the edge-centric kernel
+    int edge_base = 0;  // first slot of this group on the function axis of the edge scratch
     // device tables in the working dtype, n_slots entries each (slot = lane*fpl + i); col = -1 marks padding
     void *d_zeta = nullptr, *d_lam = nullptr, *d_coef = nullptr;
     int *d_col = nullptr;
@@ -45,4 +49,5 @@ struct nnmd_sf_plan {
     double rc_max;
     nnmd::RadialTab rad;
     std::vector<nnmd::AngGroup> groups;
+    int edge_slots = 0;  // function-axis length of the edge scratch (sum of n_slots over edge-path groups)
 };

@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from .features.calculate_sf import SfPlan, get_plan, normalize, raise_on_flag, raw_descriptors
+from .features.calculate_sf import SfPlan, edge_scratch, get_plan, normalize, raise_on_flag, raw_descriptors
 from .neighbor import NeighborList, build_from_wrapped, wrap_positions
 
 
@@ -48,10 +48,12 @@ def fused_force(plan: SfPlan, nl: NeighborList, w: torch.Tensor) -> torch.Tensor
     lib = _lib.load()
     w2 = w.detach().reshape(-1, plan.nf).contiguous()
     out = torch.empty((nl.n_rows, 3), dtype=w.dtype, device=w.device)
+    ews = edge_scratch(plan, nl)
     with torch.cuda.device(w.device):
         _lib.check(lib.nnmd_sf_force(plan.handle, _lib.ptr(nl.posw), nl.n_frames, nl.n_atoms, nl.n_centres,
-                                     _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(w2), _lib.ptr(out),
-                                     None, _lib.stream_ptr()))
+                                     _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(nl.edge_offsets),
+                                     nl.n_edges, _lib.ptr(ews), 0 if ews is None else ews.numel(), _lib.ptr(w2),
+                                     _lib.ptr(out), None, _lib.stream_ptr()))
     return out
 
 

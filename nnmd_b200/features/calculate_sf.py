@@ -67,6 +67,20 @@ def get_plan(symm_funcs_data: dict, dtype: torch.dtype, device: torch.device) ->
     return plan
 
 
+def edge_scratch(plan: SfPlan, nl: NeighborList):
+    """Scratch for the edge-centric angular kernel (Phi/Gamma per owned edge), or None when the plan does not use it
+    or the buffer does not fit: the C side then runs the vertex-centric kernel (no scratch, ~2x the arithmetic)."""
+    if nl.edge_offsets is None or nl.n_edges == 0:
+        return None
+    need = int(_lib.load().nnmd_sf_edge_scratch_bytes(plan.handle, nl.n_edges))
+    if need == 0:
+        return None
+    try:
+        return torch.empty(need, dtype=torch.uint8, device=nl.posw.device)
+    except torch.cuda.OutOfMemoryError:
+        return None
+
+
 def raw_descriptors(plan: SfPlan, nl: NeighborList, with_grad: bool = True):
     """K2+K3(+K4a): un-normalised G (n_rows,F) and dG (n_rows,F,3) for the rows of `nl`, plus the device flag word."""
     lib = _lib.load()
@@ -75,10 +89,12 @@ def raw_descriptors(plan: SfPlan, nl: NeighborList, with_grad: bool = True):
     G = torch.empty((n_rows, plan.nf), dtype=plan.dtype, device=dev)
     dG = torch.empty((n_rows, plan.nf, 3), dtype=plan.dtype, device=dev) if with_grad else None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ews = edge_scratch(plan, nl)
     with torch.cuda.device(dev):
         _lib.check(lib.nnmd_sf_eval(plan.handle, _lib.ptr(nl.posw), nl.n_frames, nl.n_atoms, nl.n_centres,
-                                    _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(G), _lib.ptr(dG),
-                                    _lib.ptr(flag), _lib.stream_ptr()))
+                                    _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(nl.edge_offsets),
+                                    nl.n_edges, _lib.ptr(ews), 0 if ews is None else ews.numel(), _lib.ptr(G),
+                                    _lib.ptr(dG), _lib.ptr(flag), _lib.stream_ptr()))
     return G, dG, flag
 
 

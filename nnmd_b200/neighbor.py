@@ -27,6 +27,8 @@ class NeighborList:
     rc: float
     total: int
     max_row: int
+    edge_offsets: torch.Tensor | None = None   # int64 (n_rows+1): prefix sums of per-row neighbours with a larger index
+    n_edges: int = 0
 
     @property
     def n_rows(self) -> int:
@@ -86,16 +88,17 @@ def build_from_wrapped(posw: torch.Tensor, n_frames: int, n_atoms: int, rc: floa
         ws_bytes = int(lib.nnmd_nlist_workspace_bytes(n_frames, n_atoms))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
         offsets = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
-        stats = torch.empty(2, dtype=torch.int64, device=dev)
+        edge_offsets = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        stats = torch.empty(3, dtype=torch.int64, device=dev)
         st = _lib.stream_ptr()
         _lib.check(lib.nnmd_nlist_count(code, _lib.ptr(posw), n_frames, n_atoms, n_centres, float(rc), _lib.ptr(ws),
-                                        _lib.ptr(offsets), _lib.ptr(stats), st))
-        total, max_row = (int(v) for v in stats.tolist())  # the one sync of the build
+                                        _lib.ptr(offsets), _lib.ptr(edge_offsets), _lib.ptr(stats), st))
+        total, max_row, n_edges = (int(v) for v in stats.tolist())  # the one sync of the build
         idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
         _lib.check(lib.nnmd_nlist_fill(code, _lib.ptr(posw), n_frames, n_atoms, n_centres, float(rc), _lib.ptr(ws),
                                        _lib.ptr(offsets), max_row, _lib.ptr(idx), st))
     return NeighborList(posw, offsets, idx[:total] if total > 0 else idx[:0], n_frames, n_atoms, n_centres, float(rc),
-                        total, max_row)
+                        total, max_row, edge_offsets, n_edges)
 
 
 def build_neighbor_list(cart: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, rc: float,

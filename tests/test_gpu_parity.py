@@ -261,6 +261,46 @@ def test_large_cell_properties():
     assert edg < 1e-5
 
 
+def test_edge_centric_and_vertex_centric_kernels_agree(monkeypatch):
+    """The fp32 64-function group runs the edge-centric kernel pair (K3e + gather); NNMD_NO_EDGE=1 forces the
+    vertex-centric kernel.  Same G, dG and fused forces to fp32 round-off, and both within 1e-5 of the fp64 truth."""
+    from nnmd_b200.engine import fused_force
+    from nnmd_b200.features import calculate_sf as csf_mod  # noqa: F401
+    from nnmd_b200.features.calculate_sf import _PLAN_CACHE, get_plan, raw_descriptors
+    from nnmd_b200.neighbor import build_neighbor_list
+    from nnmd_b200.workloads import bench_table, fcc_cell
+    from oracle import nl_oracle as O3
+    sfd = bench_table()
+    pos, cell, pbc = fcc_cell(5, dtype=torch.float32)
+    pos = pos + 0.3  # some atoms wrap
+    nl = build_neighbor_list(pos[None].to(DEV), cell.to(DEV), pbc.to(DEV), 6.0)
+    assert nl.n_edges * 2 == nl.total and nl.edge_offsets is not None
+    out = {}
+    for tag, env in (("edge", "0"), ("vertex", "1")):
+        monkeypatch.setenv("NNMD_NO_EDGE", env)
+        _PLAN_CACHE.clear()
+        plan = get_plan(sfd, torch.float32, nl.posw.device)
+        G, dG, flag = raw_descriptors(plan, nl)
+        Gv, _, _ = raw_descriptors(plan, nl, with_grad=False)
+        torch.manual_seed(3)
+        w = torch.randn(nl.n_rows, plan.nf, device=DEV)
+        F = fused_force(plan, nl, w)
+        assert int(flag.item()) == 0
+        out[tag] = (G.cpu(), dG.cpu(), Gv.cpu(), F.cpu(), w.cpu())
+    _PLAN_CACHE.clear()
+    p64 = nl.posw[:, :3].double().cpu()[None]
+    z3 = torch.zeros(3, 3, dtype=torch.float64)
+    G3, dG3, _ = O3.raw_descriptors(p64, z3, torch.zeros(3, dtype=torch.float64), sfd)
+    for tag in ("edge", "vertex"):
+        G, dG, Gv, F, w = out[tag]
+        eg, edg = col_relerr(G, G3[0], 1), col_relerr(dG, dG3[0], 1)
+        F3 = -(w.double().unsqueeze(-1) * dG3[0]).sum(dim=1)
+        ef = float((F.double() - F3).abs().max() / F3.abs().max())
+        print(f"{tag}: G {eg:.2e} dG {edg:.2e} values-only G {col_relerr(Gv, G3[0], 1):.2e} fused force {ef:.2e}")
+        assert eg < 1e-5 and edg < 1e-5 and col_relerr(Gv, G3[0], 1) < 1e-5 and ef < 1e-5
+    assert col_relerr(out["edge"][1], out["vertex"][1], 1) < 1e-5
+
+
 def test_predict_api_shapes_and_values():
     from nnmd_b200.nn import BPNN
     from oracle import dense_oracle as O2
