@@ -860,7 +860,7 @@ static int sf_run(const nnmd_sf_plan *p, const T *posw, int64_t n_frames, int64_
                 e.rc = float(g.rc); e.eta = float(g.eta); e.step = float(g.ladder_step);
                 e.zeta = (const float *)g.d_zeta; e.lam = (const float *)g.d_lam; e.coef = (const float *)g.d_coef; e.col = g.d_col;
                 e.nf = p->nf; e.nfa = p->edge_slots; e.ebase = g.edge_base; e.E = (float *)edge_ws;
-                e.G = G; e.dG = dG; e.w = w; e.force = force; e.flag = flag;
+                e.G = G; e.dG = dG; e.w = w; e.force = force; e.flag = flag; e.row_counter = p->d_row_counter;
                 int r = launch_edge<MODE>(g, e, st);
                 if (r) return r;
                 continue;
@@ -931,12 +931,17 @@ extern "C" int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, cons
     if (r) { nnmd_sf_plan_destroy(p); return r; }
     for (AngGroup &g : p->groups)
         if (g.edge_path) { g.edge_base = p->edge_slots; p->edge_slots += g.n_slots; }
+    if (cudaMalloc((void **)&p->d_row_counter, sizeof(unsigned long long)) != cudaSuccess) {
+        nnmd_sf_plan_destroy(p);
+        return set_err(NNMD_ERR_CUDA, "plan: cudaMalloc failed");
+    }
     *out = p;
     return NNMD_OK;
 }
 
 extern "C" void nnmd_sf_plan_destroy(nnmd_sf_plan *p) {
     if (!p) return;
+    cudaFree(p->d_row_counter);
     cudaFree(p->rad.d_rc); cudaFree(p->rad.d_eta); cudaFree(p->rad.d_rs); cudaFree(p->rad.d_col);
     for (AngGroup &g : p->groups) { cudaFree(g.d_zeta); cudaFree(g.d_lam); cudaFree(g.d_coef); cudaFree(g.d_col); }
     delete p;

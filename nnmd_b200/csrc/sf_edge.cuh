@@ -36,6 +36,7 @@ struct EdgeArgs {
     const float *w;
     float *force;
     uint32_t *flag;
+    unsigned long long *row_counter;  // dynamic row scheduling (zeroed before the launch)
 };
 
 // record: per lambda class (EREC_CLASS floats)  [ L0 L1 L2 eid | A0 A1 B0 B1 | A2 B2 V0a V0j | R0 R1 R2 . ]
@@ -108,7 +109,6 @@ __global__ void __launch_bounds__(128, 4) angular_edge_kernel(EdgeArgs a) {
     NbView<float> nb;
     nb.bind(recs + ANG_BATCH * EREC_STRIDE, a.cap);
     int *queue = reinterpret_cast<int *>(recs + ANG_BATCH * EREC_STRIDE + size_t(NB_FIELDS) * a.cap);
-    int *queue_eid = queue + 64;
 
     const float inv_rc = MF::rcp(a.rc), rc2 = a.rc * a.rc;
     const float zeta0 = a.zeta[2 * lane], zeta1 = a.zeta[2 * lane + 1];
@@ -119,7 +119,14 @@ __global__ void __launch_bounds__(128, 4) angular_edge_kernel(EdgeArgs a) {
     const int kind = a.kind;
     const float eta = a.eta, step = a.step;
 
-    for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
+    // Rows cost between 0 and ~2x the mean (an atom owns only the edges towards larger indices), so warps pull
+    // rows from a global counter instead of striding.
+    (void)wpb;
+    for (;;) {
+        unsigned long long next = 0;
+        if (lane == 0) next = atomicAdd(a.row_counter, 1ull);
+        const int64_t row = int64_t(__shfl_sync(0xffffffffu, next, 0));
+        if (row >= a.n_rows) break;
         const int64_t frame = row / a.n_centres;
         const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
         float xa, ya, za;
@@ -132,19 +139,24 @@ __global__ void __launch_bounds__(128, 4) angular_edge_kernel(EdgeArgs a) {
         // phi*: two partial sums of Phi per function; vg*: (centre-a value of the row, Gamma of the current edge)
         float2 phi0 = make_float2(0.f, 0.f), phi1 = phi0, vg0 = phi0, vg1 = phi0;
         int cur_eid = -1;
-        int head = 0, qn = 0;
+        int head = 0, qn = 0, pushed_total = 0;
+        int last_tj = -1;  // edge (row slot) of the last record already processed
 
         // process `cnt` queued (edge, third atom) pairs: phase 1 (records, one per lane) then phase 2 (functions)
         auto flush = [&](int cnt) {
             __syncwarp();
             bool is_first = false;
+            const int pk = lane < cnt ? queue[(head + lane) & 63] : 0;
+            const int my_tj = lane < cnt ? (pk & 0x7fff) : -2;
+            int prev_tj = __shfl_up_sync(0xffffffffu, my_tj, 1);
+            if (lane == 0) prev_tj = last_tj;
             if (lane < cnt) {
-                const int pk = queue[(head + lane) & 63];
-                is_first = (pk >> 30) & 1;
-                const int eid = is_first ? queue_eid[(head + lane) & 63] : -1;
-                make_record_edge<WITH_PHI, LADDER>(nb, pk & 0x7fff, (pk >> 15) & 0x7fff, kind, step, inv_rc, eta, eid,
+                is_first = my_tj != prev_tj;  // the queue is edge-major: a change of tj opens the next edge
+                const int eid = is_first ? int(e0 + nb.epos[my_tj]) : -1;
+                make_record_edge<WITH_PHI, LADDER>(nb, my_tj, (pk >> 15) & 0x7fff, kind, step, inv_rc, eta, eid,
                                                    recs + lane * EREC_STRIDE);
             }
+            last_tj = __shfl_sync(0xffffffffu, my_tj, cnt - 1);
             const unsigned firsts = __ballot_sync(0xffffffffu, is_first);
             __syncwarp();
             int t = 0;
@@ -199,28 +211,21 @@ __global__ void __launch_bounds__(128, 4) angular_edge_kernel(EdgeArgs a) {
         for (int tj = 0; tj < nn; ++tj) {
             const int ep = nb.epos[tj];
             if (ep < 0) continue;  // the neighbour owns this edge (warp-uniform)
-            const int eid = int(e0 + ep);
             const Q4<float> uj = ld4<float>(nb.u4 + 4 * tj);
-            int pushed = 0;
+            const int pushed0 = pushed_total;
             for (int kb = 0; kb < nn; kb += 32) {
                 const int tk = kb + lane;
                 bool ok = false;
-                if (tk < nn && tk != tj) {
+                if (tk < nn) {
                     const Q4<float> uk = ld4<float>(nb.u4 + 4 * tk);
                     const float wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
                     const float z2 = wx * wx + wy * wy + wz * wz;
-                    ok = (z2 < rc2) && (z2 > 0.f);  // the third side of the triangle (symm_funcs.py:34-50)
+                    ok = (z2 < rc2) && (z2 > 0.f);  // third side inside (0, rc) (symm_funcs.py:34-50); z2 = 0 for tk == tj
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) {
-                    const int before = __popc(m & ((1u << lane) - 1u));
-                    const int slot = (head + qn + before) & 63;
-                    const int first = (pushed == 0 && before == 0) ? 1 : 0;
-                    queue[slot] = tj | (tk << 15) | (first << 30);
-                    if (first) queue_eid[slot] = eid;
-                }
+                if (ok) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 63] = tj | (tk << 15);
                 const int c = __popc(m);
-                pushed += c;
+                pushed_total += c;
                 qn += c;
                 if (qn >= ANG_BATCH) {
                     flush(ANG_BATCH);
@@ -228,8 +233,8 @@ __global__ void __launch_bounds__(128, 4) angular_edge_kernel(EdgeArgs a) {
                     qn -= ANG_BATCH;
                 }
             }
-            if (pushed == 0) {  // an edge that closes no triangle still owns a (zero) slot the gather will read
-                float *dst = a.E + (size_t(eid) * 2) * nfa + a.ebase + 2 * lane;
+            if (pushed_total == pushed0) {  // an edge that closes no triangle still owns a (zero) slot the gather reads
+                float *dst = a.E + (size_t(e0 + ep) * 2) * nfa + a.ebase + 2 * lane;
                 if (WITH_PHI) *reinterpret_cast<float2 *>(dst) = make_float2(0.f, 0.f);
                 *reinterpret_cast<float2 *>(dst + nfa) = make_float2(0.f, 0.f);
             }
@@ -372,6 +377,7 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
         if (occ < 1) occ = 1;
         int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * occ);
+        NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
         ProfScope prof(PROF_ANGULAR, st);
         kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
         NNMD_LAUNCH_CHECK("angular_edge_kernel");

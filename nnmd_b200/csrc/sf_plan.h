@@ -50,4 +50,5 @@ struct nnmd_sf_plan {
     nnmd::RadialTab rad;
     std::vector<nnmd::AngGroup> groups;
     int edge_slots = 0;  // function-axis length of the edge scratch (sum of n_slots over edge-path groups)
+    unsigned long long *d_row_counter = nullptr;  // work counter of the dynamically scheduled kernels
 };
