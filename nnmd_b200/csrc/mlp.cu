@@ -145,6 +145,188 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_kernel(MlpArgs<T> a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v2: register-tiled kernel (fp32).  A CTA of 256 threads owns 64 atoms; every thread produces a 4 atoms x 4 neurons
+// tile per layer, so one 16 B load of activations and one 16 B load of weights feed 16 FMAs.  Weights live in shared
+// memory in BOTH layouts: transposed [k][n] for the forward sweep (4 neurons contiguous) and row-major [n][k] for
+// the backward sweep (4 inputs contiguous).  Used when everything fits in shared memory; otherwise v1 above.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MLP2_TILE = 64;
+constexpr int MLP2_PITCH = 68;   // activations [k][68]: 16 B aligned rows, staggered banks
+constexpr int MLP2_THREADS = 256;
+
+struct Mlp2Args {
+    int L;
+    int sizes[MLP_MAX_LAYERS + 1];
+    int hoff[MLP_MAX_LAYERS];   // activations of layer l's input (floats)
+    int wtoff[MLP_MAX_LAYERS];  // W^T  [K][Np]
+    int woff[MLP_MAX_LAYERS];   // W    [N][Kp]
+    int boff[MLP_MAX_LAYERS];   // bias [Np]
+    const float *W[MLP_MAX_LAYERS];
+    const float *b[MLP_MAX_LAYERS];
+    const float *x;
+    int64_t n_rows;
+    float *e;
+    float *dEdx;
+};
+
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+__global__ void __launch_bounds__(MLP2_THREADS, 1) mlp2_kernel(Mlp2Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sm = reinterpret_cast<float *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int L = a.L, K0 = a.sizes[0];
+    // ---- weights into shared memory, both layouts, zero padded to multiples of 4
+    for (int l = 0; l < L; ++l) {
+        const int K = a.sizes[l], N = a.sizes[l + 1], Np = (N + 3) & ~3, Kp = (K + 3) & ~3;
+        float *wt = sm + a.wtoff[l], *w = sm + a.woff[l], *bb = sm + a.boff[l];
+        for (int i = tid; i < K * Np; i += blockDim.x) {
+            const int k = i / Np, n = i - k * Np;
+            wt[i] = n < N ? __ldg(a.W[l] + size_t(n) * K + k) : 0.f;
+        }
+        for (int i = tid; i < N * Kp; i += blockDim.x) {
+            const int n = i / Kp, k = i - n * Kp;
+            w[i] = k < K ? __ldg(a.W[l] + size_t(n) * K + k) : 0.f;
+        }
+        for (int i = tid; i < Np; i += blockDim.x) bb[i] = i < N ? __ldg(a.b[l] + i) : 0.f;
+    }
+    __syncthreads();
+    const int aq = tid & 15;  // atom quad inside the tile
+    const int64_t n_tiles = (a.n_rows + MLP2_TILE - 1) / MLP2_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t m0 = tile * MLP2_TILE;
+        const int valid = int(min(int64_t(MLP2_TILE), a.n_rows - m0));
+        float *h0 = sm + a.hoff[0];
+        for (int i = tid; i < MLP2_TILE * K0; i += blockDim.x) {
+            const int m = i / K0, k = i - m * K0;
+            h0[k * MLP2_PITCH + m] = m < valid ? a.x[(m0 + m) * K0 + k] : 0.f;
+        }
+        __syncthreads();
+        // ---- forward
+        for (int l = 0; l < L; ++l) {
+            const int K = a.sizes[l], N = a.sizes[l + 1], Np = (N + 3) & ~3;
+            const float *hin = sm + a.hoff[l], *wt = sm + a.wtoff[l], *bb = sm + a.boff[l];
+            for (int nq = tid >> 4; nq * 4 < Np; nq += MLP2_THREADS / 16) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(bb + 4 * nq);
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { acc[i][0] = b4.x; acc[i][1] = b4.y; acc[i][2] = b4.z; acc[i][3] = b4.w; }
+                const float *hp = hin + 4 * aq, *wp = wt + 4 * nq;
+#pragma unroll 4
+                for (int k = 0; k < K; ++k) {
+                    const float4 h4 = *reinterpret_cast<const float4 *>(hp + k * MLP2_PITCH);
+                    const float4 w4 = *reinterpret_cast<const float4 *>(wp + k * Np);
+                    const float hv[4] = {h4.x, h4.y, h4.z, h4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(hv[i], wv[j], acc[i][j]);
+                }
+                if (l < L - 1) {
+                    float *hout = sm + a.hoff[l + 1];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (4 * nq + j < N)
+                            *reinterpret_cast<float4 *>(hout + (4 * nq + j) * MLP2_PITCH + 4 * aq) =
+                                make_float4(sigmoidf_(acc[0][j]), sigmoidf_(acc[1][j]), sigmoidf_(acc[2][j]), sigmoidf_(acc[3][j]));
+                } else if (nq == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (4 * aq + i < valid) a.e[m0 + 4 * aq + i] = acc[i][0];
+                }
+            }
+            __syncthreads();
+        }
+        // ---- backward (dE/dx), in place as in v1
+        if (a.dEdx) {
+            {
+                const int l = L - 1, K = a.sizes[l];
+                float *buf = sm + a.hoff[l];
+                const float *w = sm + a.woff[l];  // single row
+                for (int i = tid; i < K * MLP2_TILE; i += blockDim.x) {
+                    const int k = i >> 6, m = i & 63;
+                    const float wv = w[k];
+                    if (l > 0) { const float h = buf[k * MLP2_PITCH + m]; buf[k * MLP2_PITCH + m] = wv * h * (1.f - h); }
+                    else buf[k * MLP2_PITCH + m] = wv;
+                }
+                __syncthreads();
+            }
+            for (int l = L - 1; l >= 1; --l) {
+                const int N = a.sizes[l], Kc = a.sizes[l - 1], Kp = (Kc + 3) & ~3;  // W_{l-1} is (N x Kc)
+                const float *buf = sm + a.hoff[l], *w = sm + a.woff[l - 1];
+                float *prev = sm + a.hoff[l - 1];
+                for (int kq = tid >> 4; kq * 4 < Kp; kq += MLP2_THREADS / 16) {
+                    float acc[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+                    const float *dp = buf + 4 * aq, *wp = w + 4 * kq;
+#pragma unroll 4
+                    for (int n = 0; n < N; ++n) {
+                        const float4 d4 = *reinterpret_cast<const float4 *>(dp + n * MLP2_PITCH);
+                        const float4 w4 = *reinterpret_cast<const float4 *>(wp + n * Kp);
+                        const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dv[i], wv[j], acc[i][j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = 4 * kq + j;
+                        if (k >= Kc) continue;
+                        float4 *pp = reinterpret_cast<float4 *>(prev + k * MLP2_PITCH + 4 * aq);
+                        if (l - 1 >= 1) {
+                            const float4 h = *pp;
+                            *pp = make_float4(acc[0][j] * h.x * (1.f - h.x), acc[1][j] * h.y * (1.f - h.y),
+                                              acc[2][j] * h.z * (1.f - h.z), acc[3][j] * h.w * (1.f - h.w));
+                        } else {
+                            *pp = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            for (int i = tid; i < MLP2_TILE * K0; i += blockDim.x) {
+                const int m = i / K0, k = i - m * K0;
+                if (m < valid) a.dEdx[(m0 + m) * K0 + k] = h0[k * MLP2_PITCH + m];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// returns NNMD_OK after launching, or -1 when the network does not fit (caller falls back to v1)
+static int mlp2_try(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases,
+                    const void *x, int64_t n_rows, void *e, void *dEdx, cudaStream_t st) {
+    Mlp2Args a;
+    a.L = n_layers;
+    int off = 0;
+    for (int l = 0; l <= n_layers; ++l) a.sizes[l] = sizes[l];
+    for (int l = 0; l < n_layers; ++l) {
+        const int K = sizes[l], N = sizes[l + 1], Np = (N + 3) & ~3, Kp = (K + 3) & ~3;
+        a.hoff[l] = off;  off += K * MLP2_PITCH;
+        a.wtoff[l] = off; off += K * Np;
+        a.woff[l] = off;  off += N * Kp;
+        a.boff[l] = off;  off += Np;
+        off = (off + 3) & ~3;
+        a.W[l] = (const float *)weights[l];
+        a.b[l] = (const float *)biases[l];
+    }
+    const size_t smem = size_t(off) * sizeof(float);
+    if (smem > 220 * 1024) return -1;
+    a.x = (const float *)x; a.n_rows = n_rows; a.e = (float *)e; a.dEdx = (float *)dEdx;
+    NNMD_CUDA_CHECK(cudaFuncSetAttribute(mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int64_t n_tiles = (n_rows + MLP2_TILE - 1) / MLP2_TILE;
+    const int64_t blocks = std::min<int64_t>(n_tiles, int64_t(sm_count()));
+    ProfScope prof(PROF_MLP, st);
+    mlp2_kernel<<<unsigned(blocks), MLP2_THREADS, smem, st>>>(a);
+    NNMD_LAUNCH_CHECK("mlp2_kernel");
+    return NNMD_OK;
+}
+
 template <typename T>
 static int mlp_run(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases,
                    const void *x, int64_t n_rows, void *e, void *dEdx, cudaStream_t st) {
@@ -200,6 +382,10 @@ extern "C" int nnmd_mlp_energy_grad(int dtype, int precision, int n_layers, cons
         return mlp_tf32_run(n_layers, sizes, weights, biases, x, n_rows, e, dEdx, st);
     }
     if (precision != NNMD_MLP_EXACT) return set_err(NNMD_ERR_INVALID, "mlp: bad precision %d", precision);
-    if (dtype == NNMD_F32) return mlp_run<float>(n_layers, sizes, weights, biases, x, n_rows, e, dEdx, st);
+    if (dtype == NNMD_F32) {
+        const int r = mlp2_try(n_layers, sizes, weights, biases, x, n_rows, e, dEdx, st);
+        if (r >= 0) return r;
+        return mlp_run<float>(n_layers, sizes, weights, biases, x, n_rows, e, dEdx, st);
+    }
     return mlp_run<double>(n_layers, sizes, weights, biases, x, n_rows, e, dEdx, st);
 }
