@@ -266,18 +266,36 @@ def run_ours(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (angular K3): algorithmic bytes per centre atom
+    # ---- roofline of the dominant kernel (angular K3e): algorithmic bytes per centre atom
     peak, peak_src = load_peaks()
     n_ang = sum(1 for k in sfd["features"] if k in (4, 5))
     ang_ms, ang_n = prof["angular"]
     ang_ms_per_launch = ang_ms / max(ang_n, 1)
+    # own position + neighbour row (int32) + each neighbour position once + the angular columns of G and dG
     bytes_per_atom = 16 + 4 * mean_nbrs + 16 + n_ang * 4 + (n_ang * 12 if args.mode == "materialize" else 0)
     achieved = bytes_per_atom * n_owned / (ang_ms_per_launch * 1e-3) / 1e9 if ang_ms_per_launch > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "angular_kernel<float,2,DG>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "angular_edge_kernel<true,true> (K3e)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "ms_per_launch": ang_ms_per_launch, "algorithmic_bytes_per_atom": bytes_per_atom,
-                "note": "K3 is bound by the FP32 FMA pipe and the SFU (ex2), not by HBM; see DESIGN.md and profiles/",
+                "note": "K3e is bound by the FP32 FMA pipe and the SFU (ex2), not by HBM: see fp32_pipe/sfu_pipe, DESIGN.md, profiles/",
                 "stage_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+    # compute-side view of the same kernel against the MEASURED pipe peaks (tools/microbench.cu -> profiles/microbench_r1.json):
+    # one (edge, third atom, function) costs 11 FMA-pipe lane-ops and 1.5 ex2; records per atom
+    # = closed ordered (j,k) pairs / 2 = triangles-per-atom (3 edges x 1/3 ownership)
+    try:
+        with open(os.path.join(ROOT, "profiles", "microbench_r1.json")) as fh:
+            mb = json.load(fh)
+    except Exception:
+        mb = None
+    if mb is not None and ang_ms_per_launch > 0 and args.tri_per_atom > 0:
+        rec = args.tri_per_atom * (mean_nbrs / 78.0) ** 2 * n_owned  # free surfaces of the wrap-only cell thin the rows
+        fma_ops = rec * n_ang * 11.0
+        sfu_ops = rec * n_ang * 1.5
+        roofline["fp32_pipe"] = {"achieved_lane_ops_per_s": fma_ops / (ang_ms_per_launch * 1e-3), "peak": mb["ffma_lane_ops_per_s"],
+                                 "frac": fma_ops / (ang_ms_per_launch * 1e-3) / mb["ffma_lane_ops_per_s"],
+                                 "peak_source": "measured, tools/microbench.cu (FFMA and FFMA2 give the same lane rate)"}
+        roofline["sfu_pipe"] = {"achieved_lane_ops_per_s": sfu_ops / (ang_ms_per_launch * 1e-3), "peak": mb["mufu_ex2_lane_ops_per_s"],
+                                "frac": sfu_ops / (ang_ms_per_launch * 1e-3) / mb["mufu_ex2_lane_ops_per_s"]}
     line = {"metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -306,6 +324,8 @@ def main():
     ap.add_argument("--mlp", default="exact", choices=["exact", "tf32"])
     ap.add_argument("--ref-cells", type=int, default=3, help="reference arm sample: cells per edge (3 -> 108 atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tri-per-atom", type=float, default=1350.0,
+                    help="closed triangles per atom of the workload (bulk fcc, rc=6: 1350) for the pipe-utilisation estimate")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
