@@ -72,6 +72,17 @@ class SlabShard:
             send.append(sel if sel.numel() else None)
         return cls(rank, world, float(rc), pos.shape[0], mine, pos[mine].contiguous(), send, edges)
 
+    def to(self, device) -> "SlabShard":
+        """Move the owned positions and the send plan to `device` (done once; the per-step exchange then stays on it)."""
+        device = torch.device(device)
+        self.owned_pos = self.owned_pos.to(device)
+        self.send_idx = [None if s is None else s.to(device) for s in self.send_idx]
+        return self
+
+    def set_owned_positions(self, pos: torch.Tensor) -> None:
+        """New positions of the owned atoms (same order), e.g. after an MD step or an H2D copy."""
+        self.owned_pos = pos
+
     def exchange_halo(self, device=None) -> torch.Tensor:
         """Positions this rank computes on: owned atoms first, then the halo atoms received from the peers.
 
