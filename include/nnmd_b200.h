@@ -157,6 +157,20 @@ int nnmd_mlp_energy_grad(int dtype, int precision, int n_layers, const int32_t *
                          const void *const *biases, const void *x, int64_t n_rows, void *e, void *dEdx,
                          void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K7  training backward of the atomic MLP: gradients of a loss L(e, w = dE/dx) w.r.t. weights and biases, i.e. the
+ *     double backward torch.autograd performs for bpnn.py:342-366 (energy term through e, force term through dE/dg).
+ *   ge dev (n_rows)            dL/de per atom
+ *   u  dev (n_rows, sizes[0])  dL/d(dE/dx) per atom, or NULL when the loss has no force term
+ *   grad_weights / grad_biases: host arrays of n_layers DEVICE pointers, same shapes as the parameters;
+ *   the kernel ADDS into them (atomicAdd): zero them first.  Activations are recomputed, nothing is stored.
+ * K4c' backward of the force contraction: u[a,f] = - sum_c gf[a,c] dG[a,f,c]   (gf = dL/dF, (n_rows,3))
+ * ------------------------------------------------------------------------------------- */
+int nnmd_mlp_train_backward(int dtype, int n_layers, const int32_t *sizes, const void *const *weights,
+                            const void *const *biases, const void *x, int64_t n_rows, const void *ge, const void *u,
+                            void *const *grad_weights, void *const *grad_biases, void *stream);
+int nnmd_force_contract_backward(int dtype, const void *gf, const void *dG, int64_t n_rows, int nf, void *u, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

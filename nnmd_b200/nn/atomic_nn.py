@@ -7,8 +7,10 @@ nn.Linear) so `state_dict()` keys are `model.{i}.weight|bias` and the reference'
 Two execution paths:
   * `energy_and_grad(x)`  -- K6 (csrc/mlp.cu): e and dE/dx in one fused CUDA pass, no autograd graph; used by
     `BPNN.predict` and the evaluation engine.
-  * `forward(x)`          -- differentiable torch ops (needed while the training step differentiates through
-    dE/dx); same arithmetic.
+  * `energy_and_grad_autograd(x)` -- the same forward, wired into autograd with K7 (csrc/mlp_train.cu) as the
+    backward: gradients of a loss of (e, dE/dx) w.r.t. weights and biases.  `BPNN._train_loop` uses this.
+  * `forward(x)`          -- plain torch ops, kept for API compatibility (`net(x)` works like the reference's
+    module); not used by the training or prediction paths of this package.
 """
 from __future__ import annotations
 
@@ -39,6 +41,14 @@ class AtomicNN(nn.Module):
             if i != last:
                 x = self.activation(x)
         return x
+
+    # ---- CUDA training path ---------------------------------------------------------------------------------
+    def energy_and_grad_autograd(self, x: torch.Tensor):
+        """(e, dE/dx) on the CUDA kernels (K6), differentiable w.r.t. the parameters through both outputs (K7)."""
+        if self.activation is not torch.sigmoid:
+            raise NotImplementedError("the CUDA atomic network implements the reference's sigmoid activation only")
+        from .functional import atomic_energy_and_grad
+        return atomic_energy_and_grad(x, [m.weight for m in self.model], [m.bias for m in self.model])
 
     # ---- CUDA inference path ------------------------------------------------------------------------------
     def layer_sizes(self) -> list[int]:

@@ -7,6 +7,9 @@ Deviations from the reference, all of them places where the reference raises as 
     (bpnn.py:529-531).  Here pbc defaults to `self.pbc` when `config` received one, else all-False for a
     zero-determinant cell and all-True otherwise.
   * `fit` works without the DEBUG environment variable and without installed package metadata.
+  * The training step does not build a torch graph through the MLP: forward (K6) and the double backward (K7) are
+    CUDA kernels behind two autograd Functions; `retain_graph=True` and the `.grad` accumulation on the cached
+    descriptors (SURVEY 3.2 notes ii, iii) have no counterpart.
 """
 from __future__ import annotations
 
@@ -17,6 +20,7 @@ from torch.utils.data import DataLoader
 
 from .._util._logger import Logger
 from ..engine import force_contract
+from .functional import force_contract as autograd_force_contract
 from ..features import calculate_sf
 from .atomic_nn import AtomicNN
 from .dataset import TrainAtomicDataset
@@ -111,13 +115,13 @@ class BPNN(torch.nn.Module):
         return E_loss + F_loss, E_loss, F_loss
 
     def _energies_forces(self, g: dict, dG: dict):
-        """Per-species MLP, dE/dg (graph kept for the force loss) and the force contraction (bpnn.py:342-364)."""
+        """Per-species MLP, dE/dg and the force contraction (bpnn.py:342-364) on K6 / K4c; the backward of the loss
+        through both (the reference's double backward) is K7 / K4c' (nn/functional.py)."""
         e_nn, f_nn = [], []
         for i, spec in enumerate(self.species):
-            e_spec = self.atomic_nets[i](g[spec])
-            dE = torch.autograd.grad(e_spec.sum(), g[spec], create_graph=True)[0]
+            e_spec, dE = self.atomic_nets[i].energy_and_grad_autograd(g[spec])
             e_nn.append(e_spec)
-            f_nn.append(-torch.einsum("ijk,ijkl->ijl", dE, dG[spec]))
+            f_nn.append(autograd_force_contract(dE, dG[spec]))
         return torch.cat(e_nn, dim=0), torch.cat(f_nn, dim=0)
 
     # ------------------------------------------------------------------------------------------------ loops

@@ -1,0 +1,92 @@
+"""GPU tests of the training step: K7 (double backward of the atomic MLP) and K4c' against torch.autograd on the
+same arithmetic, and `BPNN._train_loop` against the losses and weights the UNMODIFIED reference produced
+(tests/golden/train_step.npz: 3 epochs of Adam and AdamW from recorded initial weights)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _torch_reference(net, g, dG, e_ref, f_ref, ec, fc):
+    """The reference's step in plain torch ops (bpnn.py:342-366)."""
+    g = g.detach().clone().requires_grad_(True)
+    e = net(g)
+    dE = torch.autograd.grad(e.sum(), g, create_graph=True)[0]
+    f = -torch.einsum("ijk,ijkl->ijl", dE, dG)
+    loss = ec * torch.mean((e.sum(dim=1) - e_ref) ** 2) + fc / 3 * torch.mean((f - f_ref) ** 2)
+    grads = torch.autograd.grad(loss, list(net.parameters()))
+    return e.detach(), dE.detach(), f.detach(), loss.detach(), grads
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-4)])
+@pytest.mark.parametrize("hidden,F,B,N", [([16, 8], 10, 3, 40), ([7], 5, 2, 3), ([24, 12, 6], 14, 5, 27), (33, 9, 1, 70)])
+def test_training_gradients_match_autograd(dtype, tol, hidden, F, B, N):
+    from nnmd_b200.nn import AtomicNN
+    from nnmd_b200.nn.functional import force_contract
+    torch.manual_seed(hash((str(hidden), F)) % 1000)
+    net = AtomicNN(F, hidden).to(DEV, dtype)
+    g = torch.rand(B, N, F, device=DEV, dtype=dtype)
+    g = g / g.norm(dim=-1, keepdim=True)
+    dG = torch.randn(B, N, F, 3, device=DEV, dtype=dtype)
+    e_ref = torch.rand(B, 1, device=DEV, dtype=dtype)
+    f_ref = torch.randn(B, N, 3, device=DEV, dtype=dtype) * 0.1
+    ec, fc = 1.0, 0.7
+    e0, dE0, f0, loss0, grads0 = _torch_reference(net, g, dG, e_ref, f_ref, ec, fc)
+    e, dE = net.energy_and_grad_autograd(g)
+    f = force_contract(dE, dG)
+    loss = ec * torch.mean((e.sum(dim=1) - e_ref) ** 2) + fc / 3 * torch.mean((f - f_ref) ** 2)
+    grads = torch.autograd.grad(loss, list(net.parameters()))
+    ftol = 1e-10 if dtype == torch.float64 else 1e-5
+    assert relerr(e.cpu(), e0.cpu()) < ftol and relerr(dE.cpu(), dE0.cpu()) < ftol and relerr(f.cpu(), f0.cpu()) < ftol
+    assert abs(float(loss - loss0)) < ftol * abs(float(loss0))
+    for (name, _), ga, gb in zip(net.named_parameters(), grads, grads0):
+        assert ga.shape == gb.shape
+        assert relerr(ga.cpu(), gb.cpu()) < tol, name
+
+
+def test_energy_only_loss_has_no_force_path():
+    from nnmd_b200.nn import AtomicNN
+    torch.manual_seed(0)
+    net = AtomicNN(6, [8, 4]).to(DEV, torch.float64)
+    x = torch.rand(50, 6, device=DEV, dtype=torch.float64)
+    e, _ = net.energy_and_grad_autograd(x)
+    ga = torch.autograd.grad((e ** 2).sum(), list(net.parameters()))
+    gb = torch.autograd.grad((net(x) ** 2).sum(), list(net.parameters()))
+    for a, b in zip(ga, gb):
+        assert relerr(a.cpu(), b.cpu()) < 1e-10
+
+
+@pytest.mark.parametrize("opt", ["adam", "adamw"])
+def test_train_loop_reproduces_reference_run(opt):
+    """Same initial weights, same batch, 3 epochs: losses per epoch, validation loss and final weights of the reference."""
+    from nnmd_b200.nn import BPNN, TrainAtomicDataset
+    d = np.load(os.path.join(GOLDEN, "train_step.npz"))
+    lr, l2, ec, fc = (float(v) for v in d["cfg_scalars"])
+    g = torch.tensor(d["g"], device=DEV)
+    dg = torch.tensor(d["dg"], device=DEV)
+    B, N, F = g.shape
+    cfg = dict(atom_species=["X"], input_sizes=[F], hidden_sizes=[[int(v) for v in d["cfg_hidden"]]], learning_rate=lr,
+               l2_regularization=l2, e_loss_coeff=ec, f_loss_coeff=fc, load_models=False, path="", optimizer=opt,
+               batch_size=B, epochs=3)
+    net = BPNN(dtype=torch.float32)
+    net.config(cfg)
+    net.atomic_nets[0].load_state_dict({k[3:]: torch.tensor(d[k]) for k in d.files if k.startswith("w0_")})
+    ds = TrainAtomicDataset({"X": (g.requires_grad_(True), dg)}, torch.tensor(d["e_ref"], device=DEV),
+                            torch.tensor(d["f_ref"], device=DEV), {})
+    loader = torch.utils.data.DataLoader(ds, batch_size=B, shuffle=False)
+    losses = []
+    for ep in range(3):
+        e_l, f_l, l = net._train_loop(ep, loader)
+        losses.append([e_l.item(), f_l.item(), l.item()])
+    np.testing.assert_allclose(np.asarray(losses), d[f"losses_{opt}"], rtol=5e-4)
+    for k, v in net.atomic_nets[0].state_dict().items():
+        ref = d[f"w3_{opt}_" + k]
+        assert np.abs(v.cpu().numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), k
+    e_l, f_l, l = net._validate(0, loader)
+    np.testing.assert_allclose([e_l.item(), f_l.item(), l.item()], d[f"val_{opt}"], rtol=2e-3)
