@@ -19,6 +19,7 @@ import torch
 from torch.utils.data import DataLoader
 
 from .._util._logger import Logger
+from ..dist import allreduce_gradients
 from ..engine import force_contract
 from .functional import force_contract as autograd_force_contract
 from ..features import calculate_sf
@@ -33,6 +34,46 @@ if DEBUG:
 else:
     def tqdm(iterable, **_kwargs):
         return iterable
+
+
+class FrameBatches:
+    """Iterable over shuffled frame batches of a TrainAtomicDataset (or a Subset of one): yields the same
+    (g_dict, dG_dict, E, F) tuples a DataLoader with default collation would, built by tensor indexing."""
+
+    def __init__(self, base: TrainAtomicDataset, indices: torch.Tensor, batch_size: int, shuffle: bool):
+        self.base, self.indices, self.batch_size, self.shuffle = base, indices, int(batch_size), shuffle
+
+    def __len__(self):
+        return (self.indices.numel() + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        idx = self.indices
+        if self.shuffle:
+            idx = idx[torch.randperm(idx.numel())]
+        for s in range(0, idx.numel(), self.batch_size):
+            sel = idx[s:s + self.batch_size]
+            g, dG = {}, {}
+            for spec, (gs, dgs) in self.base.sf_data.items():
+                sel_d = sel.to(gs.device)
+                g[spec] = gs.detach().index_select(0, sel_d)
+                dG[spec] = dgs.index_select(0, sel_d)
+            yield g, dG, self.base.energies.index_select(0, sel.to(self.base.energies.device)), \
+                self.base.forces.index_select(0, sel.to(self.base.forces.device))
+
+
+def batch_loader(dataset, batch_size: int, shuffle: bool):
+    """FrameBatches for a TrainAtomicDataset / Subset chain, else a stock DataLoader."""
+    indices = None
+    base = dataset
+    while isinstance(base, torch.utils.data.Subset):
+        sub = torch.as_tensor(base.indices, dtype=torch.int64)
+        indices = sub if indices is None else sub[indices]
+        base = base.dataset
+    if isinstance(base, TrainAtomicDataset):
+        if indices is None:
+            indices = torch.arange(len(base), dtype=torch.int64)
+        return FrameBatches(base, indices, batch_size, shuffle)
+    return DataLoader(dataset, batch_size=batch_size, shuffle=shuffle)
 
 
 class RMSELoss(torch.nn.Module):
@@ -104,8 +145,11 @@ class BPNN(torch.nn.Module):
             raise ValueError(f"Optimizer {name} is not available. "
                              f"Available optimizers: {list(available_optimizers.keys())}")
         betas = (0.9, 0.999) if name == "adamw" else (0.8, 0.9999)
-        self.optim = available_optimizers[name](params=params, lr=self.learning_rate,
-                                                weight_decay=self.l2_regularization, betas=betas, amsgrad=True)
+        kwargs = dict(params=params, lr=self.learning_rate, weight_decay=self.l2_regularization, betas=betas, amsgrad=True)
+        try:  # same update rule, one fused kernel per step instead of a dozen foreach launches
+            self.optim = available_optimizers[name](fused=self.device.type == "cuda", **kwargs)
+        except (RuntimeError, TypeError, ValueError):
+            self.optim = available_optimizers[name](**kwargs)
 
     # ------------------------------------------------------------------------------------------------- loss
     def _loss(self, e_nn, energies, f_nn, forces):
@@ -128,16 +172,19 @@ class BPNN(torch.nn.Module):
     def _run_epoch(self, loader, train: bool, desc: str):
         for net in self.atomic_nets:
             net.train(train)
+        params = [p for net in self.atomic_nets for p in net.parameters()]
         tot = torch.zeros(3, device=self.device)
         for g, dG, energy, forces in tqdm(loader, desc=desc, total=len(loader)):
             if train:
                 self.optim.zero_grad(set_to_none=True)
-            e_nn, f_nn = self._energies_forces(g, dG)
             energy = energy.to(device=self.device)
             forces = forces.to(device=self.device)
-            loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), energy, f_nn, forces)
+            with torch.set_grad_enabled(train):
+                e_nn, f_nn = self._energies_forces(g, dG)
+                loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), energy, f_nn, forces)
             if train:
                 loss.backward()
+                allreduce_gradients(params)  # frames are sharded across ranks: one flat all-reduce (no-op on 1 rank)
                 self.optim.step()
             tot += torch.stack([e_loss.detach(), f_loss.detach(), loss.detach()])
         tot /= len(loader)
@@ -182,9 +229,11 @@ class BPNN(torch.nn.Module):
         """reference: bpnn.py:217-306 (ExponentialLR gamma 0.99, net.log, per-epoch train/validation lines)."""
         batch_size = self.neural_net_data["batch_size"]
         epochs = self.neural_net_data["epochs"]
-        train_loader = DataLoader(train_dataset, batch_size=batch_size, shuffle=True)
-        val_loader = DataLoader(val_dataset, batch_size=batch_size, shuffle=True)
-        test_loader = DataLoader(test_dataset, batch_size=batch_size, shuffle=True)
+        # same batching as DataLoader(dataset, batch_size, shuffle=True) (bpnn.py:234-236), but a batch is ONE
+        # index_select per cached tensor instead of batch_size per-frame lookups and a Python collate
+        train_loader = batch_loader(train_dataset, batch_size, shuffle=True)
+        val_loader = batch_loader(val_dataset, batch_size, shuffle=True)
+        test_loader = batch_loader(test_dataset, batch_size, shuffle=True)
         self.sched = torch.optim.lr_scheduler.ExponentialLR(self.optim, gamma=0.99)
         self.net_log = Logger.get_logger("Net training info", "net.log")
         self._describe_training(len(train_dataset), len(val_dataset), len(test_dataset), batch_size, epochs)
