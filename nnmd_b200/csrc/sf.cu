@@ -85,9 +85,15 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
         int fpl = 1;
         auto slots_for = [&](int l) { return int((plus.size() + l - 1) / l + (minus.size() + l - 1) / l); };
         while (fpl < ANG_MAX_FPL && slots_for(fpl) > 32) fpl <<= 1;
-        if (const char *env = getenv("NNMD_ANG_FPL")) {  // tuning knob: force more functions per lane
+        // fp32, lambda = +-1, 33..64 functions: 4 per lane on 16 lanes, so the two half-warps of the edge-centric
+        // kernel work on two records at once (fewer shared-memory wavefronts and SFU ops per record)
+        if (dtype == NNMD_F32 && pm1 && fpl == 2 && slots_for(2) > 16 && slots_for(4) <= 16) fpl = 4;
+        if (const char *env = getenv("NNMD_ANG_FPL")) {  // tuning knob: force the number of functions per lane
             const int want = atoi(env);
-            while (fpl < want && fpl < ANG_MAX_FPL) fpl <<= 1;
+            if (want == 1 || want == 2 || want == 4) {
+                fpl = want;
+                while (fpl < ANG_MAX_FPL && slots_for(fpl) > 32) fpl <<= 1;
+            }
         }
         if (slots_for(fpl) > 32) return set_err(NNMD_ERR_INVALID, "internal: angular group does not fit a warp");
         AngGroup g;
@@ -119,18 +125,20 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
         // step (to within the 6-decimal rounding of the table, <= 2e-6), the second power is the first one times
         // 2^(step * L), and 2^(step * L) does not depend on the lane: it moves into the triangle record.
         const char *no_ladder = getenv("NNMD_NO_LADDER");  // tuning knob
-        if (pm1 && fpl == 2 && !(no_ladder && no_ladder[0] == '1')) {
+        if (pm1 && fpl >= 2 && !(no_ladder && no_ladder[0] == '1')) {
             double sum = 0, lo = 1e300, hi = -1e300;
             int n = 0;
             for (int l = 0; l < g.lanes; ++l)
-                if (col[2 * l] >= 0 && col[2 * l + 1] >= 0) {
-                    const double d = zeta[2 * l + 1] - zeta[2 * l];
-                    sum += d; lo = std::min(lo, d); hi = std::max(hi, d); ++n;
-                }
+                for (int i = 0; i + 1 < fpl; ++i)
+                    if (col[fpl * l + i] >= 0 && col[fpl * l + i + 1] >= 0) {
+                        const double d = zeta[fpl * l + i + 1] - zeta[fpl * l + i];
+                        sum += d; lo = std::min(lo, d); hi = std::max(hi, d); ++n;
+                    }
             if (n > 0 && hi - lo <= 2e-6) { g.ladder = 1; g.ladder_step = sum / n; }
         }
         const char *no_edge = getenv("NNMD_NO_EDGE");  // tuning knob
-        g.edge_path = (dtype == NNMD_F32 && pm1 && fpl == 2 && g.lanes == 32 && !(no_edge && no_edge[0] == '1')) ? 1 : 0;
+        g.edge_path = (dtype == NNMD_F32 && pm1 && ((fpl == 2 && g.lanes == 32) || (fpl == 4 && g.lanes == 16)) &&
+                       !(no_edge && no_edge[0] == '1')) ? 1 : 0;
         int r;
         if ((r = upload_real(dtype, zeta, &g.d_zeta))) return r;
         if ((r = upload_real(dtype, lam, &g.d_lam))) return r;
@@ -860,7 +868,7 @@ static int sf_run(const nnmd_sf_plan *p, const T *posw, int64_t n_frames, int64_
                 e.rc = float(g.rc); e.eta = float(g.eta); e.step = float(g.ladder_step);
                 e.zeta = (const float *)g.d_zeta; e.lam = (const float *)g.d_lam; e.coef = (const float *)g.d_coef; e.col = g.d_col;
                 e.nf = p->nf; e.nfa = p->edge_slots; e.ebase = g.edge_base; e.E = (float *)edge_ws;
-                e.G = G; e.dG = dG; e.w = w; e.force = force; e.flag = flag; e.row_counter = p->d_row_counter;
+                e.G = G; e.dG = dG; e.w = w; e.force = force; e.flag = flag; e.row_counter = p->d_row_counter; e.dbg = 0;
                 int r = launch_edge<MODE>(g, e, st);
                 if (r) return r;
                 continue;

@@ -37,6 +37,7 @@ struct EdgeArgs {
     float *force;
     uint32_t *flag;
     unsigned long long *row_counter;  // dynamic row scheduling (zeroed before the launch)
+    int dbg;                          // profiling knob (NNMD_DBG): 1 = skip phase 2, 2 = skip phase 1 as well
 };
 
 // record: per lambda class (EREC_CLASS floats)  [ L0 L1 L2 eid | A0 A1 B0 B1 | A2 B2 V0a V0j | R0 R1 R2 . ]
@@ -153,13 +154,14 @@ __global__ void __launch_bounds__(128, 4) angular_edge_kernel(EdgeArgs a) {
             if (lane < cnt) {
                 is_first = my_tj != prev_tj;  // the queue is edge-major: a change of tj opens the next edge
                 const int eid = is_first ? int(e0 + nb.epos[my_tj]) : -1;
-                make_record_edge<WITH_PHI, LADDER>(nb, my_tj, (pk >> 15) & 0x7fff, kind, step, inv_rc, eta, eid,
-                                                   recs + lane * EREC_STRIDE);
+                if (!(a.dbg & 2))
+                    make_record_edge<WITH_PHI, LADDER>(nb, my_tj, (pk >> 15) & 0x7fff, kind, step, inv_rc, eta, eid,
+                                                       recs + lane * EREC_STRIDE);
             }
             last_tj = __shfl_sync(0xffffffffu, my_tj, cnt - 1);
             const unsigned firsts = __ballot_sync(0xffffffffu, is_first);
             __syncwarp();
-            int t = 0;
+            int t = (a.dbg & 1) ? cnt : 0;
             while (t < cnt) {
                 if ((firsts >> t) & 1u) {  // record t opens the next edge: retire the previous one (warp-uniform)
                     if (cur_eid >= 0) {
@@ -249,6 +251,186 @@ __global__ void __launch_bounds__(128, 4) angular_edge_kernel(EdgeArgs a) {
         if (a.G) {
             if (col0 >= 0) a.G[row * a.nf + col0] = vg0.x;
             if (col1 >= 0) a.G[row * a.nf + col1] = vg1.x;
+        }
+        __syncwarp();
+    }
+}
+
+// K3e, 4 functions per lane: 16 lanes cover the 64 functions, so the two half-warps work on two different records at
+// once.  Per record pair the warp issues ~40 instructions, 3 ex2 and 44 FMA-pipe cycles: the FMA pipe alone is the
+// limiter (the 2-per-lane form co-saturates FMA pipe, SFU and issue).  LADDER: q_{i+1} = q_i * R_X along the lane's 4 zetas.
+template <bool WITH_PHI, bool LADDER>
+__global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using MF = M<float>;
+    const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t per_warp = size_t(ANG_BATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
+    unsigned char *wbase = smem_raw + per_warp * warp;
+    float *recs = reinterpret_cast<float *>(wbase);
+    NbView<float> nb;
+    nb.bind(recs + ANG_BATCH * EREC_STRIDE, a.cap);
+    int *queue = reinterpret_cast<int *>(recs + ANG_BATCH * EREC_STRIDE + size_t(NB_FIELDS) * a.cap);
+
+    const float inv_rc = MF::rcp(a.rc), rc2 = a.rc * a.rc;
+    const int half = lane >> 4, l16 = lane & 15;
+    float zeta[4], zm1[4];
+    int col[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { zeta[i] = a.zeta[4 * l16 + i]; zm1[i] = zeta[i] - 1.f; col[i] = a.col[4 * l16 + i]; }
+    const int class_off = (a.lam[4 * l16] < 0.f) ? EREC_CLASS : 0;  // lambda class of this lane's four functions
+    const size_t nfa = size_t(a.nfa);
+    const int kind = a.kind;
+    const float eta = a.eta, step = a.step;
+
+    // Rows cost between 0 and ~2x the mean (an atom owns only the edges towards larger indices), so warps pull
+    // rows from a global counter instead of striding.
+    (void)wpb;
+    for (;;) {
+        unsigned long long next = 0;
+        if (lane == 0) next = atomicAdd(a.row_counter, 1ull);
+        const int64_t row = int64_t(__shfl_sync(0xffffffffu, next, 0));
+        if (row >= a.n_rows) break;
+        const int64_t frame = row / a.n_centres;
+        const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
+        float xa, ya, za;
+        load_pos<float>(a.posw, gi, xa, ya, za);
+        const int64_t o0 = a.offsets[row], o1 = a.offsets[row + 1];
+        const int64_t e0 = a.edge_offsets[row], e1 = a.edge_offsets[row + 1];
+        const int first_gt = int((o1 - o0) - (e1 - e0));
+        const int nn = stage_row<float, true>(a.posw, a.idx, o0, o1, xa, ya, za, a.rc, inv_rc, eta, nb, a.cap, first_gt);
+
+        // phi*: two partial sums of Phi per function; vg*: (centre-a value of the row, Gamma of the current edge)
+        float2 phi[4], vg[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { phi[i] = make_float2(0.f, 0.f); vg[i] = phi[i]; }
+        // the two half-warps hold partial sums of the same edge: combine, then half 0 writes 16 B per lane
+        auto retire = [&](int eid) {
+            float ph[4], ga[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ph[i] = phi[i].x + phi[i].y;
+                ph[i] += __shfl_xor_sync(0xffffffffu, ph[i], 16);
+                ga[i] = vg[i].y + __shfl_xor_sync(0xffffffffu, vg[i].y, 16);
+            }
+            if (half == 0) {
+                float *dst = a.E + (size_t(eid) * 2) * nfa + a.ebase + 4 * l16;
+                if (WITH_PHI) *reinterpret_cast<float4 *>(dst) = make_float4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<float4 *>(dst + nfa) = make_float4(ga[0], ga[1], ga[2], ga[3]);
+            }
+        };
+        int cur_eid = -1;
+        int head = 0, qn = 0, pushed_total = 0;
+        int last_tj = -1;  // edge (row slot) of the last record already processed
+
+        // process `cnt` queued (edge, third atom) pairs: phase 1 (records, one per lane) then phase 2 (functions)
+        auto flush = [&](int cnt) {
+            __syncwarp();
+            bool is_first = false;
+            const int pk = lane < cnt ? queue[(head + lane) & 63] : 0;
+            const int my_tj = lane < cnt ? (pk & 0x7fff) : -2;
+            int prev_tj = __shfl_up_sync(0xffffffffu, my_tj, 1);
+            if (lane == 0) prev_tj = last_tj;
+            if (lane < cnt) {
+                is_first = my_tj != prev_tj;  // the queue is edge-major: a change of tj opens the next edge
+                const int eid = is_first ? int(e0 + nb.epos[my_tj]) : -1;
+                if (!(a.dbg & 2))
+                    make_record_edge<WITH_PHI, LADDER>(nb, my_tj, (pk >> 15) & 0x7fff, kind, step, inv_rc, eta, eid,
+                                                       recs + lane * EREC_STRIDE);
+            }
+            last_tj = __shfl_sync(0xffffffffu, my_tj, cnt - 1);
+            const unsigned firsts = __ballot_sync(0xffffffffu, is_first);
+            __syncwarp();
+            int t = (a.dbg & 1) ? cnt : 0;
+            while (t < cnt) {
+                if ((firsts >> t) & 1u) {  // record t opens the next edge: retire the previous one (warp-uniform)
+                    if (cur_eid >= 0) retire(cur_eid);
+                    cur_eid = __float_as_int(recs[t * EREC_STRIDE + 3]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { phi[i] = make_float2(0.f, 0.f); vg[i].y = 0.f; }
+                }
+                const unsigned rest = t < 31 ? (firsts & ~((2u << t) - 1u)) : 0u;
+                const int t_end = rest ? min(__ffs(rest) - 1, cnt) : cnt;
+                const float *r = recs + (t + half) * EREC_STRIDE + class_off;
+#pragma unroll 2
+                for (int tt = t + half; tt < t_end; tt += 2, r += 2 * EREC_STRIDE) {
+                    const float4 l = *reinterpret_cast<const float4 *>(r);       // L0 L1 L2 .
+                    const float4 c2 = *reinterpret_cast<const float4 *>(r + 8);  // A2 B2 V0a V0j
+                    float2 q01[4];
+                    float q2[4];
+                    const float2 e01 = __fmul2_rn(make_float2(zm1[0], zm1[0]), make_float2(l.x, l.y));
+                    q01[0].x = MF::exp2_fast(e01.x); q01[0].y = MF::exp2_fast(e01.y);
+                    q2[0] = MF::exp2_fast(zm1[0] * l.z);
+                    if (LADDER) {
+                        const float4 rr = *reinterpret_cast<const float4 *>(r + 12);  // R0 R1 R2 .
+#pragma unroll
+                        for (int i = 1; i < 4; ++i) {
+                            q01[i] = __fmul2_rn(q01[i - 1], make_float2(rr.x, rr.y));
+                            q2[i] = q2[i - 1] * rr.z;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 1; i < 4; ++i) {
+                            const float2 f01 = __fmul2_rn(make_float2(zm1[i], zm1[i]), make_float2(l.x, l.y));
+                            q01[i].x = MF::exp2_fast(f01.x); q01[i].y = MF::exp2_fast(f01.y);
+                            q2[i] = MF::exp2_fast(zm1[i] * l.z);
+                        }
+                    }
+                    if (WITH_PHI) {
+                        const float4 c1 = *reinterpret_cast<const float4 *>(r + 4);  // A0 A1 B0 B1
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 t01 = __ffma2_rn(make_float2(zeta[i], zeta[i]), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w));
+                            const float t2 = fmaf(zeta[i], c2.x, c2.y);
+                            phi[i] = __ffma2_rn(q01[i], t01, phi[i]);
+                            phi[i].x = fmaf(q2[i], t2, phi[i].x);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vg[i] = __ffma2_rn(q01[i], make_float2(c2.z, c2.w), vg[i]);
+                }
+                t = t_end;
+            }
+            __syncwarp();
+        };
+
+        for (int tj = 0; tj < nn; ++tj) {
+            const int ep = nb.epos[tj];
+            if (ep < 0) continue;  // the neighbour owns this edge (warp-uniform)
+            const Q4<float> uj = ld4<float>(nb.u4 + 4 * tj);
+            const int pushed0 = pushed_total;
+            for (int kb = 0; kb < nn; kb += 32) {
+                const int tk = kb + lane;
+                bool ok = false;
+                if (tk < nn) {
+                    const Q4<float> uk = ld4<float>(nb.u4 + 4 * tk);
+                    const float wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
+                    const float z2 = wx * wx + wy * wy + wz * wz;
+                    ok = (z2 < rc2) && (z2 > 0.f);  // third side inside (0, rc) (symm_funcs.py:34-50); z2 = 0 for tk == tj
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 63] = tj | (tk << 15);
+                const int c = __popc(m);
+                pushed_total += c;
+                qn += c;
+                if (qn >= ANG_BATCH) {
+                    flush(ANG_BATCH);
+                    head = (head + ANG_BATCH) & 63;
+                    qn -= ANG_BATCH;
+                }
+            }
+            if (pushed_total == pushed0 && half == 0) {  // an edge that closes no triangle still owns a (zero) slot
+                float *dst = a.E + (size_t(e0 + ep) * 2) * nfa + a.ebase + 4 * l16;
+                if (WITH_PHI) *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4 *>(dst + nfa) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (qn > 0) flush(qn);
+        if (cur_eid >= 0) retire(cur_eid);
+        // the centre's own share of its value (raw sum; scaled and completed by the gather kernel)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float v = vg[i].x + __shfl_xor_sync(0xffffffffu, vg[i].x, 16);
+            if (a.G && half == 0 && col[i] >= 0) a.G[row * a.nf + col[i]] = v;
         }
         __syncwarp();
     }
@@ -371,13 +553,15 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
         if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "angular: neighbour row of %d entries exceeds shared memory", a.cap);
-        auto kern = a.ladder ? angular_edge_kernel<WITH_PHI, true> : angular_edge_kernel<WITH_PHI, false>;
+        auto kern = g.fpl == 4 ? (a.ladder ? angular_edge4_kernel<WITH_PHI, true> : angular_edge4_kernel<WITH_PHI, false>)
+                               : (a.ladder ? angular_edge_kernel<WITH_PHI, true> : angular_edge_kernel<WITH_PHI, false>);
         NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int occ = 1;
         NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
         if (occ < 1) occ = 1;
         int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * occ);
         NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
+        if (const char *env = getenv("NNMD_DBG")) a.dbg = atoi(env);
         ProfScope prof(PROF_ANGULAR, st);
         kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
         NNMD_LAUNCH_CHECK("angular_edge_kernel");

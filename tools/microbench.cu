@@ -36,6 +36,44 @@ __global__ void k_ffma2(float *out, float a, float b) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FFMA2 with three VARYING register-pair operands (the form the angular inner loop uses for q*t + acc)
+__global__ void k_ffma2_3op(float *out, float a, float b) {
+    float2 x[6], y[6], z[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i);
+        y[i] = make_float2(a + i * 1e-4f, a - i * 1e-4f);
+        z[i] = make_float2(b + i * 1e-5f, b - i * 1e-5f);
+    }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = __ffma2_rn(y[i], z[(i + 1) % 6], x[i]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) y[i] = __ffma2_rn(z[i], x[(i + 2) % 6], y[i]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s += x[i].x + x[i].y + y[i].x + y[i].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// scalar FFMA with three varying operands, same dataflow
+__global__ void k_ffma_3op(float *out, float a, float b) {
+    float x[12], y[12], z[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { x[i] = threadIdx.x * 1e-3f + i; y[i] = a + i * 1e-4f; z[i] = b + i * 1e-5f; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) x[i] = fmaf(y[i], z[(i + 1) % 12], x[i]);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) y[i] = fmaf(z[i], x[(i + 2) % 12], y[i]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s += x[i] + y[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __device__ __forceinline__ float ex2(float x) { float r; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 __global__ void k_mufu(float *out, float a) {
@@ -114,10 +152,13 @@ int main() {
     const double t_mufu = time_ms([&] { k_mufu<<<blocks, threads>>>(out, -0.5f); });
     const double t_mixs = time_ms([&] { k_mix_scalar<<<blocks, threads>>>(out, 0.9999f, -0.5f); });
     const double t_mixp = time_ms([&] { k_mix_packed<<<blocks, threads>>>(out, 0.9999f, -0.5f); });
+    const double t_f2_3 = time_ms([&] { k_ffma2_3op<<<blocks, threads>>>(out, 0.999f, 1e-3f); });
+    const double t_f1_3 = time_ms([&] { k_ffma_3op<<<blocks, threads>>>(out, 0.999f, 1e-3f); });
     auto lane_ops = [&](double per_iter, double ms) { return warps * 32.0 * ITERS * per_iter / (ms * 1e-3); };
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_attr\": %d,\n", p.name, sms, clk_khz);
     printf(" \"ffma_lane_ops_per_s\": %.4e, \"ffma_ms\": %.4f,\n", lane_ops(16, t_ffma), t_ffma);
     printf(" \"ffma2_fma_lane_ops_per_s\": %.4e, \"ffma2_ms\": %.4f,\n", lane_ops(16, t_ffma2), t_ffma2);
+    printf(" \"ffma2_3op_fma_lane_ops_per_s\": %.4e, \"ffma_3op_lane_ops_per_s\": %.4e,\n", lane_ops(24, t_f2_3), lane_ops(24, t_f1_3));
     printf(" \"mufu_ex2_lane_ops_per_s\": %.4e, \"mufu_ms\": %.4f,\n", lane_ops(8, t_mufu), t_mufu);
     printf(" \"mix_scalar_14ffma_2mufu_ms\": %.4f, \"mix_packed_7ffma2_2mufu_ms\": %.4f,\n", t_mixs, t_mixp);
     printf(" \"fp32_tflops_ffma\": %.2f, \"fp32_tflops_ffma2\": %.2f}\n", 2e-12 * lane_ops(16, t_ffma), 2e-12 * lane_ops(16, t_ffma2));
