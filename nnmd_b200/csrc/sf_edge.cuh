@@ -38,6 +38,7 @@ struct EdgeArgs {
     uint32_t *flag;
     unsigned long long *row_counter;  // dynamic row scheduling (zeroed before the launch)
     int dbg;                          // profiling knob (NNMD_DBG): 1 = skip phase 2, 2 = skip phase 1 as well
+    int owner_applied;                // K3e already added the owner's own Phi*u terms to dG / force: the gather skips owned edges
 };
 
 // record: per lambda class (EREC_CLASS floats)  [ L0 L1 L2 eid | A0 A1 B0 B1 | A2 B2 V0a V0j | R0 R1 R2 . ]
@@ -273,10 +274,12 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
 
     const float inv_rc = MF::rcp(a.rc), rc2 = a.rc * a.rc;
     const int half = lane >> 4, l16 = lane & 15;
-    float zeta[4], zm1[4];
+    float zeta[4], zm1[4], coef[4];
     int col[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { zeta[i] = a.zeta[4 * l16 + i]; zm1[i] = zeta[i] - 1.f; col[i] = a.col[4 * l16 + i]; }
+    for (int i = 0; i < 4; ++i) {
+        zeta[i] = a.zeta[4 * l16 + i]; zm1[i] = zeta[i] - 1.f; col[i] = a.col[4 * l16 + i]; coef[i] = a.coef[4 * l16 + i];
+    }
     const int class_off = (a.lam[4 * l16] < 0.f) ? EREC_CLASS : 0;  // lambda class of this lane's four functions
     const size_t nfa = size_t(a.nfa);
     const int kind = a.kind;
@@ -303,6 +306,11 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
         float2 phi[4], vg[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { phi[i] = make_float2(0.f, 0.f); vg[i] = phi[i]; }
+        // the owner's own share of dG: sum over its edges of Phi * u (the gather then only visits the other edges)
+        float gox[4], goy[4], goz[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gox[i] = goy[i] = goz[i] = 0.f;
+        int cur_tj = 0;
         // the two half-warps hold partial sums of the same edge: combine, then half 0 writes 16 B per lane
         auto retire = [&](int eid) {
             float ph[4], ga[4];
@@ -311,6 +319,15 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
                 ph[i] = phi[i].x + phi[i].y;
                 ph[i] += __shfl_xor_sync(0xffffffffu, ph[i], 16);
                 ga[i] = vg[i].y + __shfl_xor_sync(0xffffffffu, vg[i].y, 16);
+            }
+            if (WITH_PHI) {
+                const Q4<float> u = ld4<float>(nb.u4 + 4 * cur_tj);
+                const float inv = nb.invd[cur_tj];
+                const float ux = u.a * inv, uy = u.b * inv, uz = u.c * inv;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    gox[i] = fmaf(ph[i], ux, gox[i]); goy[i] = fmaf(ph[i], uy, goy[i]); goz[i] = fmaf(ph[i], uz, goz[i]);
+                }
             }
             if (half == 0) {
                 float *dst = a.E + (size_t(eid) * 2) * nfa + a.ebase + 4 * l16;
@@ -345,6 +362,7 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
                 if ((firsts >> t) & 1u) {  // record t opens the next edge: retire the previous one (warp-uniform)
                     if (cur_eid >= 0) retire(cur_eid);
                     cur_eid = __float_as_int(recs[t * EREC_STRIDE + 3]);
+                    cur_tj = __shfl_sync(0xffffffffu, my_tj, t);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { phi[i] = make_float2(0.f, 0.f); vg[i].y = 0.f; }
                 }
@@ -432,6 +450,25 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
             const float v = vg[i].x + __shfl_xor_sync(0xffffffffu, vg[i].x, 16);
             if (a.G && half == 0 && col[i] >= 0) a.G[row * a.nf + col[i]] = v;
         }
+        if (WITH_PHI) {
+            float fx = 0.f, fy = 0.f, fz = 0.f;
+            if (half == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (col[i] < 0) continue;
+                    const int64_t o = row * a.nf + col[i];
+                    if (a.dG) { a.dG[3 * o] = -coef[i] * gox[i]; a.dG[3 * o + 1] = -coef[i] * goy[i]; a.dG[3 * o + 2] = -coef[i] * goz[i]; }
+                    if (a.force) {
+                        const float wv = a.w[o] * coef[i];
+                        fx = fmaf(wv, gox[i], fx); fy = fmaf(wv, goy[i], fy); fz = fmaf(wv, goz[i], fz);
+                    }
+                }
+            }
+            if (a.force) {
+                fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+                if (lane == 0) { a.force[3 * row] += fx; a.force[3 * row + 1] += fy; a.force[3 * row + 2] += fz; }
+            }
+        }
         __syncwarp();
     }
 }
@@ -472,6 +509,9 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
                 d = norm3<float>(ux, uy, uz);  // the same expression as stage_row: both kernels see the same edge set
                 keep = (d < a.rc) && (d > 0.f);
             }
+            // entries the gather has to visit: all edges, or only those owned by the neighbour when K3e already
+            // applied the centre's own edges
+            if (keep && a.owner_applied && (int(e - o0) - first_gt) >= 0) keep = false;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int p = nn + __popc(m & ((1u << lane) - 1u));
@@ -502,21 +542,27 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
         __syncwarp();
         nn = min(nn, a.cap);
         float gx[2] = {0, 0}, gy[2] = {0, 0}, gz[2] = {0, 0}, gam[2] = {0, 0};
-#pragma unroll 4
-        for (int t = 0; t < nn; ++t) {
-            const float4 u = *reinterpret_cast<const float4 *>(ubuf + 4 * t);
-            const int code = __float_as_int(u.w);
-            const bool owner = code >= 0;
-            const size_t eid = size_t(owner ? code : ~code);
-            const float *src = a.E + (eid * 2) * nfa + a.ebase + 2 * lane;
-            if (MODE != MODE_G) {
-                const float2 ph = __ldg(reinterpret_cast<const float2 *>(src));
-                gx[0] = fmaf(ph.x, u.x, gx[0]); gy[0] = fmaf(ph.x, u.y, gy[0]); gz[0] = fmaf(ph.x, u.z, gz[0]);
-                gx[1] = fmaf(ph.y, u.x, gx[1]); gy[1] = fmaf(ph.y, u.y, gy[1]); gz[1] = fmaf(ph.y, u.z, gz[1]);
+        // batches of 4 edges: issue all loads of a batch before using any (the kernel lives on memory-level parallelism)
+        for (int t0 = 0; t0 < nn; t0 += 4) {
+            float4 u[4];
+            float2 ph[4], ga[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int t = min(t0 + k, nn - 1);
+                u[k] = *reinterpret_cast<const float4 *>(ubuf + 4 * t);
+                const int code = __float_as_int(u[k].w);
+                const bool owner = code >= 0;
+                const size_t eid = size_t(owner ? code : ~code);
+                const float *src = a.E + (eid * 2) * nfa + a.ebase + 2 * lane;
+                ph[k] = (MODE != MODE_G) ? __ldg(reinterpret_cast<const float2 *>(src)) : make_float2(0.f, 0.f);
+                ga[k] = (MODE != MODE_FORCE && !owner) ? __ldg(reinterpret_cast<const float2 *>(src + nfa)) : make_float2(0.f, 0.f);
             }
-            if (MODE != MODE_FORCE && !owner) {
-                const float2 ga = __ldg(reinterpret_cast<const float2 *>(src + nfa));
-                gam[0] += ga.x; gam[1] += ga.y;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (t0 + k >= nn) break;
+                gx[0] = fmaf(ph[k].x, u[k].x, gx[0]); gy[0] = fmaf(ph[k].x, u[k].y, gy[0]); gz[0] = fmaf(ph[k].x, u[k].z, gz[0]);
+                gx[1] = fmaf(ph[k].y, u[k].x, gx[1]); gy[1] = fmaf(ph[k].y, u[k].y, gy[1]); gz[1] = fmaf(ph[k].y, u[k].z, gz[1]);
+                gam[0] += ga[k].x; gam[1] += ga[k].y;
             }
         }
         float fx = 0, fy = 0, fz = 0;
@@ -526,7 +572,8 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
             const int64_t o = row * a.nf + col[i];
             if (MODE != MODE_FORCE) a.G[o] = 0.5f * coef[i] * (a.G[o] + gam[i]);  // ordered (j,k): both edges of a pair counted
             if (MODE == MODE_DG) {
-                const float dx = -coef[i] * gx[i], dy = -coef[i] * gy[i], dz = -coef[i] * gz[i];
+                float dx = -coef[i] * gx[i], dy = -coef[i] * gy[i], dz = -coef[i] * gz[i];
+                if (a.owner_applied) { dx += a.dG[3 * o]; dy += a.dG[3 * o + 1]; dz += a.dG[3 * o + 2]; }
                 a.dG[3 * o] = dx; a.dG[3 * o + 1] = dy; a.dG[3 * o + 2] = dz;
                 bad |= !(isfinite(dx) && isfinite(dy) && isfinite(dz));
             }
@@ -562,6 +609,7 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * occ);
         NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
         if (const char *env = getenv("NNMD_DBG")) a.dbg = atoi(env);
+        a.owner_applied = (g.fpl == 4 && WITH_PHI) ? 1 : 0;
         ProfScope prof(PROF_ANGULAR, st);
         kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
         NNMD_LAUNCH_CHECK("angular_edge_kernel");
