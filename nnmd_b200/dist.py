@@ -37,6 +37,7 @@ class SlabShard:
     owned_pos: torch.Tensor                     # (n_owned, 3) ORIGINAL (unwrapped) positions
     send_idx: list = field(default_factory=list)  # per peer: indices into `owned_*` to send (None: nothing)
     edges: torch.Tensor | None = None           # (world+1,) slab boundaries on the wrapped x axis
+    recv_counts: list | None = None             # atoms each peer sends here; learned once per send plan (no per-step sync)
 
     @property
     def n_owned(self) -> int:
@@ -93,10 +94,12 @@ class SlabShard:
         own = self.owned_pos.to(device)
         if self.world == 1:
             return own
-        counts = torch.tensor([0 if s is None else int(s.numel()) for s in self.send_idx], dtype=torch.int64, device=device)
-        all_counts = [torch.empty_like(counts) for _ in range(self.world)]
-        td.all_gather(all_counts, counts)
-        recv_counts = [int(all_counts[peer][self.rank]) for peer in range(self.world)]
+        if self.recv_counts is None:  # the send plan is fixed between re-decompositions: learn the peers' counts once
+            counts = torch.tensor([0 if s is None else int(s.numel()) for s in self.send_idx], dtype=torch.int64, device=device)
+            all_counts = [torch.empty_like(counts) for _ in range(self.world)]
+            td.all_gather(all_counts, counts)
+            self.recv_counts = [int(all_counts[peer][self.rank]) for peer in range(self.world)]
+        recv_counts = self.recv_counts
         ops, recv_bufs, keep = [], [], []
         for peer in range(self.world):
             if peer == self.rank:
