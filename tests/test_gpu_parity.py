@@ -301,6 +301,56 @@ def test_edge_centric_and_vertex_centric_kernels_agree(monkeypatch):
     assert col_relerr(out["edge"][1], out["vertex"][1], 1) < 1e-5
 
 
+@pytest.mark.parametrize("kind", [4, 5])
+@pytest.mark.parametrize("ladder", [True, False])
+def test_edge_centric_kernel_on_small_multi_frame_input(kind, ladder):
+    """G4 and G5, zeta ladder and arbitrary zetas, 3 frames of a triclinic cluster: the fp32 edge-centric kernels (taken
+    for 33..64 functions) against the fp64 truth on the same wrapped positions, and against the fp64 CUDA path."""
+    from nnmd_b200.features import calculate_params, calculate_sf
+    from nnmd_b200.features.calculate_sf import get_plan, raw_descriptors
+    from nnmd_b200.neighbor import build_neighbor_list
+    from oracle import nl_oracle as O3
+    d, _ = load_case("sf_cluster")
+    if ladder:
+        rows = calculate_params(3.0, 0, 2, 0, 64, 0)[2:]
+        params = [[float(r[0]), float(r[1]), float(r[2]), float(r[3])] for r in rows]
+    else:
+        rng = np.random.default_rng(11)
+        params = [[3.0, 0.15, float(z), float(l)] for z, l in zip(rng.uniform(1, 12, 50), rng.choice([1.0, -1.0], 50))]
+    sfd = {"features": [kind] * len(params) + [1], "params": params + [[3.0]]}
+    cart, cell, pbc = _inputs(d, torch.float32)
+    nl = build_neighbor_list(cart, cell, pbc, 3.0)
+    G, dG, flag = raw_descriptors(get_plan(sfd, torch.float32, cart.device), nl)
+    p64 = nl.posw[:, :3].double().cpu().view(cart.shape)
+    z3 = torch.zeros(3, 3, dtype=torch.float64)
+    G3, dG3, _ = O3.raw_descriptors(p64, z3, torch.zeros(3, dtype=torch.float64), sfd)
+    G3, dG3 = G3.reshape(-1, G3.shape[-1]), dG3.reshape(-1, *dG3.shape[-2:])
+    eg, edg = col_relerr(G.cpu(), G3, 1), col_relerr(dG.cpu(), dG3, 1)
+    print(f"G{kind} ladder={ladder}: fp32 edge-centric G {eg:.2e} dG {edg:.2e}")
+    assert eg < 1e-5 and edg < 1e-5
+    g64, dg64 = calculate_sf(cart.double(), cell.double(), pbc.double(), sfd)   # fp64: vertex-centric kernel
+    g3, dg3 = O3.descriptors(cart.double().cpu(), cell.double().cpu(), pbc.double().cpu(), sfd)
+    assert relerr(g64.cpu(), g3) < 1e-10 and col_relerr(dg64.cpu(), dg3, 2) < 1e-10
+
+
+def test_degenerate_inputs():
+    """Empty batch, a frame without any pair, and a single atom: shapes and the reference's NaN error."""
+    from nnmd_b200.features import calculate_sf
+    from nnmd_b200.neighbor import build_neighbor_list
+    sfd = {"features": [2, 4], "params": [[3.0, 1.0, 0.5], [3.0, 0.1, 2, 1]]}
+    z = torch.zeros(3, 3, device=DEV)
+    p0 = torch.zeros(3, device=DEV)
+    g, dg = calculate_sf(torch.zeros(0, 5, 3, device=DEV), z, p0, sfd)
+    assert g.shape == (0, 5, 2) and dg.shape == (0, 5, 2, 3)
+    nl = build_neighbor_list(torch.tensor([[[0.0, 0, 0], [10.0, 0, 0]]], device=DEV), z, p0, 3.0)
+    assert nl.total == 0 and nl.max_row == 0 and nl.pairs().shape == (0, 3)
+    with pytest.raises(ValueError, match="NaN values in the symmetry functions"):
+        calculate_sf(torch.zeros(1, 1, 3, device=DEV), z, p0, sfd)
+    # two coincident atoms are not neighbours (d > 0), like the reference's mask
+    nl = build_neighbor_list(torch.tensor([[[1.0, 1, 1], [1.0, 1, 1], [2.0, 1, 1]]], device=DEV), z, p0, 3.0)
+    assert nl.pairs().cpu().tolist() == [[0, 0, 2], [0, 1, 2], [0, 2, 0], [0, 2, 1]]
+
+
 def test_spatial_shards_reproduce_the_single_gpu_result():
     """Two x-slab shards with halo (emulated on one GPU: the exchange is replaced by indexing the peer's send list)
     give the same per-atom energies and forces as the unsharded evaluation; the edge ownership rule must cope with
