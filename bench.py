@@ -343,7 +343,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=63, help="fcc conventional cells per edge (63 -> 1,000,188 atoms)")
     ap.add_argument("--mode", default="materialize", choices=["materialize", "fused"])
-    ap.add_argument("--mlp", default="exact", choices=["exact", "tf32"])
+    ap.add_argument("--mlp", default="auto", choices=["auto", "exact", "tf32"],
+                    help="atomic MLP kernel: auto = tensor cores (3xTF32, parity-tested to 1e-5) when the shape allows")
     ap.add_argument("--ref-cells", type=int, default=3, help="reference arm sample: cells per edge (3 -> 108 atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tri-per-atom", type=float, default=1350.0,

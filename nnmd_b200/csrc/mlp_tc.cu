@@ -1,9 +1,200 @@
-// mlp_tc.cu -- tensor-core (TF32) variant of K6.  Placeholder until the mma path lands.
+// mlp_tc.cu -- tensor-core variant of K6 (NNMD_MLP_TF32): e = MLP(x) and dE/dx for two-hidden-layer atomic networks.
+//
+// Replaces nnmd/nn/atomic_nn.py:43-48 + the autograd.grad of nnmd/nn/bpnn.py:347-349 like mlp.cu does, but runs the four
+// dense contractions (two forward, two backward) on the tensor cores with TF32 operands and fp32 accumulation.
+// Plain TF32 (10-bit mantissa) cannot meet the 1e-5 fp32 parity bar, so every product is error-compensated
+// ("3xTF32"): a = a_hi + a_lo, b = b_hi + b_lo, a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, three MMAs per tile.
+//
+// One warp owns 16 atoms and never leaves registers between layers: the accumulator fragment of layer l (rows g, g+8;
+// columns 2t, 2t+1 of an 8-wide tile) IS the A fragment of layer l+1 once the k-slots of that MMA are read as
+// (slot t -> neuron 8j+2t, slot t+4 -> neuron 8j+2t+1); the B fragments are laid out in shared memory to match, already
+// split into hi/lo, one 16 B load per (k-step, n-tile, lane).  The backward sweep reuses the same trick with the
+// transposed weight fragments.  Shapes are template parameters (tiles of 8): <input tiles, hidden-1 tiles, hidden-2 tiles>.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nnmd {
-int mlp_tf32_run(int, const int32_t *, const void *const *, const void *const *, const void *, int64_t, void *, void *,
-                 cudaStream_t) {
-    return set_err(NNMD_ERR_INVALID, "mlp: TF32 tensor-core path is not built in this revision");
+
+struct TcArgs {
+    const float *W0, *b0, *W1, *b1, *W2, *b2;  // W0 (H1,K0)  W1 (H2,H1)  W2 (1,H2), torch.nn.Linear layout
+    int K0, H1, H2;
+    const float *x;
+    int64_t n_rows;
+    float *e, *dEdx;
+};
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const float (&a)[4], float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
+
+// c[NT][4] += A (16 x 8*KT, fragments a[KT][4]) * B, B fragments at bf[(j*NT + i)*32 + lane] = (b0_hi, b1_hi, b0_lo, b1_lo)
+template <int KT, int NT>
+__device__ __forceinline__ void gemm3x(float (&c)[NT][4], const float (&a)[KT][4], const float4 *__restrict__ bf, int lane) {
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        float ah[4], al[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { ah[r] = tf32_hi(a[j][r]); al[r] = a[j][r] - ah[r]; }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const float4 b = bf[(j * NT + i) * 32 + lane];
+            mma_tf32(c[i], al, b.x, b.y);
+            mma_tf32(c[i], ah, b.z, b.w);
+            mma_tf32(c[i], ah, b.x, b.y);
+        }
+    }
+}
+
+// Fill B fragments for out[m][n] = sum_k in[m][k] * Wsrc(k, n):  element (k, n) = W[n*ld_n + k*ld_k] (zero outside kmax, nmax)
+__device__ __forceinline__ void fill_frags(float4 *dst, const float *W, int ld_n, int ld_k, int KT, int NT, int kmax, int nmax) {
+    for (int idx = threadIdx.x; idx < KT * NT * 32; idx += blockDim.x) {
+        const int lane = idx & 31, tile = idx >> 5, i = tile % NT, j = tile / NT;
+        const int g = lane >> 2, t = lane & 3;
+        const int n = 8 * i + g, k0 = 8 * j + 2 * t, k1 = k0 + 1;
+        const float v0 = (n < nmax && k0 < kmax) ? __ldg(W + size_t(n) * ld_n + size_t(k0) * ld_k) : 0.f;
+        const float v1 = (n < nmax && k1 < kmax) ? __ldg(W + size_t(n) * ld_n + size_t(k1) * ld_k) : 0.f;
+        const float h0 = tf32_hi(v0), h1 = tf32_hi(v1);
+        dst[idx] = make_float4(h0, h1, v0 - h0, v1 - h1);
+    }
+}
+
+template <int K0T, int H1T, int H2T>
+__global__ void __launch_bounds__(256, 1) mlp_tc_kernel(TcArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *f_fwd0 = reinterpret_cast<float4 *>(smem_raw);   // x  (K0) -> z1 (H1):  k = input feature, n = neuron of layer 0
+    float4 *f_fwd1 = f_fwd0 + K0T * H1T * 32;                 // h1 (H1) -> z2 (H2)
+    float4 *f_bwd1 = f_fwd1 + H1T * H2T * 32;                 // d2 (H2) -> g1 (H1):  k = neuron of layer 1, n = neuron of layer 0 output
+    float4 *f_bwd0 = f_bwd1 + H2T * H1T * 32;                 // d1 (H1) -> dE/dx (K0)
+    float *bias0 = reinterpret_cast<float *>(f_bwd0 + H1T * K0T * 32);
+    float *bias1 = bias0 + 8 * H1T;
+    float *w2 = bias1 + 8 * H2T;
+    // forward: element (k, n) = W[n][k]; backward: element (k = out neuron, n = in feature) = W[k][n]
+    fill_frags(f_fwd0, a.W0, a.K0, 1, K0T, H1T, a.K0, a.H1);
+    fill_frags(f_fwd1, a.W1, a.H1, 1, H1T, H2T, a.H1, a.H2);
+    fill_frags(f_bwd1, a.W1, 1, a.H1, H2T, H1T, a.H2, a.H1);
+    fill_frags(f_bwd0, a.W0, 1, a.K0, H1T, K0T, a.H1, a.K0);
+    for (int i = threadIdx.x; i < 8 * H1T; i += blockDim.x) bias0[i] = i < a.H1 ? __ldg(a.b0 + i) : 0.f;
+    for (int i = threadIdx.x; i < 8 * H2T; i += blockDim.x) { bias1[i] = i < a.H2 ? __ldg(a.b1 + i) : 0.f; w2[i] = i < a.H2 ? __ldg(a.W2 + i) : 0.f; }
+    __syncthreads();
+    const float b2 = __ldg(a.b2);
+    const int lane = lane_id(), warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int64_t n_groups = (a.n_rows + 15) / 16;
+    for (int64_t grp = int64_t(blockIdx.x) * 8 + warp; grp < n_groups; grp += int64_t(gridDim.x) * 8) {
+        const int64_t r0 = grp * 16 + g, r1 = r0 + 8;
+        const bool v0 = r0 < a.n_rows, v1 = r1 < a.n_rows;
+        // ---- x as A fragments
+        float xa[K0T][4];
+#pragma unroll
+        for (int j = 0; j < K0T; ++j) {
+            const int k = 8 * j + 2 * t;
+            xa[j][0] = (v0 && k < a.K0) ? __ldg(a.x + r0 * a.K0 + k) : 0.f;
+            xa[j][2] = (v0 && k + 1 < a.K0) ? __ldg(a.x + r0 * a.K0 + k + 1) : 0.f;
+            xa[j][1] = (v1 && k < a.K0) ? __ldg(a.x + r1 * a.K0 + k) : 0.f;
+            xa[j][3] = (v1 && k + 1 < a.K0) ? __ldg(a.x + r1 * a.K0 + k + 1) : 0.f;
+        }
+        // ---- layer 0
+        float h1[H1T][4];
+#pragma unroll
+        for (int i = 0; i < H1T; ++i) { h1[i][0] = h1[i][2] = bias0[8 * i + 2 * t]; h1[i][1] = h1[i][3] = bias0[8 * i + 2 * t + 1]; }
+        gemm3x<K0T, H1T>(h1, xa, f_fwd0, lane);
+        // accumulator (row g: c0 c1 | row g+8: c2 c3) -> A fragment (a0 = row g slot t, a1 = row g+8 slot t, a2 = row g slot t+4, a3 = row g+8 slot t+4)
+#pragma unroll
+        for (int i = 0; i < H1T; ++i) {
+            const float s0 = 1.f / (1.f + expf(-h1[i][0])), s1 = 1.f / (1.f + expf(-h1[i][1]));
+            const float s2 = 1.f / (1.f + expf(-h1[i][2])), s3 = 1.f / (1.f + expf(-h1[i][3]));
+            h1[i][0] = s0; h1[i][1] = s2; h1[i][2] = s1; h1[i][3] = s3;
+        }
+        // ---- layer 1
+        float h2[H2T][4];
+#pragma unroll
+        for (int i = 0; i < H2T; ++i) { h2[i][0] = h2[i][2] = bias1[8 * i + 2 * t]; h2[i][1] = h2[i][3] = bias1[8 * i + 2 * t + 1]; }
+        gemm3x<H1T, H2T>(h2, h1, f_fwd1, lane);
+        // ---- output layer (one neuron) on the FMA pipe, and d2 = w2 * h2 (1 - h2) in A-fragment order
+        float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < H2T; ++i) {
+            const float wa = w2[8 * i + 2 * t], wb = w2[8 * i + 2 * t + 1];
+            const float s0 = 1.f / (1.f + expf(-h2[i][0])), s1 = 1.f / (1.f + expf(-h2[i][1]));
+            const float s2 = 1.f / (1.f + expf(-h2[i][2])), s3 = 1.f / (1.f + expf(-h2[i][3]));
+            e0 = fmaf(wa, s0, fmaf(wb, s1, e0));
+            e1 = fmaf(wa, s2, fmaf(wb, s3, e1));
+            h2[i][0] = wa * s0 * (1.f - s0); h2[i][2] = wb * s1 * (1.f - s1);
+            h2[i][1] = wa * s2 * (1.f - s2); h2[i][3] = wb * s3 * (1.f - s3);
+        }
+        e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
+        e1 += __shfl_xor_sync(0xffffffffu, e1, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+        if (t == 0) {
+            if (v0) a.e[r0] = e0 + b2;
+            if (v1) a.e[r1] = e1 + b2;
+        }
+        if (a.dEdx) {
+            // ---- g1 = d2 W1, d1 = g1 * h1 (1 - h1)
+            float d1[H1T][4];
+#pragma unroll
+            for (int i = 0; i < H1T; ++i) d1[i][0] = d1[i][1] = d1[i][2] = d1[i][3] = 0.f;
+            gemm3x<H2T, H1T>(d1, h2, f_bwd1, lane);
+#pragma unroll
+            for (int i = 0; i < H1T; ++i) {
+                // d1 is an accumulator (c0 c1 | c2 c3), h1 already sits in A-fragment order (a0 a1 a2 a3) = (c0 c2 c1 c3)
+                const float q0 = d1[i][0] * h1[i][0] * (1.f - h1[i][0]), q1 = d1[i][1] * h1[i][2] * (1.f - h1[i][2]);
+                const float q2 = d1[i][2] * h1[i][1] * (1.f - h1[i][1]), q3 = d1[i][3] * h1[i][3] * (1.f - h1[i][3]);
+                d1[i][0] = q0; d1[i][1] = q2; d1[i][2] = q1; d1[i][3] = q3;
+            }
+            // ---- dE/dx = d1 W0
+            float gx[K0T][4];
+#pragma unroll
+            for (int i = 0; i < K0T; ++i) gx[i][0] = gx[i][1] = gx[i][2] = gx[i][3] = 0.f;
+            gemm3x<H1T, K0T>(gx, d1, f_bwd0, lane);
+#pragma unroll
+            for (int i = 0; i < K0T; ++i) {
+                const int k = 8 * i + 2 * t;
+                if (v0 && k < a.K0) a.dEdx[r0 * a.K0 + k] = gx[i][0];
+                if (v0 && k + 1 < a.K0) a.dEdx[r0 * a.K0 + k + 1] = gx[i][1];
+                if (v1 && k < a.K0) a.dEdx[r1 * a.K0 + k] = gx[i][2];
+                if (v1 && k + 1 < a.K0) a.dEdx[r1 * a.K0 + k + 1] = gx[i][3];
+            }
+        }
+    }
+}
+
+template <int K0T, int H1T, int H2T>
+static int tc_launch(const TcArgs &a, cudaStream_t st) {
+    const size_t smem = size_t(K0T * H1T + H1T * H2T + H2T * H1T + H1T * K0T) * 32 * sizeof(float4) + size_t(8 * H1T + 16 * H2T) * sizeof(float);
+    if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "mlp(tf32): weights need %zu B of shared memory", smem);
+    auto kern = mlp_tc_kernel<K0T, H1T, H2T>;
+    NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int occ = 1;
+    NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+    if (occ < 1) occ = 1;
+    const int64_t n_groups = (a.n_rows + 15) / 16;
+    const int64_t blocks = std::min<int64_t>((n_groups + 7) / 8, int64_t(sm_count()) * occ);
+    ProfScope prof(PROF_MLP, st);
+    kern<<<unsigned(blocks), 256, smem, st>>>(a);
+    NNMD_LAUNCH_CHECK("mlp_tc_kernel");
+    return NNMD_OK;
+}
+
+int mlp_tf32_run(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases, const void *x,
+                 int64_t n_rows, void *e, void *dEdx, cudaStream_t st) {
+    if (n_layers != 3) return set_err(NNMD_ERR_INVALID, "mlp(tf32): the tensor-core path covers networks with two hidden layers");
+    TcArgs a;
+    a.W0 = (const float *)weights[0]; a.b0 = (const float *)biases[0];
+    a.W1 = (const float *)weights[1]; a.b1 = (const float *)biases[1];
+    a.W2 = (const float *)weights[2]; a.b2 = (const float *)biases[2];
+    a.K0 = sizes[0]; a.H1 = sizes[1]; a.H2 = sizes[2];
+    a.x = (const float *)x; a.n_rows = n_rows; a.e = (float *)e; a.dEdx = (float *)dEdx;
+    const int k0t = (a.K0 + 7) / 8, h1t = (a.H1 + 7) / 8, h2t = (a.H2 + 7) / 8;
+    if (k0t <= 2 && h1t <= 4 && h2t <= 4) return tc_launch<2, 4, 4>(a, st);     // e.g. LJ 3-25-25-1
+    if (k0t <= 2 && h1t <= 8 && h2t <= 8) return tc_launch<2, 8, 8>(a, st);     // e.g. Li 14-64-64-1
+    if (k0t <= 7 && h1t <= 8 && h2t <= 8) return tc_launch<7, 8, 8>(a, st);     // up to 56 descriptors
+    if (k0t <= 12 && h1t <= 8 && h2t <= 8) return tc_launch<12, 8, 8>(a, st);   // the 96-function bench table
+    return set_err(NNMD_ERR_CAPACITY, "mlp(tf32): shape %d-%d-%d-1 has no tensor-core instantiation", a.K0, a.H1, a.H2);
+}
+
 }  // namespace nnmd

@@ -58,7 +58,7 @@ def fused_force(plan: SfPlan, nl: NeighborList, w: torch.Tensor) -> torch.Tensor
 
 
 def energy_forces(cart: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, symm_funcs_data: dict, net,
-                  mode: str = "materialize", mlp_precision: str = "exact", n_centres: int | None = None,
+                  mode: str = "materialize", mlp_precision: str = "auto", n_centres: int | None = None,
                   check: bool = True) -> EvalResult:
     """Evaluate one species: cart (B,N,3) on the GPU -> energies and reference-semantic forces."""
     _lib.require_cuda()

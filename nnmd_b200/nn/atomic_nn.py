@@ -54,8 +54,16 @@ class AtomicNN(nn.Module):
     def layer_sizes(self) -> list[int]:
         return [self.model[0].in_features] + [m.out_features for m in self.model]
 
-    def energy_and_grad(self, x: torch.Tensor, need_grad: bool = True, precision: str = "exact"):
-        """K6: per-atom energies e (..., 1) and dE/dx (..., F) for x (..., F) on the GPU; no autograd graph."""
+    def tensor_core_shape(self) -> bool:
+        """True when csrc/mlp_tc.cu has an instantiation for this network (two hidden layers, <= 96 inputs, <= 64 wide)."""
+        s = self.layer_sizes()
+        return len(s) == 4 and s[3] == 1 and s[0] <= 96 and s[1] <= 64 and s[2] <= 64
+
+    def energy_and_grad(self, x: torch.Tensor, need_grad: bool = True, precision: str = "auto"):
+        """K6: per-atom energies e (..., 1) and dE/dx (..., F) for x (..., F) on the GPU; no autograd graph.
+
+        precision: "exact" = fp32/fp64 FMA kernels; "tf32" = tensor cores with 3xTF32 error compensation (fp32 only,
+        ~2e-6 relative); "auto" = "tf32" when the data is fp32 and the shape has a tensor-core instantiation."""
         if self.activation is not torch.sigmoid:
             raise NotImplementedError("the CUDA atomic network implements the reference's sigmoid activation only")
         _lib.require_cuda()
@@ -74,6 +82,8 @@ class AtomicNN(nn.Module):
         c_sizes = (ctypes.c_int32 * (L + 1))(*sizes)
         c_w = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
         c_b = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
+        if precision == "auto":
+            precision = "tf32" if (dtype == torch.float32 and self.tensor_core_shape()) else "exact"
         prec = {"exact": _lib.MLP_EXACT, "tf32": _lib.MLP_TF32}[precision]
         with torch.cuda.device(x.device):
             _lib.check(lib.nnmd_mlp_energy_grad(_lib.dtype_code(dtype), prec, L, c_sizes, c_w, c_b, _lib.ptr(x2), n_rows,

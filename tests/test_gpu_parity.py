@@ -177,6 +177,26 @@ def test_mlp_energy_force_against_reference(dtype, tol_e, tol_f):
     assert float((f.cpu() - torch.tensor(d["f_nn"])).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("F,hidden,rows", [(96, [64, 64], 1000), (14, [64, 64], 77), (3, [25, 25], 16), (50, [40, 17], 333)])
+def test_tensor_core_mlp_matches_exact_path(F, hidden, rows):
+    """NNMD_MLP_TF32 (mma.sync TF32 with 3xTF32 error compensation) against the exact fp32 kernel and the fp64 truth."""
+    from nnmd_b200.nn import AtomicNN
+    from oracle import dense_oracle as O2
+    torch.manual_seed(F)
+    net = AtomicNN(F, hidden).to(DEV)
+    x = torch.rand(rows, F, device=DEV)
+    x = x / x.norm(dim=-1, keepdim=True)
+    e_t, d_t = net.energy_and_grad(x, precision="tf32")
+    e_x, d_x = net.energy_and_grad(x, precision="exact")
+    Ws = [m.weight.detach().double().cpu() for m in net.model]
+    bs = [m.bias.detach().double().cpu() for m in net.model]
+    e_o, dE_o, _ = O2.energy_force(x.double().cpu(), torch.zeros(rows, F, 3, dtype=torch.float64), Ws, bs)
+    print(f"{F}-{hidden}: tf32x3 e {relerr(e_t.cpu(), e_o):.2e} dE {relerr(d_t.cpu(), dE_o):.2e} | exact e {relerr(e_x.cpu(), e_o):.2e} dE {relerr(d_x.cpu(), dE_o):.2e}")
+    assert relerr(e_t.cpu(), e_o) < 1e-5 and relerr(d_t.cpu(), dE_o) < 1e-5
+    e_only, none = net.energy_and_grad(x, need_grad=False, precision="tf32")
+    assert none is None and torch.equal(e_only, e_t)
+
+
 @pytest.mark.parametrize("mode", ["materialize", "fused"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_engine_energy_forces(mode, dtype):
