@@ -13,6 +13,9 @@
 //   posw   (n_total,4) working dtype        wrapped positions, 16 B (fp32) / 32 B (fp64) per atom
 //   ws     header | cell_start | cursor | cell_of | order | spos (cell-sorted copy of posw) | counts | scan scratch
 //   offsets int64 (n_rows+1), idx int32 (total pairs, global atom indices)
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace nnmd {
@@ -401,6 +404,167 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
     }
 }
 
+// ------------------------------------------------------------------ K1, cell-tiled form
+// One CTA per occupied cell: the candidates of its 9 z-runs (27 cells) are staged ONCE in shared memory and shared by
+// every atom of the cell, instead of every atom streaming ~600 candidate positions through L2 on its own
+// (that form, nlist_rows_kernel above, is L2-bound and remains the path for cells whose candidate set does not fit).
+constexpr int CELL_MCAND = 1536;
+constexpr int CELL_WARPS = 4;
+
+template <typename T> __device__ __forceinline__ void load_pos_smem(const T *p, int i, T &x, T &y, T &z);
+template <> __device__ __forceinline__ void load_pos_smem<float>(const float *p, int i, float &x, float &y, float &z) {
+    const float4 v = *(reinterpret_cast<const float4 *>(p) + i);
+    x = v.x; y = v.y; z = v.z;
+}
+template <> __device__ __forceinline__ void load_pos_smem<double>(const double *p, int i, double &x, double &y, double &z) {
+    const double2 a = *(reinterpret_cast<const double2 *>(p) + 2 * i), b = *(reinterpret_cast<const double2 *>(p) + 2 * i + 1);
+    x = a.x; y = a.y; z = b.x;
+}
+
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__restrict__ spos, int64_t n_frames, int64_t n_atoms,
+                                                                     int64_t n_centres, int64_t cap, const GridHdr *__restrict__ h,
+                                                                     const int *__restrict__ cell_start, const int *__restrict__ order,
+                                                                     T rc, int *__restrict__ counts, int *__restrict__ ecounts,
+                                                                     const int64_t *__restrict__ offsets, int max_row,
+                                                                     int32_t *__restrict__ idx, unsigned long long *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char cell_smem[];
+    T *cpos = reinterpret_cast<T *>(cell_smem);                                  // CELL_MCAND x 4
+    int *cidx = reinterpret_cast<int *>(cpos + 4 * CELL_MCAND);                  // CELL_MCAND global atom indices
+    int *rowbuf = cidx + CELL_MCAND;                                             // FILL: CELL_WARPS x max_row
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int ncx = h->nc[0], ncy = h->nc[1], ncz = h->nc[2];
+    const int64_t ncell = h->ncell;
+    int *buf = FILL ? rowbuf + size_t(warp) * max_row : nullptr;
+    for (int64_t cid = blockIdx.x; cid < n_frames * ncell; cid += gridDim.x) {
+        const int64_t frame = cid / ncell;
+        const int c = int(cid - frame * ncell);
+        const int64_t fbase = frame * cap;
+        const int a0 = cell_start[fbase + c], a1 = cell_start[fbase + c + 1];
+        if (a0 == a1) continue;  // empty cell (block-uniform)
+        const int cz = c % ncz, cy = (c / ncz) % ncy, cx = c / (ncz * ncy);
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, ncz - 1);
+        // the 9 runs and their total
+        int rs0[9], rlen[9], nrun = 0, M = 0;
+        for (int ix = max(cx - 1, 0); ix <= min(cx + 1, ncx - 1); ++ix)
+            for (int iy = max(cy - 1, 0); iy <= min(cy + 1, ncy - 1); ++iy) {
+                const int64_t cb = fbase + (int64_t(ix) * ncy + iy) * ncz;
+                const int s0 = cell_start[cb + z0], s1 = cell_start[cb + z1 + 1];
+                rs0[nrun] = s0; rlen[nrun] = s1 - s0; M += s1 - s0; ++nrun;
+            }
+        const bool staged = M <= CELL_MCAND;
+        if (staged) {
+            int off = 0;
+            for (int r = 0; r < nrun; ++r) {
+                for (int k = threadIdx.x; k < rlen[r]; k += blockDim.x) {
+                    T x, y, z;
+                    load_pos<T>(spos, rs0[r] + k, x, y, z);
+                    T *o = cpos + 4 * (off + k);
+                    o[0] = x; o[1] = y; o[2] = z; o[3] = T(0);
+                    cidx[off + k] = order[rs0[r] + k];
+                }
+                off += rlen[r];
+            }
+        }
+        __syncthreads();
+        for (int s = a0 + warp; s < a1; s += CELL_WARPS) {
+            const int64_t gi = order[s];
+            const int64_t local = gi - frame * n_atoms;
+            if (local >= n_centres) continue;  // halo atoms are neighbours, never centres (warp-uniform)
+            const int64_t row = frame * n_centres + local;
+            T xi, yi, zi;
+            load_pos<T>(spos, s, xi, yi, zi);
+            int n_found = 0, n_gt = 0;
+            if (staged) {
+                for (int jb = 0; jb < M; jb += 32) {
+                    const int j = jb + lane;
+                    bool ok = false;
+                    int gj = 0;
+                    if (j < M) {
+                        T xj, yj, zj;
+                        load_pos_smem<T>(cpos, j, xj, yj, zj);
+                        ok = is_pair<T>(xi, yi, zi, xj, yj, zj, rc);
+                        gj = cidx[j];
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (FILL) {
+                        if (ok) {
+                            const int p = n_found + __popc(m & ((1u << lane) - 1u));
+                            if (p < max_row) buf[p] = gj;
+                        }
+                    } else {
+                        n_gt += __popc(__ballot_sync(0xffffffffu, ok && int64_t(gj) > gi));
+                    }
+                    n_found += __popc(m);
+                }
+            } else {
+                for (int r = 0; r < nrun; ++r) {
+                    const int s0 = rs0[r], s1 = rs0[r] + rlen[r];
+                    for (int sb = s0; sb < s1; sb += 32) {
+                        const int q = sb + lane;
+                        bool ok = false;
+                        int gj = 0;
+                        if (q < s1) {
+                            T xj, yj, zj;
+                            load_pos<T>(spos, q, xj, yj, zj);
+                            ok = is_pair<T>(xi, yi, zi, xj, yj, zj, rc);
+                            gj = order[q];
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, ok);
+                        if (FILL) {
+                            if (ok) {
+                                const int p = n_found + __popc(m & ((1u << lane) - 1u));
+                                if (p < max_row) buf[p] = gj;
+                            }
+                        } else {
+                            n_gt += __popc(__ballot_sync(0xffffffffu, ok && int64_t(gj) > gi));
+                        }
+                        n_found += __popc(m);
+                    }
+                }
+            }
+            if (!FILL) {
+                if (lane == 0) {
+                    counts[row] = n_found;
+                    ecounts[row] = n_gt;
+                    atomicMax(&stats[1], (unsigned long long)n_found);
+                }
+            } else {
+                __syncwarp();
+                const int n = min(n_found, max_row);
+                const int64_t o = offsets[row];
+                for (int e = lane; e < n; e += 32) {  // rank sort (unique indices -> ranks are a permutation)
+                    const int v = buf[e];
+                    int rk = 0;
+                    for (int t = 0; t < n; ++t) rk += (buf[t] < v);
+                    idx[o + rk] = v;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, bool FILL>
+static int launch_cell_kernel(const T *spos, int64_t n_frames, int64_t n_atoms, int64_t n_centres, int64_t cap, const GridHdr *h,
+                              const int *cell_start, const int *order, T rc, int *counts, int *ecounts, const int64_t *offsets,
+                              int max_row, int32_t *idx, unsigned long long *stats, cudaStream_t st) {
+    const size_t smem = size_t(CELL_MCAND) * (4 * sizeof(T) + sizeof(int)) + (FILL ? size_t(CELL_WARPS) * max_row * sizeof(int) : 0);
+    if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "neighbour row of %d entries exceeds shared memory", max_row);
+    auto kern = nlist_cell_kernel<T, FILL>;
+    NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int occ = 1;
+    NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CELL_WARPS * 32, smem));
+    if (occ < 1) occ = 1;
+    int64_t blocks = std::min<int64_t>(n_frames * std::max<int64_t>(cap, 1), int64_t(sm_count()) * occ * 4);
+    if (blocks < 1) blocks = 1;
+    kern<<<unsigned(blocks), CELL_WARPS * 32, smem, st>>>(spos, n_frames, n_atoms, n_centres, cap, h, cell_start, order, rc, counts,
+                                                         ecounts, offsets, max_row, idx, stats);
+    NNMD_LAUNCH_CHECK("nlist_cell_kernel");
+    return NNMD_OK;
+}
+
 }  // namespace nnmd
 
 using namespace nnmd;
@@ -439,6 +603,11 @@ extern "C" int nnmd_wrap_positions(int dtype, const void *pos, int64_t n_total, 
     }
     NNMD_LAUNCH_CHECK("wrap_kernel");
     return NNMD_OK;
+}
+
+static bool use_cell_kernel() {
+    const char *env = getenv("NNMD_NLIST_ROWS");  // tuning knob: 1 = per-atom traversal (the first form of K1)
+    return !(env && env[0] == '1');
 }
 
 template <typename T>
@@ -484,7 +653,11 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
     NNMD_CUDA_CHECK(cudaMemsetAsync(cursor, 0, 4 * (L.ncells_total + 1), st));
     bin_fill_kernel<T><<<ablocks, 256, 0, st>>>(posw, n_total, n_atoms, L.cap, cell_of, cell_start, cursor, order, spos);
     NNMD_LAUNCH_CHECK("bin_fill_kernel");
-    {
+    if (use_cell_kernel()) {
+        rcode = launch_cell_kernel<T, false>(spos, n_frames, n_atoms, n_centres, L.cap, h, cell_start, order, T(rc), counts,
+                                             ecounts, nullptr, 0, nullptr, (unsigned long long *)stats, st);
+        if (rcode) return rcode;
+    } else {
         const int wpb = 8;
         int64_t blocks = (n_rows + wpb - 1) / wpb;
         if (blocks > int64_t(sms) * 16) blocks = int64_t(sms) * 16;
@@ -516,6 +689,11 @@ static int nlist_fill_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int
     const int *cell_of = (const int *)(ws + L.off_cell_of);
     const int *order = (const int *)(ws + L.off_order);
     const T *spos = (const T *)(ws + L.off_spos);
+    if (use_cell_kernel()) {
+        ProfScope prof(PROF_NLIST, st);
+        return launch_cell_kernel<T, true>(spos, n_frames, n_atoms, n_centres, L.cap, h, cell_start, order, T(rc), nullptr, nullptr,
+                                           offsets, int(max_row), idx, nullptr, st);
+    }
     int wpb = 8;
     while (wpb > 1 && size_t(wpb) * max_row * 4 > 160 * 1024) wpb >>= 1;
     const size_t smem = size_t(wpb) * max_row * 4;
