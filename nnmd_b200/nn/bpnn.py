@@ -7,6 +7,8 @@ Deviations from the reference, all of them places where the reference raises as 
     (bpnn.py:529-531).  Here pbc defaults to `self.pbc` when `config` received one, else all-False for a
     zero-determinant cell and all-True otherwise.
   * `fit` works without the DEBUG environment variable and without installed package metadata.
+  * Two or more species: the training step concatenates species along the atom axis (the reference's dim-0
+    concatenation raises a shape error there); descriptors stay per-species isolated like the reference's (Q9).
   * The training step does not build a torch graph through the MLP: forward (K6) and the double backward (K7) are
     CUDA kernels behind two autograd Functions; `retain_graph=True` and the `.grad` accumulation on the cached
     descriptors (SURVEY 3.2 notes ii, iii) have no counterpart.
@@ -166,7 +168,12 @@ class BPNN(torch.nn.Module):
             e_spec, dE = self.atomic_nets[i].energy_and_grad_autograd(g[spec])
             e_nn.append(e_spec)
             f_nn.append(autograd_force_contract(dE, dG[spec]))
-        return torch.cat(e_nn, dim=0), torch.cat(f_nn, dim=0)
+        # The reference concatenates the species along dim 0 (bpnn.py:357-358), which for batched (B, N_s, .) tensors
+        # stacks species on the FRAME axis and fails against (B,1) energies as soon as there are two species
+        # (SURVEY Q9).  One species: identical.  Several species: atoms are concatenated along the atom axis, so that
+        # e.sum(1) is the frame energy and f matches the (B, N_total, 3) reference forces in species order.
+        cat_dim = 0 if len(e_nn) == 1 else 1
+        return torch.cat(e_nn, dim=cat_dim), torch.cat(f_nn, dim=cat_dim)
 
     # ------------------------------------------------------------------------------------------------ loops
     def _run_epoch(self, loader, train: bool, desc: str):

@@ -90,3 +90,40 @@ def test_train_loop_reproduces_reference_run(opt):
         assert np.abs(v.cpu().numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), k
     e_l, f_l, l = net._validate(0, loader)
     np.testing.assert_allclose([e_l.item(), f_l.item(), l.item()], d[f"val_{opt}"], rtol=2e-3)
+
+
+def test_two_species_step_matches_torch_autograd():
+    """Two species: atoms are concatenated along the atom axis (the reference's dim-0 concatenation raises there)."""
+    from nnmd_b200.nn import BPNN
+    torch.manual_seed(9)
+    dt = torch.float64
+    B, NA, NB, F = 4, 5, 7, 6
+    net = BPNN(dtype=dt)
+    net.config(dict(atom_species=["A", "B"], input_sizes=[F, F], hidden_sizes=[[8, 4], [6, 6]], learning_rate=0.01,
+                    l2_regularization=0.0, e_loss_coeff=1.0, f_loss_coeff=0.5, load_models=False, path="", optimizer="adam",
+                    batch_size=B, epochs=1))
+    for an in net.atomic_nets:
+        an.to(dt)
+    g = {"A": torch.rand(B, NA, F, device=DEV, dtype=dt), "B": torch.rand(B, NB, F, device=DEV, dtype=dt)}
+    dG = {"A": torch.randn(B, NA, F, 3, device=DEV, dtype=dt), "B": torch.randn(B, NB, F, 3, device=DEV, dtype=dt)}
+    E = torch.rand(B, 1, device=DEV, dtype=dt)
+    Fr = torch.randn(B, NA + NB, 3, device=DEV, dtype=dt)
+    e, f = net._energies_forces(g, dG)
+    assert e.shape == (B, NA + NB, 1) and f.shape == (B, NA + NB, 3)
+    loss, _, _ = net._loss(e.sum(dim=1), E, f, Fr)
+    params = [p for an in net.atomic_nets for p in an.parameters()]
+    grads = torch.autograd.grad(loss, params)
+    # torch reference
+    es, fs = [], []
+    for i, s in enumerate(["A", "B"]):
+        x = g[s].detach().clone().requires_grad_(True)
+        ei = net.atomic_nets[i](x)
+        dE = torch.autograd.grad(ei.sum(), x, create_graph=True)[0]
+        es.append(ei)
+        fs.append(-torch.einsum("ijk,ijkl->ijl", dE, dG[s]))
+    e0, f0 = torch.cat(es, dim=1), torch.cat(fs, dim=1)
+    loss0 = torch.mean((e0.sum(dim=1) - E) ** 2) + 0.5 / 3 * torch.mean((f0 - Fr) ** 2)
+    grads0 = torch.autograd.grad(loss0, params)
+    assert abs(float(loss - loss0)) < 1e-12 * abs(float(loss0)) + 1e-14
+    for a, b in zip(grads, grads0):
+        assert relerr(a.cpu(), b.cpu()) < 1e-10
