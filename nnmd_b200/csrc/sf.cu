@@ -137,8 +137,7 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
             if (n > 0 && hi - lo <= 2e-6) { g.ladder = 1; g.ladder_step = sum / n; }
         }
         const char *no_edge = getenv("NNMD_NO_EDGE");  // tuning knob
-        g.edge_path = (dtype == NNMD_F32 && pm1 && ((fpl == 2 && g.lanes == 32) || (fpl == 4 && g.lanes == 16)) &&
-                       !(no_edge && no_edge[0] == '1')) ? 1 : 0;
+        g.edge_path = (dtype == NNMD_F32 && pm1 && fpl == 4 && g.lanes == 16 && !(no_edge && no_edge[0] == '1')) ? 1 : 0;
         int r;
         if ((r = upload_real(dtype, zeta, &g.d_zeta))) return r;
         if ((r = upload_real(dtype, lam, &g.d_lam))) return r;

@@ -11,9 +11,13 @@
 // owner accumulates it in registers for its own edges and hands the other endpoint its share (Gamma) through the
 // same edge array.  Still gather-only and atomic-free: the summation order is fixed.
 //
-// Edge scratch layout: E[edge][2][nfa] floats, edge = edge_offsets[row] + slot among the row's neighbours with a
-// larger global index (rows are ascending, so those are a suffix), [0] = Phi, [1] = Gamma (share of the NON-owner),
-// function axis in lane order (slot 2*lane, 2*lane+1 of the group at ebase).
+// Edge scratch layout: E[slot][2][nfa] floats, [0] = Phi, [1] = Gamma (share of the NON-owner), function axis in lane
+// order.  The slot is the position of the edge in the NON-owner's row: rows are ascending, so the entries of row j that
+// j does not own (neighbours with a smaller index) are its first first_gt(j) entries, and
+//     slot(a -> j) = (offsets[j] - edge_offsets[j]) + position of a in row j.
+// The owner finds that position once per edge with a binary search while it stages its row; the gather of atom j then
+// streams one contiguous block of its row's slots (no search, no scattered reads).  Edges towards halo atoms (which have
+// no row of their own) get no slot.
 #pragma once
 // (included inside namespace nnmd)
 
@@ -98,165 +102,6 @@ __device__ __forceinline__ void make_record_edge(const NbView<float> &nb, int tj
     }
 }
 
-// K3e: one warp per centre atom, lanes over functions (2 per lane), edges owned by the centre only.
-// LADDER: the lane's second power is the first one times the record's R_X (zeta ladder, see build_group).
-template <bool WITH_PHI, bool LADDER>
-__global__ void __launch_bounds__(128, 4) angular_edge_kernel(EdgeArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    using MF = M<float>;
-    const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = size_t(ANG_BATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
-    unsigned char *wbase = smem_raw + per_warp * warp;
-    float *recs = reinterpret_cast<float *>(wbase);
-    NbView<float> nb;
-    nb.bind(recs + ANG_BATCH * EREC_STRIDE, a.cap);
-    int *queue = reinterpret_cast<int *>(recs + ANG_BATCH * EREC_STRIDE + size_t(NB_FIELDS) * a.cap);
-
-    const float inv_rc = MF::rcp(a.rc), rc2 = a.rc * a.rc;
-    const float zeta0 = a.zeta[2 * lane], zeta1 = a.zeta[2 * lane + 1];
-    const float zm10 = zeta0 - 1.f, zm11 = zeta1 - 1.f;
-    const int col0 = a.col[2 * lane], col1 = a.col[2 * lane + 1];
-    const int class_off = (a.lam[2 * lane] < 0.f) ? EREC_CLASS : 0;  // lambda class of this lane's two functions
-    const size_t nfa = size_t(a.nfa);
-    const int kind = a.kind;
-    const float eta = a.eta, step = a.step;
-
-    // Rows cost between 0 and ~2x the mean (an atom owns only the edges towards larger indices), so warps pull
-    // rows from a global counter instead of striding.
-    (void)wpb;
-    for (;;) {
-        unsigned long long next = 0;
-        if (lane == 0) next = atomicAdd(a.row_counter, 1ull);
-        const int64_t row = int64_t(__shfl_sync(0xffffffffu, next, 0));
-        if (row >= a.n_rows) break;
-        const int64_t frame = row / a.n_centres;
-        const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
-        float xa, ya, za;
-        load_pos<float>(a.posw, gi, xa, ya, za);
-        const int64_t o0 = a.offsets[row], o1 = a.offsets[row + 1];
-        const int64_t e0 = a.edge_offsets[row], e1 = a.edge_offsets[row + 1];
-        const int first_gt = int((o1 - o0) - (e1 - e0));
-        const int nn = stage_row<float, true>(a.posw, a.idx, o0, o1, xa, ya, za, a.rc, inv_rc, eta, nb, a.cap, first_gt);
-
-        // phi*: two partial sums of Phi per function; vg*: (centre-a value of the row, Gamma of the current edge)
-        float2 phi0 = make_float2(0.f, 0.f), phi1 = phi0, vg0 = phi0, vg1 = phi0;
-        int cur_eid = -1;
-        int head = 0, qn = 0, pushed_total = 0;
-        int last_tj = -1;  // edge (row slot) of the last record already processed
-
-        // process `cnt` queued (edge, third atom) pairs: phase 1 (records, one per lane) then phase 2 (functions)
-        auto flush = [&](int cnt) {
-            __syncwarp();
-            bool is_first = false;
-            const int pk = lane < cnt ? queue[(head + lane) & 63] : 0;
-            const int my_tj = lane < cnt ? (pk & 0x7fff) : -2;
-            int prev_tj = __shfl_up_sync(0xffffffffu, my_tj, 1);
-            if (lane == 0) prev_tj = last_tj;
-            if (lane < cnt) {
-                is_first = my_tj != prev_tj;  // the queue is edge-major: a change of tj opens the next edge
-                const int eid = is_first ? int(e0 + nb.epos[my_tj]) : -1;
-                if (!(a.dbg & 2))
-                    make_record_edge<WITH_PHI, LADDER>(nb, my_tj, (pk >> 15) & 0x7fff, kind, step, inv_rc, eta, eid,
-                                                       recs + lane * EREC_STRIDE);
-            }
-            last_tj = __shfl_sync(0xffffffffu, my_tj, cnt - 1);
-            const unsigned firsts = __ballot_sync(0xffffffffu, is_first);
-            __syncwarp();
-            int t = (a.dbg & 1) ? cnt : 0;
-            while (t < cnt) {
-                if ((firsts >> t) & 1u) {  // record t opens the next edge: retire the previous one (warp-uniform)
-                    if (cur_eid >= 0) {
-                        float *dst = a.E + (size_t(cur_eid) * 2) * nfa + a.ebase + 2 * lane;
-                        if (WITH_PHI) *reinterpret_cast<float2 *>(dst) = make_float2(phi0.x + phi0.y, phi1.x + phi1.y);
-                        *reinterpret_cast<float2 *>(dst + nfa) = make_float2(vg0.y, vg1.y);
-                    }
-                    cur_eid = __float_as_int(recs[t * EREC_STRIDE + 3]);
-                    phi0 = make_float2(0.f, 0.f); phi1 = phi0; vg0.y = 0.f; vg1.y = 0.f;
-                }
-                const unsigned rest = t < 31 ? (firsts & ~((2u << t) - 1u)) : 0u;
-                const int t_end = rest ? min(__ffs(rest) - 1, cnt) : cnt;
-                const float *r = recs + t * EREC_STRIDE + class_off;
-#pragma unroll 2
-                for (; t < t_end; ++t, r += EREC_STRIDE) {
-                    const float4 l = *reinterpret_cast<const float4 *>(r);       // L0 L1 L2 .
-                    const float4 c2 = *reinterpret_cast<const float4 *>(r + 8);  // A2 B2 V0a V0j
-                    const float2 e01 = __fmul2_rn(make_float2(zm10, zm10), make_float2(l.x, l.y));
-                    float2 qa, qb;
-                    qa.x = MF::exp2_fast(e01.x); qa.y = MF::exp2_fast(e01.y);
-                    const float qa2 = MF::exp2_fast(zm10 * l.z);
-                    float qb2;
-                    if (LADDER) {
-                        const float4 rr = *reinterpret_cast<const float4 *>(r + 12);  // R0 R1 R2 .
-                        qb = __fmul2_rn(qa, make_float2(rr.x, rr.y));
-                        qb2 = qa2 * rr.z;
-                    } else {
-                        const float2 f01 = __fmul2_rn(make_float2(zm11, zm11), make_float2(l.x, l.y));
-                        qb.x = MF::exp2_fast(f01.x); qb.y = MF::exp2_fast(f01.y);
-                        qb2 = MF::exp2_fast(zm11 * l.z);
-                    }
-                    if (WITH_PHI) {
-                        const float4 c1 = *reinterpret_cast<const float4 *>(r + 4);  // A0 A1 B0 B1
-                        const float2 ta = __ffma2_rn(make_float2(zeta0, zeta0), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w));
-                        const float2 tb = __ffma2_rn(make_float2(zeta1, zeta1), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w));
-                        const float ta2 = fmaf(zeta0, c2.x, c2.y), tb2 = fmaf(zeta1, c2.x, c2.y);
-                        phi0 = __ffma2_rn(qa, ta, phi0);
-                        phi1 = __ffma2_rn(qb, tb, phi1);
-                        phi0.x = fmaf(qa2, ta2, phi0.x);
-                        phi1.x = fmaf(qb2, tb2, phi1.x);
-                    }
-                    vg0 = __ffma2_rn(qa, make_float2(c2.z, c2.w), vg0);
-                    vg1 = __ffma2_rn(qb, make_float2(c2.z, c2.w), vg1);
-                }
-            }
-            __syncwarp();
-        };
-
-        for (int tj = 0; tj < nn; ++tj) {
-            const int ep = nb.epos[tj];
-            if (ep < 0) continue;  // the neighbour owns this edge (warp-uniform)
-            const Q4<float> uj = ld4<float>(nb.u4 + 4 * tj);
-            const int pushed0 = pushed_total;
-            for (int kb = 0; kb < nn; kb += 32) {
-                const int tk = kb + lane;
-                bool ok = false;
-                if (tk < nn) {
-                    const Q4<float> uk = ld4<float>(nb.u4 + 4 * tk);
-                    const float wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
-                    const float z2 = wx * wx + wy * wy + wz * wz;
-                    ok = (z2 < rc2) && (z2 > 0.f);  // third side inside (0, rc) (symm_funcs.py:34-50); z2 = 0 for tk == tj
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 63] = tj | (tk << 15);
-                const int c = __popc(m);
-                pushed_total += c;
-                qn += c;
-                if (qn >= ANG_BATCH) {
-                    flush(ANG_BATCH);
-                    head = (head + ANG_BATCH) & 63;
-                    qn -= ANG_BATCH;
-                }
-            }
-            if (pushed_total == pushed0) {  // an edge that closes no triangle still owns a (zero) slot the gather reads
-                float *dst = a.E + (size_t(e0 + ep) * 2) * nfa + a.ebase + 2 * lane;
-                if (WITH_PHI) *reinterpret_cast<float2 *>(dst) = make_float2(0.f, 0.f);
-                *reinterpret_cast<float2 *>(dst + nfa) = make_float2(0.f, 0.f);
-            }
-        }
-        if (qn > 0) flush(qn);
-        if (cur_eid >= 0) {
-            float *dst = a.E + (size_t(cur_eid) * 2) * nfa + a.ebase + 2 * lane;
-            if (WITH_PHI) *reinterpret_cast<float2 *>(dst) = make_float2(phi0.x + phi0.y, phi1.x + phi1.y);
-            *reinterpret_cast<float2 *>(dst + nfa) = make_float2(vg0.y, vg1.y);
-        }
-        // the centre's own share of its value (raw sum; scaled and completed by the gather kernel)
-        if (a.G) {
-            if (col0 >= 0) a.G[row * a.nf + col0] = vg0.x;
-            if (col1 >= 0) a.G[row * a.nf + col1] = vg1.x;
-        }
-        __syncwarp();
-    }
-}
-
 // K3e, 4 functions per lane: 16 lanes cover the 64 functions, so the two half-warps work on two different records at
 // once.  Per record pair the warp issues ~40 instructions, 3 ex2 and 44 FMA-pipe cycles: the FMA pipe alone is the
 // limiter (the 2-per-lane form co-saturates FMA pipe, SFU and issue).  LADDER: q_{i+1} = q_i * R_X along the lane's 4 zetas.
@@ -301,6 +146,28 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
         const int64_t e0 = a.edge_offsets[row], e1 = a.edge_offsets[row + 1];
         const int first_gt = int((o1 - o0) - (e1 - e0));
         const int nn = stage_row<float, true>(a.posw, a.idx, o0, o1, xa, ya, za, a.rc, inv_rc, eta, nb, a.cap, first_gt);
+        // owned edges: replace the own-row slot by the slot in the OTHER endpoint's row (-1 not owned, -2 owned without slot)
+        for (int t = lane; t < nn; t += 32) {
+            const int ep = nb.epos[t];
+            int code = -1;
+            if (ep >= 0) {
+                const int64_t j = __ldg(a.idx + o0 + first_gt + ep);
+                const int64_t lj = j - frame * a.n_atoms;
+                code = -2;
+                if (lj < a.n_centres) {
+                    const int64_t rj = frame * a.n_centres + lj;
+                    const int64_t p0 = a.offsets[rj], q0 = a.edge_offsets[rj];
+                    int64_t lo = p0, hi = p0 + ((a.offsets[rj + 1] - p0) - (a.edge_offsets[rj + 1] - q0));
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if (int64_t(__ldg(a.idx + mid)) < gi) lo = mid + 1; else hi = mid;
+                    }
+                    code = int((p0 - q0) + (lo - p0));
+                }
+            }
+            nb.epos[t] = code;
+        }
+        __syncwarp();
 
         // phi*: two partial sums of Phi per function; vg*: (centre-a value of the row, Gamma of the current edge)
         float2 phi[4], vg[4];
@@ -310,7 +177,7 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
         float gox[4], goy[4], goz[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) gox[i] = goy[i] = goz[i] = 0.f;
-        int cur_tj = 0;
+        int cur_tj = -1;  // row slot of the edge being accumulated (-1: none yet)
         // the two half-warps hold partial sums of the same edge: combine, then half 0 writes 16 B per lane
         auto retire = [&](int eid) {
             float ph[4], ga[4];
@@ -329,7 +196,7 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
                     gox[i] = fmaf(ph[i], ux, gox[i]); goy[i] = fmaf(ph[i], uy, goy[i]); goz[i] = fmaf(ph[i], uz, goz[i]);
                 }
             }
-            if (half == 0) {
+            if (half == 0 && eid >= 0) {
                 float *dst = a.E + (size_t(eid) * 2) * nfa + a.ebase + 4 * l16;
                 if (WITH_PHI) *reinterpret_cast<float4 *>(dst) = make_float4(ph[0], ph[1], ph[2], ph[3]);
                 *reinterpret_cast<float4 *>(dst + nfa) = make_float4(ga[0], ga[1], ga[2], ga[3]);
@@ -349,7 +216,7 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
             if (lane == 0) prev_tj = last_tj;
             if (lane < cnt) {
                 is_first = my_tj != prev_tj;  // the queue is edge-major: a change of tj opens the next edge
-                const int eid = is_first ? int(e0 + nb.epos[my_tj]) : -1;
+                const int eid = nb.epos[my_tj];
                 if (!(a.dbg & 2))
                     make_record_edge<WITH_PHI, LADDER>(nb, my_tj, (pk >> 15) & 0x7fff, kind, step, inv_rc, eta, eid,
                                                        recs + lane * EREC_STRIDE);
@@ -360,7 +227,7 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
             int t = (a.dbg & 1) ? cnt : 0;
             while (t < cnt) {
                 if ((firsts >> t) & 1u) {  // record t opens the next edge: retire the previous one (warp-uniform)
-                    if (cur_eid >= 0) retire(cur_eid);
+                    if (cur_tj >= 0) retire(cur_eid);
                     cur_eid = __float_as_int(recs[t * EREC_STRIDE + 3]);
                     cur_tj = __shfl_sync(0xffffffffu, my_tj, t);
 #pragma unroll
@@ -413,7 +280,7 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
 
         for (int tj = 0; tj < nn; ++tj) {
             const int ep = nb.epos[tj];
-            if (ep < 0) continue;  // the neighbour owns this edge (warp-uniform)
+            if (ep == -1) continue;  // the neighbour owns this edge (warp-uniform)
             const Q4<float> uj = ld4<float>(nb.u4 + 4 * tj);
             const int pushed0 = pushed_total;
             for (int kb = 0; kb < nn; kb += 32) {
@@ -436,14 +303,14 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
                     qn -= ANG_BATCH;
                 }
             }
-            if (pushed_total == pushed0 && half == 0) {  // an edge that closes no triangle still owns a (zero) slot
-                float *dst = a.E + (size_t(e0 + ep) * 2) * nfa + a.ebase + 4 * l16;
+            if (pushed_total == pushed0 && half == 0 && ep >= 0) {  // an edge that closes no triangle still has a (zero) slot
+                float *dst = a.E + (size_t(ep) * 2) * nfa + a.ebase + 4 * l16;
                 if (WITH_PHI) *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4 *>(dst + nfa) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         if (qn > 0) flush(qn);
-        if (cur_eid >= 0) retire(cur_eid);
+        if (cur_tj >= 0) retire(cur_eid);
         // the centre's own share of its value (raw sum; scaled and completed by the gather kernel)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -473,12 +340,14 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
     }
 }
 
-// K4e: gather Phi (and Gamma) over all edges of a centre.  HBM-bound: 8 B per lane per edge, coalesced 256 B rows.
+// K4e: every centre collects Phi (and Gamma) of the edges it does NOT own -- the first first_gt entries of its row,
+// whose slots are one contiguous block of E.  HBM-bound streaming: 8 B per lane per edge, 256 B coalesced rows.
+// The centre's own edges were already added to dG / force by K3e.
 template <int MODE>
 __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    float *ubuf = reinterpret_cast<float *>(smem_raw) + size_t(warp) * 4 * a.cap;  // (ux/d, uy/d, uz/d, edge id bits)
+    float *ubuf = reinterpret_cast<float *>(smem_raw) + size_t(warp) * 4 * a.cap;  // (ux/d, uy/d, uz/d, slot bits)
     float coef[2];
     int col[2];
 #pragma unroll
@@ -487,54 +356,32 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
     bool bad = false;
     for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
         const int64_t frame = row / a.n_centres;
-        const int64_t fbase = frame * a.n_atoms;
-        const int64_t gi = fbase + (row - frame * a.n_centres);
+        const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
         float xa, ya, za;
         load_pos<float>(a.posw, gi, xa, ya, za);
         const int64_t o0 = a.offsets[row], o1 = a.offsets[row + 1];
         const int64_t e0 = a.edge_offsets[row], e1 = a.edge_offsets[row + 1];
-        const int first_gt = int((o1 - o0) - (e1 - e0));
-        // stage unit vectors and edge ids of the neighbours inside this group's cutoff
+        const int64_t first_gt = (o1 - o0) - (e1 - e0);
+        const int64_t slot0 = o0 - e0;  // first slot of this row's block in E
         int nn = 0;
-        for (int64_t base = o0; base < o1; base += 32) {
-            const int64_t e = base + lane;
+        for (int64_t base = 0; base < first_gt; base += 32) {
+            const int64_t p = base + lane;
             bool keep = false;
             float ux = 0, uy = 0, uz = 0, d = 0;
-            int j = 0;
-            if (e < o1) {
-                j = __ldg(a.idx + e);
+            if (p < first_gt) {
+                const int j = __ldg(a.idx + o0 + p);
                 float xj, yj, zj;
                 load_pos<float>(a.posw, j, xj, yj, zj);
                 ux = xj - xa; uy = yj - ya; uz = zj - za;
                 d = norm3<float>(ux, uy, uz);  // the same expression as stage_row: both kernels see the same edge set
                 keep = (d < a.rc) && (d > 0.f);
             }
-            // entries the gather has to visit: all edges, or only those owned by the neighbour when K3e already
-            // applied the centre's own edges
-            if (keep && a.owner_applied && (int(e - o0) - first_gt) >= 0) keep = false;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
-                const int p = nn + __popc(m & ((1u << lane) - 1u));
-                int code;
-                const int ep = int(e - o0) - first_gt;
-                if (ep >= 0) {
-                    code = int(e0 + ep);  // owned: non-negative edge id
-                } else {
-                    // the neighbour owns the edge: find this centre in its (ascending) row
-                    const int64_t rj = frame * a.n_centres + (int64_t(j) - fbase);
-                    const int64_t p0 = a.offsets[rj], p1 = a.offsets[rj + 1];
-                    int64_t lo = p0, hi = p1;
-                    while (lo < hi) {
-                        const int64_t mid = (lo + hi) >> 1;
-                        if (int64_t(__ldg(a.idx + mid)) < gi) lo = mid + 1; else hi = mid;
-                    }
-                    const int64_t q0 = a.edge_offsets[rj], q1 = a.edge_offsets[rj + 1];
-                    const int64_t fg = (p1 - p0) - (q1 - q0);
-                    code = ~int(q0 + (lo - p0) - fg);  // bitwise complement marks "not the owner"
-                }
-                if (p < a.cap) {
+                const int q = nn + __popc(m & ((1u << lane) - 1u));
+                if (q < a.cap) {
                     const float inv = 1.0f / d;
-                    *reinterpret_cast<float4 *>(ubuf + 4 * p) = make_float4(ux * inv, uy * inv, uz * inv, __int_as_float(code));
+                    *reinterpret_cast<float4 *>(ubuf + 4 * q) = make_float4(ux * inv, uy * inv, uz * inv, __int_as_float(int(slot0 + p)));
                 }
             }
             nn += __popc(m);
@@ -550,12 +397,9 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
             for (int k = 0; k < 4; ++k) {
                 const int t = min(t0 + k, nn - 1);
                 u[k] = *reinterpret_cast<const float4 *>(ubuf + 4 * t);
-                const int code = __float_as_int(u[k].w);
-                const bool owner = code >= 0;
-                const size_t eid = size_t(owner ? code : ~code);
-                const float *src = a.E + (eid * 2) * nfa + a.ebase + 2 * lane;
+                const float *src = a.E + (size_t(__float_as_int(u[k].w)) * 2) * nfa + a.ebase + 2 * lane;
                 ph[k] = (MODE != MODE_G) ? __ldg(reinterpret_cast<const float2 *>(src)) : make_float2(0.f, 0.f);
-                ga[k] = (MODE != MODE_FORCE && !owner) ? __ldg(reinterpret_cast<const float2 *>(src + nfa)) : make_float2(0.f, 0.f);
+                ga[k] = (MODE != MODE_FORCE) ? __ldg(reinterpret_cast<const float2 *>(src + nfa)) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -571,9 +415,8 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
             if (col[i] < 0) continue;
             const int64_t o = row * a.nf + col[i];
             if (MODE != MODE_FORCE) a.G[o] = 0.5f * coef[i] * (a.G[o] + gam[i]);  // ordered (j,k): both edges of a pair counted
-            if (MODE == MODE_DG) {
-                float dx = -coef[i] * gx[i], dy = -coef[i] * gy[i], dz = -coef[i] * gz[i];
-                if (a.owner_applied) { dx += a.dG[3 * o]; dy += a.dG[3 * o + 1]; dz += a.dG[3 * o + 2]; }
+            if (MODE == MODE_DG) {  // add to the share K3e wrote for the centre's own edges
+                const float dx = a.dG[3 * o] - coef[i] * gx[i], dy = a.dG[3 * o + 1] - coef[i] * gy[i], dz = a.dG[3 * o + 2] - coef[i] * gz[i];
                 a.dG[3 * o] = dx; a.dG[3 * o + 1] = dy; a.dG[3 * o + 2] = dz;
                 bad |= !(isfinite(dx) && isfinite(dy) && isfinite(dz));
             }
@@ -600,8 +443,7 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
         if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "angular: neighbour row of %d entries exceeds shared memory", a.cap);
-        auto kern = g.fpl == 4 ? (a.ladder ? angular_edge4_kernel<WITH_PHI, true> : angular_edge4_kernel<WITH_PHI, false>)
-                               : (a.ladder ? angular_edge_kernel<WITH_PHI, true> : angular_edge_kernel<WITH_PHI, false>);
+        auto kern = a.ladder ? angular_edge4_kernel<WITH_PHI, true> : angular_edge4_kernel<WITH_PHI, false>;
         NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int occ = 1;
         NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
@@ -609,10 +451,10 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * occ);
         NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
         if (const char *env = getenv("NNMD_DBG")) a.dbg = atoi(env);
-        a.owner_applied = (g.fpl == 4 && WITH_PHI) ? 1 : 0;
+        a.owner_applied = 1;
         ProfScope prof(PROF_ANGULAR, st);
         kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
-        NNMD_LAUNCH_CHECK("angular_edge_kernel");
+        NNMD_LAUNCH_CHECK("angular_edge4_kernel");
     }
     {
         int wpb = 8;

@@ -25,7 +25,7 @@ struct AngGroup {
     int n_slots;        // lanes * fpl table entries
     int ladder = 0;     // fpl == 2 and every lane's two zetas differ by the same step: q_b = q_a * 2^(step * L)
     double ladder_step = 0;
-    int edge_path = 0;  // fp32, lambda = +-1, 2 functions per lane on all 32 lanes: eligible for the edge-centric kernel
+    int edge_path = 0;  // fp32, lambda = +-1, 4 functions per lane on 16 lanes: eligible for the edge-centric kernel
     int edge_base = 0;  // first slot of this group on the function axis of the edge scratch
     // device tables in the working dtype, n_slots entries each (slot = lane*fpl + i); col = -1 marks padding
     void *d_zeta = nullptr, *d_lam = nullptr, *d_coef = nullptr;
