@@ -66,8 +66,13 @@ def kernel(path):
                 print(f"stall {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):40s} {v:8.3f} warps per issue")
     src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
-    hdr, data = rows[1], rows[2:]
+    hdr = rows[1]
     iE, iS = hdr.index("Instructions Executed"), hdr.index("# Samples")
+    data = []
+    for r in rows[2:]:  # first kernel of the report only
+        if len(r) <= max(iE, iS) or not r[iE].isdigit():
+            break
+        data.append(r)
     tot = sum(int(r[iE]) for r in data)
     tots = max(sum(int(r[iS]) for r in data), 1)
     runs, cur = [], None
