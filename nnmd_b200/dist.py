@@ -127,6 +127,42 @@ def shard_frames(n_frames: int, rank: int | None = None, world: int | None = Non
     return range(lo, hi)
 
 
+class FlatGradients:
+    """All parameter gradients of the atomic networks as views of ONE contiguous buffer, so that the per-step
+    collective is a single in-place all-reduce with no flatten / unflatten copies (the buffer is <= ~30k floats for the
+    shipped nets: the exchange is latency-bound)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        n = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self) -> None:
+        self.flat.zero_()
+        for p, g in zip(self.params, self.views()):
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                p.grad = g  # an optimizer.zero_grad(set_to_none=True) elsewhere dropped the view
+
+    def views(self):
+        off = 0
+        for p in self.params:
+            yield self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def allreduce(self, average: bool = True) -> None:
+        rank, world = _world()
+        if world == 1:
+            return
+        td.all_reduce(self.flat, op=td.ReduceOp.SUM)
+        if average:
+            self.flat /= world
+
+
 def allreduce_gradients(params, average: bool = True) -> None:
     """One all-reduce of the flat gradient buffer of all atomic networks (<= ~30k floats for the shipped nets:
     latency-bound, so everything goes in a single message)."""

@@ -21,7 +21,7 @@ import torch
 from torch.utils.data import DataLoader
 
 from .._util._logger import Logger
-from ..dist import allreduce_gradients
+from ..dist import FlatGradients
 from ..engine import force_contract
 from .functional import force_contract as autograd_force_contract
 from ..features import calculate_sf
@@ -124,6 +124,7 @@ class BPNN(torch.nn.Module):
             self.pbc = neural_net_data["pbc"]
 
         self.atomic_nets = []
+        self._flat_grads = None
         for i, spec in enumerate(self.species):
             net = AtomicNN(input_size=self.input_sizes[i], hidden_sizes=self.hidden_sizes[i], output_size=1)
             net = net.to(self.device)
@@ -179,11 +180,13 @@ class BPNN(torch.nn.Module):
     def _run_epoch(self, loader, train: bool, desc: str):
         for net in self.atomic_nets:
             net.train(train)
-        params = [p for net in self.atomic_nets for p in net.parameters()]
         tot = torch.zeros(3, device=self.device)
+        if train and getattr(self, "_flat_grads", None) is None:
+            # gradients live in one flat buffer: a single in-place all-reduce per step when frames are sharded
+            self._flat_grads = FlatGradients([p for net in self.atomic_nets for p in net.parameters()])
         for g, dG, energy, forces in tqdm(loader, desc=desc, total=len(loader)):
             if train:
-                self.optim.zero_grad(set_to_none=True)
+                self._flat_grads.zero()
             energy = energy.to(device=self.device)
             forces = forces.to(device=self.device)
             with torch.set_grad_enabled(train):
@@ -191,7 +194,7 @@ class BPNN(torch.nn.Module):
                 loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), energy, f_nn, forces)
             if train:
                 loss.backward()
-                allreduce_gradients(params)  # frames are sharded across ranks: one flat all-reduce (no-op on 1 rank)
+                self._flat_grads.allreduce()  # frames are sharded across ranks (no-op on 1 rank)
                 self.optim.step()
             tot += torch.stack([e_loss.detach(), f_loss.detach(), loss.detach()])
         tot /= len(loader)

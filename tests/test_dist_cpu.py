@@ -30,6 +30,14 @@ def _worker(rank, world, port, out_dir):
     p = torch.nn.Parameter(torch.zeros(5))
     p.grad = torch.full((5,), float(rank + 1))
     dist.allreduce_gradients([p])
+    q1, q2 = torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(4))
+    fg = dist.FlatGradients([q1, q2])
+    fg.zero()
+    q1.grad += float(rank + 1)
+    q2.grad += 10.0 * (rank + 1)
+    fg.allreduce()
+    assert q1.grad.data_ptr() == fg.flat.data_ptr() and torch.allclose(q1.grad, torch.full((2, 3), 1.5))
+    assert torch.allclose(q2.grad, torch.full((4,), 15.0))
     frames = list(dist.shard_frames(11))
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), owned=shard.owned_idx.numpy(), local=local.numpy(),
              grad=p.grad.numpy(), frames=np.asarray(frames))
