@@ -102,6 +102,8 @@ __device__ __forceinline__ void make_record_edge(const NbView<float> &nb, int tj
     }
 }
 
+constexpr int EBATCH = 64;  // (edge, third atom) records built per flush: two per lane
+
 // K3e, 4 functions per lane: 16 lanes cover the 64 functions, so the two half-warps work on two different records at
 // once.  Per record pair the warp issues ~40 instructions, 3 ex2 and 44 FMA-pipe cycles: the FMA pipe alone is the
 // limiter (the 2-per-lane form co-saturates FMA pipe, SFU and issue).  LADDER: q_{i+1} = q_i * R_X along the lane's 4 zetas.
@@ -110,12 +112,12 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using MF = M<float>;
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = size_t(ANG_BATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
+    const size_t per_warp = size_t(EBATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
     unsigned char *wbase = smem_raw + per_warp * warp;
     float *recs = reinterpret_cast<float *>(wbase);
     NbView<float> nb;
-    nb.bind(recs + ANG_BATCH * EREC_STRIDE, a.cap);
-    int *queue = reinterpret_cast<int *>(recs + ANG_BATCH * EREC_STRIDE + size_t(NB_FIELDS) * a.cap);
+    nb.bind(recs + EBATCH * EREC_STRIDE, a.cap);
+    int *queue = reinterpret_cast<int *>(recs + EBATCH * EREC_STRIDE + size_t(NB_FIELDS) * a.cap);  // ring of 128 packed (tj, tk)
 
     const float inv_rc = MF::rcp(a.rc), rc2 = a.rc * a.rc;
     const int half = lane >> 4, l16 = lane & 15;
@@ -209,32 +211,36 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
         // process `cnt` queued (edge, third atom) pairs: phase 1 (records, one per lane) then phase 2 (functions)
         auto flush = [&](int cnt) {
             __syncwarp();
-            bool is_first = false;
-            const int pk = lane < cnt ? queue[(head + lane) & 63] : 0;
-            const int my_tj = lane < cnt ? (pk & 0x7fff) : -2;
-            int prev_tj = __shfl_up_sync(0xffffffffu, my_tj, 1);
-            if (lane == 0) prev_tj = last_tj;
-            if (lane < cnt) {
-                is_first = my_tj != prev_tj;  // the queue is edge-major: a change of tj opens the next edge
-                const int eid = nb.epos[my_tj];
-                if (!(a.dbg & 2))
-                    make_record_edge<WITH_PHI, LADDER>(nb, my_tj, (pk >> 15) & 0x7fff, kind, step, inv_rc, eta, eid,
-                                                       recs + lane * EREC_STRIDE);
+            // phase 1: every lane builds up to two records (slots lane and lane + 32)
+            const bool has0 = lane < cnt, has1 = lane + 32 < cnt;
+            const int pk0 = has0 ? queue[(head + lane) & 127] : 0, pk1 = has1 ? queue[(head + lane + 32) & 127] : 0;
+            const int tj0 = has0 ? (pk0 & 0x7fff) : -2, tj1 = has1 ? (pk1 & 0x7fff) : -2;
+            int prev0 = __shfl_up_sync(0xffffffffu, tj0, 1), prev1 = __shfl_up_sync(0xffffffffu, tj1, 1);
+            const int tj0_last = __shfl_sync(0xffffffffu, tj0, 31);
+            if (lane == 0) { prev0 = last_tj; prev1 = tj0_last; }
+            // the queue is edge-major: a change of tj opens the next edge
+            const bool first0 = has0 && tj0 != prev0, first1 = has1 && tj1 != prev1;
+            if (!(a.dbg & 2)) {
+                if (has0) make_record_edge<WITH_PHI, LADDER>(nb, tj0, (pk0 >> 15) & 0x7fff, kind, step, inv_rc, eta, nb.epos[tj0],
+                                                             recs + lane * EREC_STRIDE);
+                if (has1) make_record_edge<WITH_PHI, LADDER>(nb, tj1, (pk1 >> 15) & 0x7fff, kind, step, inv_rc, eta, nb.epos[tj1],
+                                                             recs + (lane + 32) * EREC_STRIDE);
             }
-            last_tj = __shfl_sync(0xffffffffu, my_tj, cnt - 1);
-            const unsigned firsts = __ballot_sync(0xffffffffu, is_first);
+            last_tj = cnt > 32 ? __shfl_sync(0xffffffffu, tj1, cnt - 33) : __shfl_sync(0xffffffffu, tj0, cnt - 1);
+            const unsigned long long firsts = (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, first1)) << 32) |
+                                              __ballot_sync(0xffffffffu, first0);
             __syncwarp();
             int t = (a.dbg & 1) ? cnt : 0;
             while (t < cnt) {
-                if ((firsts >> t) & 1u) {  // record t opens the next edge: retire the previous one (warp-uniform)
+                if ((firsts >> t) & 1ull) {  // record t opens the next edge: retire the previous one (warp-uniform)
                     if (cur_tj >= 0) retire(cur_eid);
                     cur_eid = __float_as_int(recs[t * EREC_STRIDE + 3]);
-                    cur_tj = __shfl_sync(0xffffffffu, my_tj, t);
+                    cur_tj = __shfl_sync(0xffffffffu, t < 32 ? tj0 : tj1, t & 31);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { phi[i] = make_float2(0.f, 0.f); vg[i].y = 0.f; }
                 }
-                const unsigned rest = t < 31 ? (firsts & ~((2u << t) - 1u)) : 0u;
-                const int t_end = rest ? min(__ffs(rest) - 1, cnt) : cnt;
+                const unsigned long long rest = t < 63 ? (firsts & ~((2ull << t) - 1ull)) : 0ull;
+                const int t_end = rest ? min(__ffsll(static_cast<long long>(rest)) - 1, cnt) : cnt;
                 const float *r = recs + (t + half) * EREC_STRIDE + class_off;
 #pragma unroll 2
                 for (int tt = t + half; tt < t_end; tt += 2, r += 2 * EREC_STRIDE) {
@@ -293,14 +299,14 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
                     ok = (z2 < rc2) && (z2 > 0.f);  // third side inside (0, rc) (symm_funcs.py:34-50); z2 = 0 for tk == tj
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 63] = tj | (tk << 15);
+                if (ok) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 127] = tj | (tk << 15);
                 const int c = __popc(m);
                 pushed_total += c;
                 qn += c;
-                if (qn >= ANG_BATCH) {
-                    flush(ANG_BATCH);
-                    head = (head + ANG_BATCH) & 63;
-                    qn -= ANG_BATCH;
+                if (qn >= EBATCH) {
+                    flush(EBATCH);
+                    head = (head + EBATCH) & 127;
+                    qn -= EBATCH;
                 }
             }
             if (pushed_total == pushed0 && half == 0 && ep >= 0) {  // an edge that closes no triangle still has a (zero) slot
@@ -438,7 +444,7 @@ template <int MODE>
 static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
     constexpr bool WITH_PHI = MODE != MODE_G;
     {
-        const size_t per_warp = size_t(ANG_BATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
+        const size_t per_warp = size_t(EBATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
         int wpb = 4;
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
