@@ -426,3 +426,62 @@ def test_predict_api_shapes_and_values():
     E1, F1 = net.predict({"Cu": cart[0].clone()}, cell, {"Cu": sfd}, pbc=d["pbc"])
     assert E1.shape == (cart.shape[1],) and F1.shape == cart[0].shape
     assert abs(float(E1.sum() - E[0])) < 1e-4 * abs(float(E[0])) and torch.allclose(F1, F[0], atol=1e-6)
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_randomised_tables_and_geometries(seed):
+    """Random clusters / cells / periodic flags / frame counts and random symmetry-function tables (all four kinds,
+    lambda = +-1 or arbitrary, several cutoffs): fp64 against the O(N) oracle at 1e-10, fp32 at 1e-5 against the fp64
+    truth on the same wrapped positions.  Atoms are placed so that nobody is isolated (that case has its own test)."""
+    from nnmd_b200.features.calculate_sf import get_plan, raw_descriptors
+    from nnmd_b200.neighbor import build_neighbor_list
+    from oracle import nl_oracle as O3
+    rng = np.random.default_rng(1000 + seed)
+    B, N = int(rng.integers(1, 4)), int(rng.integers(2, 70))
+    box = float(rng.uniform(3.0, 7.0))
+    cart = rng.uniform(0.0, box, size=(B, N, 3))
+    if seed % 3 == 0:
+        cell, pbc = np.zeros((3, 3)), np.zeros(3)
+    else:
+        cell = np.diag(rng.uniform(box, box + 2.0, 3)) + rng.uniform(-0.5, 0.5, (3, 3)) * (seed % 3 == 2)
+        pbc = rng.integers(0, 2, 3).astype(float)
+        cart = cart + rng.uniform(-2.0, 2.0, size=(B, 1, 3))  # part of the atoms start outside the cell
+    nf = int(rng.integers(1, 45))
+    feats, params = [], []
+    for _ in range(nf):
+        kind = int(rng.choice([1, 2, 4, 5]))
+        rc = float(rng.choice([2.5, 3.0, 3.5]))
+        if kind == 1:
+            prm = [rc]
+        elif kind == 2:
+            prm = [rc, float(rng.uniform(0.1, 3.0)), float(rng.uniform(0.0, rc))]
+        else:
+            lam = float(rng.choice([1.0, -1.0])) if rng.random() < 0.7 else float(rng.uniform(-1.0, 1.0))
+            zeta = float(rng.integers(1, 9)) if rng.random() < 0.5 else float(rng.uniform(1.0, 10.0))
+            prm = [rc, float(rng.choice([0.05, 0.2])), zeta, lam]
+        feats.append(kind)
+        params.append(prm)
+    feats.append(1)
+    params.append([3.5])  # guarantees a non-zero descriptor vector for every atom that has any neighbour
+    sfd = {"features": feats, "params": params}
+    c64, cell64, pbc64 = (torch.tensor(v, dtype=torch.float64) for v in (cart, cell, pbc))
+    G3, dG3, cnt = O3.raw_descriptors(c64, cell64, pbc64, sfd)
+    if int(cnt.min()) == 0:
+        pytest.skip("an isolated atom in this draw")
+    nl = build_neighbor_list(c64.to(DEV), cell64.to(DEV), pbc64.to(DEV), 3.5)
+    assert torch.equal(nl.counts().cpu().to(torch.int32), cnt)
+    G, dG, flag = raw_descriptors(get_plan(sfd, torch.float64, torch.device(DEV)), nl)
+    F = len(feats)
+    assert int(flag.item()) == 0
+    assert col_relerr(G.cpu().view(B, N, F), G3, 2) < 1e-10
+    assert col_relerr(dG.cpu().view(B, N, F, 3), dG3, 2) < 1e-10
+    # fp32 on its own wrapped positions
+    nl32 = build_neighbor_list(c64.float().to(DEV), cell64.float().to(DEV), pbc64.float().to(DEV), 3.5)
+    G32, dG32, _ = raw_descriptors(get_plan(sfd, torch.float32, torch.device(DEV)), nl32)
+    p32 = nl32.posw[:, :3].double().cpu().view(B, N, 3)
+    z3 = torch.zeros(3, 3, dtype=torch.float64)
+    G3s, dG3s, cnt32 = O3.raw_descriptors(p32, z3, torch.zeros(3, dtype=torch.float64), sfd)
+    if not torch.equal(nl32.counts().cpu().to(torch.int32), cnt32):
+        pytest.skip("a pair sits within fp32 rounding of the cutoff")
+    eg, edg = col_relerr(G32.cpu().view(B, N, F), G3s, 2), col_relerr(dG32.cpu().view(B, N, F, 3), dG3s, 2)
+    assert eg < 1e-5 and edg < 2e-5, (eg, edg)
