@@ -253,17 +253,29 @@ def run_ours(args):
         bp.species, bp.atomic_nets, bp.pbc = ["Cu"], [net], None
         host = pos.clone().pin_memory()
 
+        out_e = torch.empty(n_atoms, dtype=torch.float32).pin_memory()     # per-atom energies (single frame: bpnn.py:532-554)
+        out_f = torch.empty(n_atoms, 3, dtype=torch.float32).pin_memory()
+
         def step_e2e():
             E, F = bp.predict({"Cu": host}, cell, {"Cu": sfd}, pbc=pbc)
-            return E.cpu(), F.cpu()
+            out_e.copy_(E, non_blocking=True)
+            out_f.copy_(F, non_blocking=True)
+            torch.cuda.synchronize()
+            return out_e, out_f
         api = "nnmd_b200.nn.BPNN.predict"
     else:
         host = shard.owned_pos.cpu().pin_memory()
 
+        out_e = torch.empty(1, dtype=torch.float32).pin_memory()
+        out_f = torch.empty(1, n_owned, 3, dtype=torch.float32).pin_memory()
+
         def step_e2e():
             shard.set_owned_positions(host.to(dev, non_blocking=True))
             r = step_device()
-            return r.energy.cpu(), r.forces.cpu()
+            out_e.copy_(r.energy, non_blocking=True)
+            out_f.copy_(r.forces, non_blocking=True)
+            torch.cuda.synchronize()
+            return out_e, out_f
         api = "nnmd_b200.engine.energy_forces on nnmd_b200.dist.SlabShard"
     step_e2e()
     barrier()

@@ -968,6 +968,7 @@ static int sf_args_ok(const nnmd_sf_plan *plan, const void *posw, int64_t n_fram
 
 extern "C" int64_t nnmd_sf_edge_scratch_bytes(const nnmd_sf_plan *plan, int64_t n_edges) {
     if (!plan || n_edges < 0 || plan->dtype != NNMD_F32) return 0;
+    if (n_edges >= (int64_t(1) << 31)) return 0;  // slots are int32: beyond that the vertex-centric kernel is used
     return n_edges * 2 * int64_t(plan->edge_slots) * int64_t(sizeof(float));
 }
 
