@@ -485,3 +485,30 @@ def test_randomised_tables_and_geometries(seed):
         pytest.skip("a pair sits within fp32 rounding of the cutoff")
     eg, edg = col_relerr(G32.cpu().view(B, N, F), G3s, 2), col_relerr(dG32.cpu().view(B, N, F, 3), dG3s, 2)
     assert eg < 1e-5 and edg < 2e-5, (eg, edg)
+
+
+def test_cu111_predict_fp64_parity():
+    """BASELINE.json configs[1]: Cu(111) slab frames (GPAW log of the reference), the reference's auto-parameter set
+    (1 G1 + 6 G2 + 6 G4 + 6 G5, rc = 8), energy + force evaluation in fp64 against the oracle chain at 1e-10."""
+    from nnmd_b200.nn import BPNN
+    from oracle import dense_oracle as O2
+    from oracle import nl_oracle as O3
+    d, sfd = load_case("sf_cu111_auto")
+    net = BPNN(dtype=torch.float64)
+    torch.manual_seed(8)
+    net.config(dict(atom_species=["Cu"], input_sizes=[len(sfd["features"])], hidden_sizes=[[32, 16]], learning_rate=0.01,
+                    l2_regularization=0.0, e_loss_coeff=1.0, f_loss_coeff=1.0, load_models=False, path="",
+                    optimizer="adamw", batch_size=2, epochs=1, pbc=[bool(v) for v in d["pbc"]]))
+    cart = torch.tensor(d["cart"], dtype=torch.float64)
+    cell = torch.tensor(d["cell"], dtype=torch.float64)
+    E, F = net.predict({"Cu": cart.clone()}, cell, {"Cu": sfd})        # pbc from config
+    g3, dg3 = O3.descriptors(cart, cell, torch.tensor(d["pbc"]), sfd)
+    Ws = [m.weight.detach().double().cpu() for m in net.atomic_nets[0].model]
+    bs = [m.bias.detach().double().cpu() for m in net.atomic_nets[0].model]
+    e_o, _, f_o = O2.energy_force(g3, dg3, Ws, bs)
+    assert E.dtype == torch.float64 and relerr(E.cpu(), e_o.sum(dim=(1, 2))) < 1e-10
+    assert relerr(F.cpu(), f_o) < 1e-10
+    # and against the reference's own descriptors for these frames (complex64-limited, SURVEY Q5)
+    g_ref, dg_ref = torch.tensor(d["g_f64"]), torch.tensor(d["dg_f64"])
+    e_r, _, f_r = O2.energy_force(g_ref, dg_ref, Ws, bs)
+    assert relerr(E.cpu(), e_r.sum(dim=(1, 2))) < 5e-7 and relerr(F.cpu(), f_r) < 5e-6
