@@ -149,10 +149,18 @@ class BPNN(torch.nn.Module):
                              f"Available optimizers: {list(available_optimizers.keys())}")
         betas = (0.9, 0.999) if name == "adamw" else (0.8, 0.9999)
         kwargs = dict(params=params, lr=self.learning_rate, weight_decay=self.l2_regularization, betas=betas, amsgrad=True)
-        try:  # same update rule, one fused kernel per step instead of a dozen foreach launches
-            self.optim = available_optimizers[name](fused=self.device.type == "cuda", **kwargs)
+        on_gpu = self.device.type == "cuda"
+        try:  # same update rule; fused = one kernel per step, capturable = step counter and lr live on the device so
+            #   the whole training step can be replayed from a CUDA graph (the step is launch-bound otherwise)
+            if on_gpu:  # a device-resident lr is what a captured optimizer step reads; schedulers update it in place
+                kwargs["lr"] = torch.tensor(float(self.learning_rate), dtype=torch.float32, device=self.device)
+            self.optim = available_optimizers[name](fused=on_gpu, capturable=on_gpu, **kwargs)
+            self._graphs_ok = on_gpu and os.environ.get("NNMD_NO_CUDA_GRAPH", "0") != "1"
         except (RuntimeError, TypeError, ValueError):
+            kwargs["lr"] = self.learning_rate
             self.optim = available_optimizers[name](**kwargs)
+            self._graphs_ok = False
+        self._graph_state = None
 
     # ------------------------------------------------------------------------------------------------- loss
     def _loss(self, e_nn, energies, f_nn, forces):
@@ -177,26 +185,79 @@ class BPNN(torch.nn.Module):
         return torch.cat(e_nn, dim=cat_dim), torch.cat(f_nn, dim=cat_dim)
 
     # ------------------------------------------------------------------------------------------------ loops
+    def _train_step_eager(self, g, dG, energy, forces, out):
+        """One optimisation step: K6 forward, loss, K7/K4c' backward, gradient all-reduce, optimizer."""
+        self._flat_grads.zero()
+        e_nn, f_nn = self._energies_forces(g, dG)
+        loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), energy, f_nn, forces)
+        loss.backward()
+        self._flat_grads.allreduce()  # frames are sharded across ranks (no-op on 1 rank)
+        self.optim.step()
+        out.copy_(torch.stack([e_loss.detach(), f_loss.detach(), loss.detach()]))
+
+    def _train_step(self, g, dG, energy, forces, out):
+        """The training step is ~40 small launches (launch-bound, ~1 ms); batches of a repeated shape are replayed from
+        CUDA graphs instead (~0.2 ms).  First batch of a shape: eager (creates the optimizer state); second: capture;
+        later ones: copy the batch into the static buffers and replay.  With several ranks the gradient all-reduce
+        sits between two graphs (forward+backward | optimizer)."""
+        if not self._graphs_ok:
+            return self._train_step_eager(g, dG, energy, forces, out)
+        key = tuple((s, tuple(g[s].shape)) for s in self.species) + (tuple(energy.shape), tuple(forces.shape))
+        st = self._graph_state
+        if st is None or st["key"] != key:
+            self._graph_state = {"key": key, "graphs": None}
+            return self._train_step_eager(g, dG, energy, forces, out)
+        if st["graphs"] is None:
+            try:
+                st["g"] = {s: g[s].detach().clone() for s in self.species}
+                st["dG"] = {s: dG[s].detach().clone() for s in self.species}
+                st["E"], st["F"], st["out"] = energy.clone(), forces.clone(), torch.zeros(3, device=self.device)
+                fwd_bwd, opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(fwd_bwd):
+                    self._flat_grads.flat.zero_()
+                    e_nn, f_nn = self._energies_forces(st["g"], st["dG"])
+                    loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), st["E"], f_nn, st["F"])
+                    loss.backward()
+                    st["out"].copy_(torch.stack([e_loss.detach(), f_loss.detach(), loss.detach()]))
+                with torch.cuda.graph(opt, pool=fwd_bwd.pool()):
+                    self.optim.step()
+                st["graphs"] = (fwd_bwd, opt)
+            except Exception as exc:  # capture not possible here: stay eager, loudly
+                print(f"nnmd_b200: CUDA-graph capture of the training step failed ({exc!r}); continuing without graphs")
+                self._graphs_ok = False
+                return self._train_step_eager(g, dG, energy, forces, out)
+        else:
+            for s in self.species:
+                st["g"][s].copy_(g[s])
+                st["dG"][s].copy_(dG[s])
+            st["E"].copy_(energy)
+            st["F"].copy_(forces)
+        fwd_bwd, opt = st["graphs"]
+        fwd_bwd.replay()
+        self._flat_grads.allreduce()
+        opt.replay()
+        out.copy_(st["out"])
+
     def _run_epoch(self, loader, train: bool, desc: str):
         for net in self.atomic_nets:
             net.train(train)
         tot = torch.zeros(3, device=self.device)
+        out = torch.zeros(3, device=self.device)
         if train and getattr(self, "_flat_grads", None) is None:
             # gradients live in one flat buffer: a single in-place all-reduce per step when frames are sharded
             self._flat_grads = FlatGradients([p for net in self.atomic_nets for p in net.parameters()])
         for g, dG, energy, forces in tqdm(loader, desc=desc, total=len(loader)):
-            if train:
-                self._flat_grads.zero()
             energy = energy.to(device=self.device)
             forces = forces.to(device=self.device)
-            with torch.set_grad_enabled(train):
-                e_nn, f_nn = self._energies_forces(g, dG)
-                loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), energy, f_nn, forces)
             if train:
-                loss.backward()
-                self._flat_grads.allreduce()  # frames are sharded across ranks (no-op on 1 rank)
-                self.optim.step()
-            tot += torch.stack([e_loss.detach(), f_loss.detach(), loss.detach()])
+                self._train_step(g, dG, energy, forces, out)
+            else:
+                with torch.no_grad():
+                    e_nn, f_nn = self._energies_forces(g, dG)
+                    loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), energy, f_nn, forces)
+                out.copy_(torch.stack([e_loss, f_loss, loss]))
+            tot += out
         tot /= len(loader)
         return tot[0], tot[1], tot[2]
 
@@ -247,7 +308,7 @@ class BPNN(torch.nn.Module):
         self.sched = torch.optim.lr_scheduler.ExponentialLR(self.optim, gamma=0.99)
         self.net_log = Logger.get_logger("Net training info", "net.log")
         self._describe_training(len(train_dataset), len(val_dataset), len(test_dataset), batch_size, epochs)
-        curr_lr = self.optim.param_groups[0]["lr"]
+        curr_lr = float(self.optim.param_groups[0]["lr"])
         line = "{loss} E = {e_loss:e}, {loss} F = {f_loss:e}, {loss} total = {total:e} eV"
         name = self.criterion.__class__.__name__
         for epoch in range(epochs):
@@ -258,8 +319,8 @@ class BPNN(torch.nn.Module):
             self.net_log.info(f"Epoch {epoch + 1}: validation: "
                               + line.format(e_loss=e_loss.item(), f_loss=f_loss.item(), loss=name, total=loss.item()))
             self.sched.step()
-            if self.optim.param_groups[0]["lr"] != curr_lr:
-                curr_lr = self.optim.param_groups[0]["lr"]
+            if float(self.optim.param_groups[0]["lr"]) != curr_lr:
+                curr_lr = float(self.optim.param_groups[0]["lr"])
                 self.net_log.info(f"Learning rate changed to {curr_lr}")
         e_loss, f_loss, loss = self._test(test_loader)
         self.net_log.info("Testing: " + line.format(e_loss=e_loss.item(), f_loss=f_loss.item(), loss=loss.item(),

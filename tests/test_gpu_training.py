@@ -127,3 +127,37 @@ def test_two_species_step_matches_torch_autograd():
     assert abs(float(loss - loss0)) < 1e-12 * abs(float(loss0)) + 1e-14
     for a, b in zip(grads, grads0):
         assert relerr(a.cpu(), b.cpu()) < 1e-10
+
+
+def test_cuda_graph_training_matches_eager(monkeypatch):
+    """Graph-replayed steps (capture on the second batch of a shape) and eager steps give the same weights; the
+    ExponentialLR schedule reaches the captured optimizer through the device-resident lr."""
+    from nnmd_b200.nn import BPNN, TrainAtomicDataset
+    from nnmd_b200.nn.bpnn import batch_loader
+    torch.manual_seed(21)
+    M, N, F = 64, 9, 7
+    g = torch.rand(M, N, F, device=DEV)
+    g = g / g.norm(dim=-1, keepdim=True)
+    dg = torch.randn(M, N, F, 3, device=DEV)
+    E, Fr = torch.rand(M, 1, device=DEV), torch.randn(M, N, 3, device=DEV) * 0.1
+    finals = {}
+    for mode in ("graph", "eager"):
+        monkeypatch.setenv("NNMD_NO_CUDA_GRAPH", "0" if mode == "graph" else "1")
+        torch.manual_seed(5)
+        net = BPNN(dtype=torch.float32)
+        net.config(dict(atom_species=["X"], input_sizes=[F], hidden_sizes=[[12, 6]], learning_rate=0.02, l2_regularization=1e-3,
+                        e_loss_coeff=1.0, f_loss_coeff=0.3, load_models=False, path="", optimizer="adamw", batch_size=16, epochs=2))
+        ds = TrainAtomicDataset({"X": (g.clone().requires_grad_(True), dg)}, E, Fr, {})
+        loader = batch_loader(ds, 16, shuffle=False)
+        sched = torch.optim.lr_scheduler.ExponentialLR(net.optim, gamma=0.5)
+        losses = []
+        for ep in range(3):
+            losses.append(float(net._train_loop(ep, loader)[2]))
+            sched.step()
+        assert (net._graph_state is not None and net._graph_state.get("graphs") is not None) == (mode == "graph")
+        finals[mode] = ([p.detach().clone() for p in net.atomic_nets[0].parameters()], losses, float(net.optim.param_groups[0]["lr"]))
+    assert abs(finals["graph"][2] - 0.02 * 0.125) < 1e-9 and abs(finals["eager"][2] - 0.02 * 0.125) < 1e-9
+    np.testing.assert_allclose(finals["graph"][1], finals["eager"][1], rtol=1e-4)
+    for a, b in zip(finals["graph"][0], finals["eager"][0]):
+        assert relerr(a.cpu(), b.cpu()) < 1e-4
+    assert finals["graph"][1][-1] < finals["graph"][1][0]
