@@ -112,12 +112,12 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using MF = M<float>;
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = size_t(EBATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
+    const size_t per_warp = size_t(EBATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 256 * sizeof(int);
     unsigned char *wbase = smem_raw + per_warp * warp;
     float *recs = reinterpret_cast<float *>(wbase);
     NbView<float> nb;
     nb.bind(recs + EBATCH * EREC_STRIDE, a.cap);
-    int *queue = reinterpret_cast<int *>(recs + EBATCH * EREC_STRIDE + size_t(NB_FIELDS) * a.cap);  // ring of 128 packed (tj, tk)
+    int *queue = reinterpret_cast<int *>(recs + EBATCH * EREC_STRIDE + size_t(NB_FIELDS) * a.cap);  // ring of 256 packed (tj, tk)
 
     const float inv_rc = MF::rcp(a.rc), rc2 = a.rc * a.rc;
     const int half = lane >> 4, l16 = lane & 15;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
             __syncwarp();
             // phase 1: every lane builds up to two records (slots lane and lane + 32)
             const bool has0 = lane < cnt, has1 = lane + 32 < cnt;
-            const int pk0 = has0 ? queue[(head + lane) & 127] : 0, pk1 = has1 ? queue[(head + lane + 32) & 127] : 0;
+            const int pk0 = has0 ? queue[(head + lane) & 255] : 0, pk1 = has1 ? queue[(head + lane + 32) & 255] : 0;
             const int tj0 = has0 ? (pk0 & 0x7fff) : -2, tj1 = has1 ? (pk1 & 0x7fff) : -2;
             int prev0 = __shfl_up_sync(0xffffffffu, tj0, 1), prev1 = __shfl_up_sync(0xffffffffu, tj1, 1);
             const int tj0_last = __shfl_sync(0xffffffffu, tj0, 31);
@@ -289,23 +289,32 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
             if (ep == -1) continue;  // the neighbour owns this edge (warp-uniform)
             const Q4<float> uj = ld4<float>(nb.u4 + 4 * tj);
             const int pushed0 = pushed_total;
-            for (int kb = 0; kb < nn; kb += 32) {
-                const int tk = kb + lane;
-                bool ok = false;
-                if (tk < nn) {
-                    const Q4<float> uk = ld4<float>(nb.u4 + 4 * tk);
-                    const float wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
-                    const float z2 = wx * wx + wy * wy + wz * wz;
-                    ok = (z2 < rc2) && (z2 > 0.f);  // third side inside (0, rc) (symm_funcs.py:34-50); z2 = 0 for tk == tj
+            // 96 candidates per trip: three independent closure tests per lane (their latencies overlap), then three
+            // compactions into the ring; the ring (256) holds a partial batch (< 64) plus one trip (<= 96)
+            for (int kb = 0; kb < nn; kb += 96) {
+                bool ok[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int tk = kb + 32 * c + lane;
+                    ok[c] = false;
+                    if (tk < nn) {
+                        const Q4<float> uk = ld4<float>(nb.u4 + 4 * tk);
+                        const float wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
+                        const float z2 = wx * wx + wy * wy + wz * wz;
+                        ok[c] = (z2 < rc2) && (z2 > 0.f);  // third side inside (0, rc) (symm_funcs.py:34-50); z2 = 0 for tk == tj
+                    }
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 127] = tj | (tk << 15);
-                const int c = __popc(m);
-                pushed_total += c;
-                qn += c;
-                if (qn >= EBATCH) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned m = __ballot_sync(0xffffffffu, ok[c]);
+                    if (ok[c]) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 255] = tj | ((kb + 32 * c + lane) << 15);
+                    const int n_ok = __popc(m);
+                    pushed_total += n_ok;
+                    qn += n_ok;
+                }
+                while (qn >= EBATCH) {
                     flush(EBATCH);
-                    head = (head + EBATCH) & 127;
+                    head = (head + EBATCH) & 255;
                     qn -= EBATCH;
                 }
             }
@@ -444,7 +453,7 @@ template <int MODE>
 static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
     constexpr bool WITH_PHI = MODE != MODE_G;
     {
-        const size_t per_warp = size_t(EBATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 128 * sizeof(int);
+        const size_t per_warp = size_t(EBATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 256 * sizeof(int);
         int wpb = 4;
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
