@@ -200,8 +200,9 @@ __global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
             }
             if (half == 0 && eid >= 0) {
                 float *dst = a.E + (size_t(eid) * 2) * nfa + a.ebase + 4 * l16;
-                if (WITH_PHI) *reinterpret_cast<float4 *>(dst) = make_float4(ph[0], ph[1], ph[2], ph[3]);
-                *reinterpret_cast<float4 *>(dst + nfa) = make_float4(ga[0], ga[1], ga[2], ga[3]);
+                // write-once, read-once data: streaming stores keep positions and neighbour rows in L2
+                if (WITH_PHI) __stcs(reinterpret_cast<float4 *>(dst), make_float4(ph[0], ph[1], ph[2], ph[3]));
+                __stcs(reinterpret_cast<float4 *>(dst + nfa), make_float4(ga[0], ga[1], ga[2], ga[3]));
             }
         };
         int cur_eid = -1;
@@ -413,8 +414,8 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
                 const int t = min(t0 + k, nn - 1);
                 u[k] = *reinterpret_cast<const float4 *>(ubuf + 4 * t);
                 const float *src = a.E + (size_t(__float_as_int(u[k].w)) * 2) * nfa + a.ebase + 2 * lane;
-                ph[k] = (MODE != MODE_G) ? __ldg(reinterpret_cast<const float2 *>(src)) : make_float2(0.f, 0.f);
-                ga[k] = (MODE != MODE_FORCE) ? __ldg(reinterpret_cast<const float2 *>(src + nfa)) : make_float2(0.f, 0.f);
+                ph[k] = (MODE != MODE_G) ? __ldcs(reinterpret_cast<const float2 *>(src)) : make_float2(0.f, 0.f);
+                ga[k] = (MODE != MODE_FORCE) ? __ldcs(reinterpret_cast<const float2 *>(src + nfa)) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
