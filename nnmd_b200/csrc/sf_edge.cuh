@@ -1,4 +1,4 @@
-// sf_edge.cuh -- edge-centric form of the angular kernel K3 (fp32, lambda = +-1, 2 functions per lane on 32 lanes).
+// sf_edge.cuh -- edge-centric form of the angular kernel K3 (fp32, lambda = +-1, 33..64 functions: 4 per lane on 16 lanes).
 // Included by sf.cu after the shared staging helpers.
 //
 // Why: with S_f(a,j,k) = sum over the three centres of P_f(c_X) E_X (one closed triangle),
@@ -6,8 +6,8 @@
 // and Phi_f(a,j) = Phi_f(j,a).  The vertex-centric kernel evaluates both derivatives (d/dx and d/dy) of every triangle
 // from each of its three vertices; here every unordered edge is evaluated ONCE, by the endpoint with the smaller
 // global index (its "owner"), for one derivative only: 11 FMA-pipe cycles per (edge, third atom, function) instead
-// of 22, no direction-vector work in the inner loop.  Phi goes to HBM as an edge array and a second, bandwidth-bound
-// kernel gathers it from both endpoints.  The value G_a needs the centre-a term of every ordered pair (j,k): the
+// of 22, no direction-vector work in the inner loop.  The owner adds its own Phi*u terms to dG when an edge retires;
+// Phi also goes to HBM as an edge array from which a second, bandwidth-bound kernel serves the other endpoint.  The value G_a needs the centre-a term of every ordered pair (j,k): the
 // owner accumulates it in registers for its own edges and hands the other endpoint its share (Gamma) through the
 // same edge array.  Still gather-only and atomic-free: the summation order is fixed.
 //
@@ -42,7 +42,6 @@ struct EdgeArgs {
     uint32_t *flag;
     unsigned long long *row_counter;  // dynamic row scheduling (zeroed before the launch)
     int dbg;                          // profiling knob (NNMD_DBG): 1 = skip phase 2, 2 = skip phase 1 as well
-    int owner_applied;                // K3e already added the owner's own Phi*u terms to dG / force: the gather skips owned edges
 };
 
 // record: per lambda class (EREC_CLASS floats)  [ L0 L1 L2 eid | A0 A1 B0 B1 | A2 B2 V0a V0j | R0 R1 R2 . ]
@@ -467,7 +466,6 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * occ);
         NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
         if (const char *env = getenv("NNMD_DBG")) a.dbg = atoi(env);
-        a.owner_applied = 1;
         ProfScope prof(PROF_ANGULAR, st);
         kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
         NNMD_LAUNCH_CHECK("angular_edge4_kernel");
