@@ -130,13 +130,21 @@ int nnmd_sf_normalize(int dtype, const void *G, int64_t n_rows, int nf, void *gh
  *   replaces the chain autograd.grad (calculate_sf.py:85-90) -> einsum (bpnn.py:353, :538-544)
  *   w      dev (n_rows, nf)  dE/dg_hat of the centre atom
  *   force  dev (n_rows, 3)   overwritten
- *   virial dev (n_frames, 9) or NULL:  -1/2 sum_a sum_t u_at (x) f_at, pairwise-decomposed
- *          (extension, the reference has no virial: SURVEY Q8)
+ *   virial must be NULL here: use nnmd_virial on the returned forces (extension, the reference has no virial: SURVEY Q8)
  * ------------------------------------------------------------------------------------- */
 int nnmd_sf_force(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
                   const int64_t *offsets, const int32_t *idx, int64_t max_row, const int64_t *edge_offsets,
                   int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes, const void *w, void *force, void *virial,
                   void *stream);
+
+/* Virial of each frame from per-atom forces, W = - sum_a (p_a - o) (x) F_a, (n_frames, 9) row-major.
+ *   The reference has no virial and never adds periodic images (Q1): every frame is a finite cluster, for which
+ *   this equals the pair-decomposed virial whenever sum_a F_a = 0.  origin: host double[3], or NULL = centroid of the
+ *   frame's centre atoms.  ws: dev scratch of nnmd_virial_workspace_bytes(n_frames).  Works on any (n_rows,3) forces:
+ *   the fused ones of nnmd_sf_force or the contracted ones of nnmd_force_contract. */
+int64_t nnmd_virial_workspace_bytes(int64_t n_frames);
+int nnmd_virial(int dtype, const void *posw, const void *force, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
+                const double *origin, void *ws, void *virial, void *stream);
 
 /* K4c  force contraction against a materialised dG      replaces bpnn.py:353  einsum("ijk,ijkl->ijl")
  *   force[a,:] = -sum_f dE[a,f] * dG[a,f,:] */

@@ -779,6 +779,48 @@ __global__ void __launch_bounds__(256) contract_kernel(const T *__restrict__ dE,
 }
 
 // =============================================================================================
+// virial of a frame from per-atom forces:  W = - sum_a (p_a - o) (x) F_a
+// The reference never adds periodic images, so every frame is a finite cluster and this IS the
+// pair-decomposed virial -1/2 sum_{a != b} r_ab (x) f_ab whenever the forces are those of a translation-invariant
+// energy (sum_a F_a = 0).  o = centroid of the frame's centre atoms (or a caller-supplied origin), which fixes the
+// otherwise origin-dependent value for the reference-semantic forces, whose sum need not vanish.
+// =============================================================================================
+template <typename T>
+__global__ void centroid_kernel(const T *__restrict__ posw, int64_t n_rows, int64_t n_atoms, int64_t n_centres, double *__restrict__ csum) {
+    for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < n_rows; row += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t frame = row / n_centres;
+        T x, y, z;
+        load_pos<T>(posw, frame * n_atoms + (row - frame * n_centres), x, y, z);
+        atomicAdd(csum + 3 * frame, double(x)); atomicAdd(csum + 3 * frame + 1, double(y)); atomicAdd(csum + 3 * frame + 2, double(z));
+    }
+}
+
+template <typename T>
+__global__ void virial_kernel(const T *__restrict__ posw, const T *__restrict__ force, int64_t n_rows, int64_t n_atoms,
+                              int64_t n_centres, const double *__restrict__ csum, double ox, double oy, double oz, int use_origin,
+                              double *__restrict__ wsum) {
+    for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < n_rows; row += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t frame = row / n_centres;
+        T x, y, z;
+        load_pos<T>(posw, frame * n_atoms + (row - frame * n_centres), x, y, z);
+        double r[3] = {double(x), double(y), double(z)};
+        if (use_origin) { r[0] -= ox; r[1] -= oy; r[2] -= oz; }
+        else { r[0] -= csum[3 * frame] / double(n_centres); r[1] -= csum[3 * frame + 1] / double(n_centres); r[2] -= csum[3 * frame + 2] / double(n_centres); }
+        const double f[3] = {double(force[3 * row]), double(force[3 * row + 1]), double(force[3 * row + 2])};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) atomicAdd(wsum + 9 * frame + 3 * i + j, -r[i] * f[j]);
+    }
+}
+
+template <typename T>
+__global__ void virial_store_kernel(const double *__restrict__ wsum, int64_t n, T *__restrict__ out) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < n) out[i] = T(wsum[i]);
+}
+
+// =============================================================================================
 // launch helpers
 // =============================================================================================
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
@@ -1003,6 +1045,37 @@ extern "C" int nnmd_sf_force(const nnmd_sf_plan *plan, const void *posw, int64_t
     if (plan->dtype == NNMD_F32)
         return sf_run<float, MODE_FORCE>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, edge_offsets, n_edges, edge_ws, edge_ws_bytes, nullptr, nullptr, (const float *)w, (float *)force, nullptr, st);
     return sf_run<double, MODE_FORCE>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, 0, nullptr, 0, nullptr, nullptr, (const double *)w, (double *)force, nullptr, st);
+}
+
+extern "C" int64_t nnmd_virial_workspace_bytes(int64_t n_frames) { return n_frames < 0 ? -1 : n_frames * 12 * int64_t(sizeof(double)); }
+
+extern "C" int nnmd_virial(int dtype, const void *posw, const void *force, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
+                           const double *origin, void *ws, void *virial, void *stream) {
+    if (dtype != NNMD_F32 && dtype != NNMD_F64) return set_err(NNMD_ERR_INVALID, "virial: bad dtype %d", dtype);
+    if (n_frames < 0 || n_atoms < 0 || n_centres < 0 || n_centres > n_atoms) return set_err(NNMD_ERR_INVALID, "virial: bad sizes");
+    if (n_frames == 0) return NNMD_OK;
+    if (!posw || !force || !ws || !virial) return set_err(NNMD_ERR_INVALID, "virial: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *csum = (double *)ws, *wsum = csum + 3 * n_frames;
+    NNMD_CUDA_CHECK(cudaMemsetAsync(ws, 0, size_t(n_frames) * 12 * sizeof(double), st));
+    const int64_t n_rows = n_frames * n_centres;
+    if (n_rows > 0) {
+        const unsigned blocks = unsigned(std::min<int64_t>((n_rows + 255) / 256, int64_t(sm_count()) * 8));
+        const double o[3] = {origin ? origin[0] : 0.0, origin ? origin[1] : 0.0, origin ? origin[2] : 0.0};
+        if (dtype == NNMD_F32) {
+            if (!origin) centroid_kernel<float><<<blocks, 256, 0, st>>>((const float *)posw, n_rows, n_atoms, n_centres, csum);
+            virial_kernel<float><<<blocks, 256, 0, st>>>((const float *)posw, (const float *)force, n_rows, n_atoms, n_centres, csum, o[0], o[1], o[2], origin ? 1 : 0, wsum);
+        } else {
+            if (!origin) centroid_kernel<double><<<blocks, 256, 0, st>>>((const double *)posw, n_rows, n_atoms, n_centres, csum);
+            virial_kernel<double><<<blocks, 256, 0, st>>>((const double *)posw, (const double *)force, n_rows, n_atoms, n_centres, csum, o[0], o[1], o[2], origin ? 1 : 0, wsum);
+        }
+        NNMD_LAUNCH_CHECK("virial_kernel");
+    }
+    const int64_t n = n_frames * 9;
+    if (dtype == NNMD_F32) virial_store_kernel<float><<<unsigned((n + 255) / 256), 256, 0, st>>>(wsum, n, (float *)virial);
+    else virial_store_kernel<double><<<unsigned((n + 255) / 256), 256, 0, st>>>(wsum, n, (double *)virial);
+    NNMD_LAUNCH_CHECK("virial_store_kernel");
+    return NNMD_OK;
 }
 
 extern "C" int nnmd_sf_normalize(int dtype, const void *G, int64_t n_rows, int nf, void *ghat, uint32_t *flag, void *stream) {

@@ -43,6 +43,23 @@ def force_contract(dE: torch.Tensor, dG: torch.Tensor) -> torch.Tensor:
     return out.view(*dE.shape[:-1], 3)
 
 
+def virial(nl: NeighborList, forces: torch.Tensor, origin=None) -> torch.Tensor:
+    """Per-frame virial W = - sum_a (p_a - o) (x) F_a, shape (n_frames, 3, 3), on the wrapped positions of `nl`.
+
+    Extension (the reference has none).  Because the reference never adds periodic images every frame is a
+    finite cluster, so this is the usual pair virial whenever the forces sum to zero; o defaults to the frame centroid."""
+    import ctypes
+    lib = _lib.load()
+    f2 = forces.detach().reshape(-1, 3).contiguous()
+    out = torch.empty((nl.n_frames, 3, 3), dtype=f2.dtype, device=f2.device)
+    ws = torch.empty(max(int(lib.nnmd_virial_workspace_bytes(nl.n_frames)), 1), dtype=torch.uint8, device=f2.device)
+    org = None if origin is None else (ctypes.c_double * 3)(*[float(v) for v in origin])
+    with torch.cuda.device(f2.device):
+        _lib.check(lib.nnmd_virial(_lib.dtype_code(f2.dtype), _lib.ptr(nl.posw), _lib.ptr(f2), nl.n_frames, nl.n_atoms, nl.n_centres,
+                                   org, _lib.ptr(ws), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
 def fused_force(plan: SfPlan, nl: NeighborList, w: torch.Tensor) -> torch.Tensor:
     """K4b: forces from dE/dg_hat without a materialised dG."""
     lib = _lib.load()

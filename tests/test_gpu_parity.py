@@ -512,3 +512,41 @@ def test_cu111_predict_fp64_parity():
     g_ref, dg_ref = torch.tensor(d["g_f64"]), torch.tensor(d["dg_f64"])
     e_r, _, f_r = O2.energy_force(g_ref, dg_ref, Ws, bs)
     assert relerr(E.cpu(), e_r.sum(dim=(1, 2))) < 5e-7 and relerr(F.cpu(), f_r) < 5e-6
+
+
+def test_virial_is_the_strain_derivative_for_a_translation_invariant_energy():
+    """Extension without a reference counterpart: with the same weights on every atom the reference-semantic
+    force is the physical force of E = sum_f w_f sum_i G_if, and W = -sum_a (p_a - o) (x) F_a must equal dE/d(strain)
+    (checked by central differences in fp64 on a free cluster), independently of the origin because sum F = 0."""
+    from nnmd_b200.engine import fused_force, virial
+    from nnmd_b200.features.calculate_sf import get_plan, raw_descriptors
+    from nnmd_b200.neighbor import build_neighbor_list
+    torch.manual_seed(12)
+    dt = torch.float64
+    pos = (torch.rand(1, 30, 3, dtype=dt) * 5.0).to(DEV)
+    z3, p0 = torch.zeros(3, 3, dtype=dt, device=DEV), torch.zeros(3, dtype=dt, device=DEV)
+    sfd = {"features": [2, 2, 4, 5, 4], "params": [[3.0, 0.8, 1.0], [3.0, 0.3, 2.0], [3.0, 0.1, 2.0, 1.0], [3.0, 0.05, 1.5, -1.0], [2.6, 0.2, 3.0, 1.0]]}
+    wf = torch.tensor([0.7, -0.4, 1.3, 0.9, -0.6], dtype=dt, device=DEV)
+    plan = get_plan(sfd, dt, pos.device)
+
+    def energy(p):
+        nl_ = build_neighbor_list(p, z3, p0, 3.0)
+        G, _, _ = raw_descriptors(plan, nl_, with_grad=False)
+        return float((G * wf).sum())
+
+    nl = build_neighbor_list(pos, z3, p0, 3.0)
+    F = fused_force(plan, nl, wf.expand(nl.n_rows, -1).contiguous())
+    assert float(F.sum(dim=0).abs().max()) < 1e-10 * float(F.abs().max())
+    W = virial(nl, F)[0].cpu()
+    W0 = virial(nl, F, origin=[10.0, -3.0, 2.0])[0].cpu()
+    assert float((W - W0).abs().max()) < 1e-9 * float(W.abs().max())
+    o = pos[0].mean(dim=0)
+    h = 1e-5
+    for i in range(3):
+        for j in range(3):
+            eps = torch.zeros(3, 3, dtype=dt, device=DEV)
+            eps[i, j] = h
+            ep = energy(pos + (pos - o) @ eps.T)
+            em = energy(pos - (pos - o) @ eps.T)
+            dE = (ep - em) / (2 * h)          # dE/d eps_ij = sum_a dE/dp_ai (p_a - o)_j = - sum_a F_ai (p_a - o)_j = W[j, i]
+            assert abs(dE - float(W[j, i])) < 1e-6 * max(1.0, float(W.abs().max())), (i, j, dE, float(W[j, i]))
