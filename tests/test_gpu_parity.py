@@ -598,3 +598,46 @@ def test_million_atom_cell_properties():
     key = pairs[:, 1] * nl.n_atoms + pairs[:, 2]
     key_t = pairs[:, 2] * nl.n_atoms + pairs[:, 1]
     assert torch.equal(key, torch.sort(key).values) and torch.equal(torch.sort(key_t).values, key)
+
+
+def test_md_callers_calculator_and_verlet():
+    """The callers either side of the path: the calculator adaptor returns predict's numbers in the caller's
+    atom order (species matched by symbol), and the device-resident integrator reproduces a hand-rolled velocity Verlet."""
+    from nnmd_b200.engine import energy_forces
+    from nnmd_b200.md import NNMDCalc, VelocityVerlet
+    from nnmd_b200.nn import BPNN
+    d, sfd = load_case("sf_cu111_json")
+    net = BPNN(dtype=torch.float32)
+    torch.manual_seed(2)
+    net.config(dict(atom_species=["Cu"], input_sizes=[len(sfd["features"])], hidden_sizes=[[16, 8]], learning_rate=0.01,
+                    l2_regularization=0.0, e_loss_coeff=1.0, f_loss_coeff=1.0, load_models=False, path="",
+                    optimizer="adam", batch_size=2, epochs=1))
+
+    class FakeAtoms:
+        positions = d["cart"][0]
+        cell = d["cell"]
+        pbc = d["pbc"].astype(bool)
+
+        def get_chemical_symbols(self):
+            return ["Cu"] * self.positions.shape[0]
+
+    calc = NNMDCalc(model=net, symm_funcs_data={"Cu": sfd})
+    res = calc.calculate(FakeAtoms())
+    E, F = net.predict({"Cu": torch.tensor(d["cart"][0], dtype=torch.float32)}, torch.tensor(d["cell"], dtype=torch.float32),
+                       {"Cu": sfd}, pbc=d["pbc"])
+    assert abs(res["energy"] - float(E.sum())) < 1e-5 * abs(float(E.sum())) and np.allclose(res["forces"], F.cpu().numpy(), atol=1e-6)
+    # integrator
+    x0 = torch.tensor(d["cart"][0], dtype=torch.float64, device=DEV)
+    v0 = torch.zeros_like(x0)
+    cell, pbc = torch.tensor(d["cell"], dtype=torch.float64, device=DEV), torch.tensor(d["pbc"], dtype=torch.float64, device=DEV)
+    atomic = net.atomic_nets[0]
+    vv = VelocityVerlet(x0, v0, mass=63.5, cell=cell, pbc=pbc, symm_funcs_data=sfd, net=atomic, dt=0.5)
+    vv.step(3)
+    x, v = x0.clone(), v0.clone()
+    f = energy_forces(x[None], cell, pbc, sfd, atomic, check=False).forces[0]
+    for _ in range(3):
+        x = x + v * 0.5 + f * (0.5 * 0.25 / 63.5)
+        fn = energy_forces(x[None], cell, pbc, sfd, atomic, check=False).forces[0]
+        v = v + (f + fn) * (0.5 * 0.5 / 63.5)
+        f = fn
+    assert torch.allclose(vv.x, x, atol=1e-12) and torch.allclose(vv.v, v, atol=1e-12) and vv.steps == 3
