@@ -106,8 +106,11 @@ constexpr int EBATCH = 64;  // (edge, third atom) records built per flush: two p
 // K3e, 4 functions per lane: 16 lanes cover the 64 functions, so the two half-warps work on two different records at
 // once.  Per record pair the warp issues ~40 instructions, 3 ex2 and 44 FMA-pipe cycles: the FMA pipe alone is the
 // limiter (the 2-per-lane form co-saturates FMA pipe, SFU and issue).  LADDER: q_{i+1} = q_i * R_X along the lane's 4 zetas.
+#ifndef NNMD_EDGE_MINB
+#define NNMD_EDGE_MINB 4
+#endif
 template <bool WITH_PHI, bool LADDER>
-__global__ void __launch_bounds__(128, 4) angular_edge4_kernel(EdgeArgs a) {
+__global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(EdgeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using MF = M<float>;
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
