@@ -101,7 +101,10 @@ __device__ __forceinline__ void make_record_edge(const NbView<float> &nb, int tj
     }
 }
 
-constexpr int EBATCH = 64;  // (edge, third atom) records built per flush: two per lane
+#ifndef NNMD_EDGE_EBATCH
+#define NNMD_EDGE_EBATCH 64
+#endif
+constexpr int EBATCH = NNMD_EDGE_EBATCH;  // (edge, third atom) records built per flush: up to two per lane
 
 // K3e, 4 functions per lane: 16 lanes cover the 64 functions, so the two half-warps work on two different records at
 // once.  Per record pair the warp issues ~40 instructions, 3 ex2 and 44 FMA-pipe cycles: the FMA pipe alone is the
@@ -150,14 +153,17 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
         const int64_t e0 = a.edge_offsets[row], e1 = a.edge_offsets[row + 1];
         const int first_gt = int((o1 - o0) - (e1 - e0));
         const int nn = stage_row<float, true>(a.posw, a.idx, o0, o1, xa, ya, za, a.rc, inv_rc, eta, nb, a.cap, first_gt);
-        // owned edges: replace the own-row slot by the slot in the OTHER endpoint's row (-1 not owned, -2 owned without slot)
-        for (int t = lane; t < nn; t += 32) {
-            const int ep = nb.epos[t];
-            int code = -1;
-            if (ep >= 0) {
+        // owned edges: replace the own-row slot by the slot in the OTHER endpoint's row (-1 not owned, -2 owned without slot).
+        // Rows are ascending, so the owned edges are the last nn - t_first staged entries.
+        int t_first = 0;
+        for (int t0 = 0; t0 < nn; t0 += 32) {
+            const int t = t0 + lane;
+            const int ep = t < nn ? nb.epos[t] : 0;
+            t_first += __popc(__ballot_sync(0xffffffffu, t < nn && ep < 0));
+            if (t < nn && ep >= 0) {
                 const int64_t j = __ldg(a.idx + o0 + first_gt + ep);
                 const int64_t lj = j - frame * a.n_atoms;
-                code = -2;
+                int code = -2;
                 if (lj < a.n_centres) {
                     const int64_t rj = frame * a.n_centres + lj;
                     const int64_t p0 = a.offsets[rj], q0 = a.edge_offsets[rj];
@@ -168,8 +174,8 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
                     }
                     code = int((p0 - q0) + (lo - p0));
                 }
+                nb.epos[t] = code;
             }
-            nb.epos[t] = code;
         }
         __syncwarp();
 
@@ -208,14 +214,14 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
             }
         };
         int cur_eid = -1;
-        int head = 0, qn = 0, pushed_total = 0;
+        int head = 0, qn = 0;
         int last_tj = -1;  // edge (row slot) of the last record already processed
 
         // process `cnt` queued (edge, third atom) pairs: phase 1 (records, one per lane) then phase 2 (functions)
         auto flush = [&](int cnt) {
             __syncwarp();
             // phase 1: every lane builds up to two records (slots lane and lane + 32)
-            const bool has0 = lane < cnt, has1 = lane + 32 < cnt;
+            const bool has0 = lane < cnt, has1 = EBATCH > 32 && lane + 32 < cnt;
             const int pk0 = has0 ? queue[(head + lane) & 255] : 0, pk1 = has1 ? queue[(head + lane + 32) & 255] : 0;
             const int tj0 = has0 ? (pk0 & 0x7fff) : -2, tj1 = has1 ? (pk1 & 0x7fff) : -2;
             int prev0 = __shfl_up_sync(0xffffffffu, tj0, 1), prev1 = __shfl_up_sync(0xffffffffu, tj1, 1);
@@ -226,24 +232,27 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
             if (!(a.dbg & 2)) {
                 if (has0) make_record_edge<WITH_PHI, LADDER>(nb, tj0, (pk0 >> 15) & 0x7fff, kind, step, inv_rc, eta, nb.epos[tj0],
                                                              recs + lane * EREC_STRIDE);
-                if (has1) make_record_edge<WITH_PHI, LADDER>(nb, tj1, (pk1 >> 15) & 0x7fff, kind, step, inv_rc, eta, nb.epos[tj1],
-                                                             recs + (lane + 32) * EREC_STRIDE);
+                if (EBATCH > 32 && has1)
+                    make_record_edge<WITH_PHI, LADDER>(nb, tj1, (pk1 >> 15) & 0x7fff, kind, step, inv_rc, eta, nb.epos[tj1],
+                                                       recs + (lane + 32) * EREC_STRIDE);
             }
             last_tj = cnt > 32 ? __shfl_sync(0xffffffffu, tj1, cnt - 33) : __shfl_sync(0xffffffffu, tj0, cnt - 1);
             const unsigned long long firsts = (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, first1)) << 32) |
                                               __ballot_sync(0xffffffffu, first0);
             __syncwarp();
+            // walk the batch edge by edge: `rest` holds the edge openings after record t (everything here is warp-uniform)
+            unsigned long long rest = firsts & ~1ull;
+            bool opens = (firsts & 1ull) != 0;
             int t = (a.dbg & 1) ? cnt : 0;
             while (t < cnt) {
-                if ((firsts >> t) & 1ull) {  // record t opens the next edge: retire the previous one (warp-uniform)
+                if (opens) {  // record t opens the next edge: retire the previous one
                     if (cur_tj >= 0) retire(cur_eid);
                     cur_eid = __float_as_int(recs[t * EREC_STRIDE + 3]);
                     cur_tj = __shfl_sync(0xffffffffu, t < 32 ? tj0 : tj1, t & 31);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { phi[i] = make_float2(0.f, 0.f); vg[i].y = 0.f; }
                 }
-                const unsigned long long rest = t < 63 ? (firsts & ~((2ull << t) - 1ull)) : 0ull;
-                const int t_end = rest ? min(__ffsll(static_cast<long long>(rest)) - 1, cnt) : cnt;
+                const int t_end = rest ? __ffsll(static_cast<long long>(rest)) - 1 : cnt;
                 const float *r = recs + (t + half) * EREC_STRIDE + class_off;
 #pragma unroll 2
                 for (int tt = t + half; tt < t_end; tt += 2, r += 2 * EREC_STRIDE) {
@@ -283,36 +292,35 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
                     for (int i = 0; i < 4; ++i) vg[i] = __ffma2_rn(q01[i], make_float2(c2.z, c2.w), vg[i]);
                 }
                 t = t_end;
+                rest &= rest - 1ull;
+                opens = true;
             }
             __syncwarp();
         };
 
-        for (int tj = 0; tj < nn; ++tj) {
+        for (int tj = t_first; tj < nn; ++tj) {
             const int ep = nb.epos[tj];
-            if (ep == -1) continue;  // the neighbour owns this edge (warp-uniform)
             const Q4<float> uj = ld4<float>(nb.u4 + 4 * tj);
-            const int pushed0 = pushed_total;
-            // 96 candidates per trip: three independent closure tests per lane (their latencies overlap), then three
-            // compactions into the ring; the ring (256) holds a partial batch (< 64) plus one trip (<= 96)
+            int pushed_edge = 0;
+            // 96 candidates per trip: three independent closure tests per lane (branch-free: the three loads are in
+            // flight together), then three compactions into the ring; the ring (256) holds a partial batch (< 64) plus
+            // one trip (<= 96)
             for (int kb = 0; kb < nn; kb += 96) {
                 bool ok[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const int tk = kb + 32 * c + lane;
-                    ok[c] = false;
-                    if (tk < nn) {
-                        const Q4<float> uk = ld4<float>(nb.u4 + 4 * tk);
-                        const float wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
-                        const float z2 = wx * wx + wy * wy + wz * wz;
-                        ok[c] = (z2 < rc2) && (z2 > 0.f);  // third side inside (0, rc) (symm_funcs.py:34-50); z2 = 0 for tk == tj
-                    }
+                    const Q4<float> uk = ld4<float>(nb.u4 + 4 * min(tk, nn - 1));
+                    const float wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
+                    const float z2 = wx * wx + wy * wy + wz * wz;
+                    ok[c] = (tk < nn) && (z2 < rc2) && (z2 > 0.f);  // third side inside (0, rc) (symm_funcs.py:34-50); z2 = 0 for tk == tj
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const unsigned m = __ballot_sync(0xffffffffu, ok[c]);
                     if (ok[c]) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 255] = tj | ((kb + 32 * c + lane) << 15);
                     const int n_ok = __popc(m);
-                    pushed_total += n_ok;
+                    pushed_edge += n_ok;
                     qn += n_ok;
                 }
                 while (qn >= EBATCH) {
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
                     qn -= EBATCH;
                 }
             }
-            if (pushed_total == pushed0 && half == 0 && ep >= 0) {  // an edge that closes no triangle still has a (zero) slot
+            if (pushed_edge == 0 && half == 0 && ep >= 0) {  // an edge that closes no triangle still has a (zero) slot
                 float *dst = a.E + (size_t(ep) * 2) * nfa + a.ebase + 4 * l16;
                 if (WITH_PHI) *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4 *>(dst + nfa) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -359,18 +367,29 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
 }
 
 // K4e: every centre collects Phi (and Gamma) of the edges it does NOT own -- the first first_gt entries of its row,
-// whose slots are one contiguous block of E.  HBM-bound streaming: 8 B per lane per edge, 256 B coalesced rows.
-// The centre's own edges were already added to dG / force by K3e.
+// whose slots are one contiguous block of E.  HBM-bound streaming.  The unit of work is one 256 B row of E (the Phi or
+// the Gamma row of an edge): a half-warp reads it with one 16 B load per lane, the two half-warps take alternate rows
+// (MODE_DG: half 0 the Phi row, half 1 the Gamma row of the same edge), GATHER_ROWS rows per half are requested before
+// any is used -- the kernel lives on memory-level parallelism.  The centre's own edges were already added to
+// dG / force by K3e.
+#ifndef NNMD_GATHER_ROWS
+#define NNMD_GATHER_ROWS 4
+#endif
+constexpr int GATHER_ROWS = NNMD_GATHER_ROWS;
 template <int MODE>
-__global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
+#ifndef NNMD_GATHER_MINB
+#define NNMD_GATHER_MINB 1
+#endif
+__global__ void __launch_bounds__(256, NNMD_GATHER_MINB) edge_gather_kernel(EdgeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
     float *ubuf = reinterpret_cast<float *>(smem_raw) + size_t(warp) * 4 * a.cap;  // (ux/d, uy/d, uz/d, slot bits)
-    float coef[2];
-    int col[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) { coef[i] = a.coef[2 * lane + i]; col[i] = a.col[2 * lane + i]; }
+    constexpr int PER = (MODE == MODE_DG) ? 2 : 1;  // rows of E read per edge
     const size_t nfa = size_t(a.nfa);
+    // this lane's row of an edge slot: Phi at +0, Gamma at +nfa
+    const size_t lane_off = size_t(a.ebase) + 4 * l16 + ((MODE == MODE_G || (MODE == MODE_DG && half == 1)) ? nfa : 0);
+    const bool phi_lane = MODE == MODE_FORCE || (MODE == MODE_DG && half == 0);
     bool bad = false;
     for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
         const int64_t frame = row / a.n_centres;
@@ -406,41 +425,61 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeArgs a) {
         }
         __syncwarp();
         nn = min(nn, a.cap);
-        float gx[2] = {0, 0}, gy[2] = {0, 0}, gz[2] = {0, 0}, gam[2] = {0, 0};
-        // batches of 4 edges: issue all loads of a batch before using any (the kernel lives on memory-level parallelism)
-        for (int t0 = 0; t0 < nn; t0 += 4) {
-            float4 u[4];
-            float2 ph[4], ga[4];
+        float gx[4] = {0, 0, 0, 0}, gy[4] = {0, 0, 0, 0}, gz[4] = {0, 0, 0, 0}, gam[4] = {0, 0, 0, 0};
+        const int n_items = nn * PER;
+        for (int i0 = 0; i0 < n_items; i0 += 2 * GATHER_ROWS) {
+            float4 v[GATHER_ROWS];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int t = min(t0 + k, nn - 1);
-                u[k] = *reinterpret_cast<const float4 *>(ubuf + 4 * t);
-                const float *src = a.E + (size_t(__float_as_int(u[k].w)) * 2) * nfa + a.ebase + 2 * lane;
-                ph[k] = (MODE != MODE_G) ? __ldcs(reinterpret_cast<const float2 *>(src)) : make_float2(0.f, 0.f);
-                ga[k] = (MODE != MODE_FORCE) ? __ldcs(reinterpret_cast<const float2 *>(src + nfa)) : make_float2(0.f, 0.f);
+            for (int k = 0; k < GATHER_ROWS; ++k) {
+                const int item = min(i0 + 2 * k + half, n_items - 1);
+                const int slot = __float_as_int(ubuf[4 * (item / PER) + 3]);
+                v[k] = __ldcs(reinterpret_cast<const float4 *>(a.E + (size_t(slot) * 2) * nfa + lane_off));
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (t0 + k >= nn) break;
-                gx[0] = fmaf(ph[k].x, u[k].x, gx[0]); gy[0] = fmaf(ph[k].x, u[k].y, gy[0]); gz[0] = fmaf(ph[k].x, u[k].z, gz[0]);
-                gx[1] = fmaf(ph[k].y, u[k].x, gx[1]); gy[1] = fmaf(ph[k].y, u[k].y, gy[1]); gz[1] = fmaf(ph[k].y, u[k].z, gz[1]);
-                gam[0] += ga[k].x; gam[1] += ga[k].y;
+            for (int k = 0; k < GATHER_ROWS; ++k) {
+                const int item = i0 + 2 * k + half;
+                if (item < n_items) {
+                    if (phi_lane) {
+                        const float4 u = *reinterpret_cast<const float4 *>(ubuf + 4 * (item / PER));
+                        gx[0] = fmaf(v[k].x, u.x, gx[0]); gy[0] = fmaf(v[k].x, u.y, gy[0]); gz[0] = fmaf(v[k].x, u.z, gz[0]);
+                        gx[1] = fmaf(v[k].y, u.x, gx[1]); gy[1] = fmaf(v[k].y, u.y, gy[1]); gz[1] = fmaf(v[k].y, u.z, gz[1]);
+                        gx[2] = fmaf(v[k].z, u.x, gx[2]); gy[2] = fmaf(v[k].z, u.y, gy[2]); gz[2] = fmaf(v[k].z, u.z, gz[2]);
+                        gx[3] = fmaf(v[k].w, u.x, gx[3]); gy[3] = fmaf(v[k].w, u.y, gy[3]); gz[3] = fmaf(v[k].w, u.z, gz[3]);
+                    } else {
+                        gam[0] += v[k].x; gam[1] += v[k].y; gam[2] += v[k].z; gam[3] += v[k].w;
+                    }
+                }
+            }
+        }
+        // bring the two half-warps together: half 0 ends up with the complete sums of its four functions
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (MODE == MODE_FORCE) {
+                gx[i] += __shfl_xor_sync(0xffffffffu, gx[i], 16);
+                gy[i] += __shfl_xor_sync(0xffffffffu, gy[i], 16);
+                gz[i] += __shfl_xor_sync(0xffffffffu, gz[i], 16);
+            } else {
+                gam[i] += __shfl_xor_sync(0xffffffffu, gam[i], 16);
             }
         }
         float fx = 0, fy = 0, fz = 0;
+        if (half == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            if (col[i] < 0) continue;
-            const int64_t o = row * a.nf + col[i];
-            if (MODE != MODE_FORCE) a.G[o] = 0.5f * coef[i] * (a.G[o] + gam[i]);  // ordered (j,k): both edges of a pair counted
-            if (MODE == MODE_DG) {  // add to the share K3e wrote for the centre's own edges
-                const float dx = a.dG[3 * o] - coef[i] * gx[i], dy = a.dG[3 * o + 1] - coef[i] * gy[i], dz = a.dG[3 * o + 2] - coef[i] * gz[i];
-                a.dG[3 * o] = dx; a.dG[3 * o + 1] = dy; a.dG[3 * o + 2] = dz;
-                bad |= !(isfinite(dx) && isfinite(dy) && isfinite(dz));
-            }
-            if (MODE == MODE_FORCE) {
-                const float wv = a.w[o] * coef[i];
-                fx = fmaf(wv, gx[i], fx); fy = fmaf(wv, gy[i], fy); fz = fmaf(wv, gz[i], fz);
+            for (int i = 0; i < 4; ++i) {
+                const int col = a.col[4 * l16 + i];
+                if (col < 0) continue;
+                const float coef = a.coef[4 * l16 + i];
+                const int64_t o = row * a.nf + col;
+                if (MODE != MODE_FORCE) a.G[o] = 0.5f * coef * (a.G[o] + gam[i]);  // ordered (j,k): both edges of a pair counted
+                if (MODE == MODE_DG) {  // add to the share K3e wrote for the centre's own edges
+                    const float dx = a.dG[3 * o] - coef * gx[i], dy = a.dG[3 * o + 1] - coef * gy[i], dz = a.dG[3 * o + 2] - coef * gz[i];
+                    a.dG[3 * o] = dx; a.dG[3 * o + 1] = dy; a.dG[3 * o + 2] = dz;
+                    bad |= !(isfinite(dx) && isfinite(dy) && isfinite(dz));
+                }
+                if (MODE == MODE_FORCE) {
+                    const float wv = a.w[o] * coef;
+                    fx = fmaf(wv, gx[i], fx); fy = fmaf(wv, gy[i], fy); fz = fmaf(wv, gz[i], fz);
+                }
             }
         }
         if (MODE == MODE_FORCE) {
