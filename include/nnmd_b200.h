@@ -179,6 +179,22 @@ int nnmd_mlp_train_backward(int dtype, int n_layers, const int32_t *sizes, const
                             void *const *grad_weights, void *const *grad_biases, void *stream);
 int nnmd_force_contract_backward(int dtype, const void *gf, const void *dG, int64_t n_rows, int nf, void *u, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K8  training loss and its gradient in one launch.  Replaces bpnn.py:196-215 (`_loss`: e_coeff * MSELoss(e.sum(1), E)
+ *     + f_coeff / 3 * MSELoss(f, F), criterion fixed to MSELoss by bpnn.py:164) and the part of loss.backward()
+ *     (bpnn.py:366) that runs from the scalar down to the per-atom energies and forces.
+ *   n_species blocks of atoms (species are concatenated on the atom axis), n_atoms host int32[n_species];
+ *   e / f / ge / gf: host arrays of n_species DEVICE pointers;  e[s], ge[s] (n_frames, n_atoms[s]);
+ *   f[s], gf[s] (n_frames, n_atoms[s], 3);  E dev (n_frames);  F dev (n_frames, sum n_atoms, 3), species in order;
+ *   ge = dL/de, gf = dL/df;  out dev [3] = (energy term, force term, total), coefficients included.
+ *   ws: nnmd_loss_workspace_bytes(n_frames) device bytes, ZEROED once before the first call (reusable afterwards).
+ *   Deterministic: per-frame partial sums are reduced in a fixed order.
+ * ------------------------------------------------------------------------------------- */
+size_t nnmd_loss_workspace_bytes(int64_t n_frames);
+int nnmd_loss_mse(int dtype, int n_species, const int32_t *n_atoms, const void *const *e, const void *const *f,
+                  const void *E, const void *F, int64_t n_frames, double e_coeff, double f_coeff, void *const *ge,
+                  void *const *gf, void *ws, void *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,15 @@ class FrameBatches:
     def __len__(self):
         return (self.indices.numel() + self.batch_size - 1) // self.batch_size
 
+    def index_batches(self, device):
+        """The frame indices of every batch of one epoch as device tensors (one host-to-device copy per epoch)."""
+        idx = self.indices
+        if self.shuffle:
+            idx = idx[torch.randperm(idx.numel())]
+        idx = idx.to(device)
+        for s in range(0, idx.numel(), self.batch_size):
+            yield idx[s:s + self.batch_size]
+
     def __iter__(self):
         idx = self.indices
         if self.shuffle:
@@ -160,7 +169,7 @@ class BPNN(torch.nn.Module):
             kwargs["lr"] = self.learning_rate
             self.optim = available_optimizers[name](**kwargs)
             self._graphs_ok = False
-        self._graph_state = None
+        self._plans, self._opt_ready = {}, False
 
     # ------------------------------------------------------------------------------------------------- loss
     def _loss(self, e_nn, energies, f_nn, forces):
@@ -195,49 +204,62 @@ class BPNN(torch.nn.Module):
         self.optim.step()
         out.copy_(torch.stack([e_loss.detach(), f_loss.detach(), loss.detach()]))
 
-    def _train_step(self, g, dG, energy, forces, out):
-        """The training step is ~40 small launches (launch-bound, ~1 ms); batches of a repeated shape are replayed from
-        CUDA graphs instead (~0.2 ms).  First batch of a shape: eager (creates the optimizer state); second: capture;
-        later ones: copy the batch into the static buffers and replay.  With several ranks the gradient all-reduce
-        sits between two graphs (forward+backward | optimizer)."""
-        if not self._graphs_ok:
-            return self._train_step_eager(g, dG, energy, forces, out)
-        key = tuple((s, tuple(g[s].shape)) for s in self.species) + (tuple(energy.shape), tuple(forces.shape))
-        st = self._graph_state
-        if st is None or st["key"] != key:
-            self._graph_state = {"key": key, "graphs": None}
-            return self._train_step_eager(g, dG, energy, forces, out)
-        if st["graphs"] is None:
-            try:
-                st["g"] = {s: g[s].detach().clone() for s in self.species}
-                st["dG"] = {s: dG[s].detach().clone() for s in self.species}
-                st["E"], st["F"], st["out"] = energy.clone(), forces.clone(), torch.zeros(3, device=self.device)
+    # ---- fused step: K6 -> K4c -> K8 -> K4c' -> K7 on static buffers, replayed from CUDA graphs
+    def _fused_ok(self, g, dG) -> bool:
+        if self.device.type != "cuda" or len(self.species) > 8 or os.environ.get("NNMD_NO_FUSED_STEP", "0") == "1":
+            return False
+        if not isinstance(self.criterion, torch.nn.MSELoss) or self.criterion.reduction != "mean":
+            return False
+        ok = all(net.activation is torch.sigmoid for net in self.atomic_nets)
+        ok = ok and all(p.dtype == torch.float32 and p.is_cuda for net in self.atomic_nets for p in net.parameters())
+        return ok and all(g[s].dtype == torch.float32 and g[s].is_cuda and g[s].dim() == 3 and dG[s].dtype == torch.float32
+                          for s in self.species)
+
+    def _plan_for(self, shapes: dict, n_frames: int):
+        from .functional import TrainStepPlan
+        key = (n_frames,) + tuple((s, tuple(shapes[s])) for s in self.species)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 4:  # full batches plus the ragged last one; anything else is churn
+                self._plans.pop(next(iter(self._plans)))
+            plan = TrainStepPlan(self.atomic_nets, self.species, shapes, n_frames, self.device, self.e_loss_coeff,
+                                 self.f_loss_coeff, self._flat_grads)
+            self._plans[key] = plan
+        return plan
+
+    def _step_plan(self, plan):
+        """Run one loaded plan: forward + backward (graph 1) | gradient all-reduce | optimizer (graph 2)."""
+        if self._graphs_ok and plan.graphs is None and self._opt_ready:
+            try:  # the optimizer state exists (one eager step was done): capture both halves
                 fwd_bwd, opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()
                 with torch.cuda.graph(fwd_bwd):
-                    self._flat_grads.flat.zero_()
-                    e_nn, f_nn = self._energies_forces(st["g"], st["dG"])
-                    loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), st["E"], f_nn, st["F"])
-                    loss.backward()
-                    st["out"].copy_(torch.stack([e_loss.detach(), f_loss.detach(), loss.detach()]))
+                    plan.run()
                 with torch.cuda.graph(opt, pool=fwd_bwd.pool()):
                     self.optim.step()
-                st["graphs"] = (fwd_bwd, opt)
+                plan.graphs = (fwd_bwd, opt)
+                # a capture does not execute: fall through to the replay below
             except Exception as exc:  # capture not possible here: stay eager, loudly
                 print(f"nnmd_b200: CUDA-graph capture of the training step failed ({exc!r}); continuing without graphs")
                 self._graphs_ok = False
-                return self._train_step_eager(g, dG, energy, forces, out)
+        if plan.graphs is not None:
+            plan.graphs[0].replay()
+            self._flat_grads.allreduce()  # frames are sharded across ranks (no-op on 1 rank)
+            plan.graphs[1].replay()
         else:
-            for s in self.species:
-                st["g"][s].copy_(g[s])
-                st["dG"][s].copy_(dG[s])
-            st["E"].copy_(energy)
-            st["F"].copy_(forces)
-        fwd_bwd, opt = st["graphs"]
-        fwd_bwd.replay()
-        self._flat_grads.allreduce()
-        opt.replay()
-        out.copy_(st["out"])
+            plan.run()
+            self._flat_grads.allreduce()
+            self.optim.step()
+            self._opt_ready = True
+
+    def _train_step(self, g, dG, energy, forces, out):
+        """One optimisation step on a batch given as tensors (DataLoader-style tuples)."""
+        if not self._fused_ok(g, dG):
+            return self._train_step_eager(g, dG, energy, forces, out)
+        plan = self._plan_for({s: g[s].shape for s in self.species}, int(energy.shape[0]))
+        plan.load(g, dG, energy, forces)
+        self._step_plan(plan)
+        out.copy_(plan.out)
 
     def _run_epoch(self, loader, train: bool, desc: str):
         for net in self.atomic_nets:
@@ -247,6 +269,22 @@ class BPNN(torch.nn.Module):
         if train and getattr(self, "_flat_grads", None) is None:
             # gradients live in one flat buffer: a single in-place all-reduce per step when frames are sharded
             self._flat_grads = FlatGradients([p for net in self.atomic_nets for p in net.parameters()])
+            self._plans, self._opt_ready = {}, False
+        if train and isinstance(loader, FrameBatches) and loader.base.energies.is_cuda \
+                and self._fused_ok({s: v[0] for s, v in loader.base.sf_data.items()}, {s: v[1] for s, v in loader.base.sf_data.items()}):
+            # batches are gathered straight into the static buffers of the step (no per-batch tensors, no copies)
+            shapes = {s: loader.base.sf_data[s][0].shape for s in self.species}
+            for plan in self._plans.values():
+                plan.acc.zero_()
+            for sel in tqdm(loader.index_batches(self.device), desc=desc, total=len(loader)):
+                plan = self._plan_for(shapes, int(sel.numel()))
+                plan.load_indexed(loader.base, sel)
+                self._step_plan(plan)
+            for plan in self._plans.values():
+                tot += plan.acc
+                plan.acc.zero_()
+            tot /= len(loader)
+            return tot[0], tot[1], tot[2]
         for g, dG, energy, forces in tqdm(loader, desc=desc, total=len(loader)):
             energy = energy.to(device=self.device)
             forces = forces.to(device=self.device)

@@ -11,9 +11,31 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
+from .. import dist
 from ..features import calculate_sf
 
 _NOT_SPECIES = ("forces", "energy", "velocities")
+
+
+def scale_targets(energies: torch.Tensor, forces: torch.Tensor, presharded: bool = False):
+    """Min-max scaling of the targets (reference: dataset.py:85-90): E -> (E - emin) / (emax - emin), F -> F / (emax - emin).
+
+    The extrema are GLOBAL over the training set.  `presharded`: the tensors hold only this rank's frames, so emin / emax
+    are completed with one MIN and one MAX all-reduce; otherwise the caller passed every frame and no
+    collective is needed.  Returns (energies, forces, emin, emax).
+    """
+    emin, emax = energies.min(), energies.max()
+    if presharded and dist._world()[1] > 1:
+        import torch.distributed as td
+        emin, emax = emin.clone(), emax.clone()
+        td.all_reduce(emin, op=td.ReduceOp.MIN)
+        td.all_reduce(emax, op=td.ReduceOp.MAX)
+    return (energies - emin) / (emax - emin), forces / (emax - emin), emin, emax
+
+
+def cache_name(kind: str, species: str, rank: int, world: int) -> str:
+    """`g_{spec}.pt` / `dg_{spec}.pt` as in the reference; one file per rank when the frame axis is sharded."""
+    return f"{kind}_{species}.pt" if world == 1 else f"{kind}_{species}.rank{rank}of{world}.pt"
 
 
 class TrainAtomicDataset(Dataset):
@@ -36,8 +58,12 @@ class TrainAtomicDataset(Dataset):
     def make_atomic_dataset(cls, dataset: dict, **kwargs) -> "TrainAtomicDataset":
         """dict from `input_parser` -> dataset of (g, dG, E, F) on the GPU (reference: dataset.py:33-123).
 
-        kwargs: saved=True reloads g_/dg_ caches from the CWD; disable_tqdm accepted; cache=False skips writing
-        the .pt files (extension; the reference always writes them).
+        kwargs: saved=True reloads g_/dg_ caches from the CWD; disable_tqdm accepted.  Extensions (the reference has none
+        of them): cache=False skips writing the .pt files; shard=True (default when torch.distributed runs with
+        world > 1) keeps only this rank's contiguous block of frames -- descriptors are computed for that block alone,
+        targets are scaled with the extrema of ALL frames, caches are written per rank; presharded=True says the dict
+        already holds only this rank's frames (extrema then come from an all-reduce); frames_per_pass=n bounds the
+        descriptor workspace by sending n frames at a time through the CUDA path.
         """
         device = torch.device("cuda")
         frames = dataset["reference_data"]
@@ -46,26 +72,37 @@ class TrainAtomicDataset(Dataset):
         cell = torch.tensor(np.asarray(dataset["unit_cell"]), **f32)
         pbc = torch.tensor(np.asarray(dataset["pbc"]), **f32)
         species = [k for k in frames[0].keys() if k not in _NOT_SPECIES]
-        cart = {s: torch.tensor(np.array([fr[s]["positions"] for fr in frames]), **f32) for s in species}
+        rank, world = kwargs.get("rank"), kwargs.get("world")
+        if rank is None or world is None:
+            rank, world = dist._world()
+        presharded = bool(kwargs.get("presharded", False))
+        shard = bool(kwargs.get("shard", world > 1)) and not presharded
+
         energies = torch.tensor(np.array([fr["energy"] for fr in frames]), **f32)
         if energies.ndim == 1:
             energies = energies.unsqueeze(1)
         forces = torch.tensor(np.array([fr["forces"] for fr in frames]), **f32)
-
-        emin, emax = energies.min(), energies.max()
-        energies = (energies - emin) / (emax - emin)
-        forces = forces / (emax - emin)
+        energies, forces, _, _ = scale_targets(energies, forces, presharded)
+        mine = dist.shard_frames(len(frames), rank, world) if shard else range(len(frames))
+        if shard:
+            energies, forces = energies[mine.start:mine.stop], forces[mine.start:mine.stop]
+        cart = {s: torch.tensor(np.array([frames[i][s]["positions"] for i in mine]), **f32) for s in species}
+        files_world = world if (shard or presharded) else 1
 
         sf_data = {}
+        per_pass = int(kwargs.get("frames_per_pass", 0)) or len(mine)
         for s in species:
             if kwargs.get("saved"):
-                g = torch.load(f"g_{s}.pt", map_location=device)
-                dg = torch.load(f"dg_{s}.pt", map_location=device)
+                g = torch.load(cache_name("g", s, rank, files_world), map_location=device)
+                dg = torch.load(cache_name("dg", s, rank, files_world), map_location=device)
             else:
-                g, dg = calculate_sf(cart[s], cell, pbc, params[s], disable_tqdm=kwargs.get("disable_tqdm", False))
+                parts = [calculate_sf(cart[s][lo:lo + per_pass], cell, pbc, params[s], disable_tqdm=kwargs.get("disable_tqdm", False))
+                         for lo in range(0, max(len(mine), 1), max(per_pass, 1))]
+                g = parts[0][0] if len(parts) == 1 else torch.cat([q[0] for q in parts], dim=0)
+                dg = parts[0][1] if len(parts) == 1 else torch.cat([q[1] for q in parts], dim=0)
                 if kwargs.get("cache", True):
-                    torch.save(g, f"g_{s}.pt")
-                    torch.save(dg, f"dg_{s}.pt")
+                    torch.save(g, cache_name("g", s, rank, files_world))
+                    torch.save(dg, cache_name("dg", s, rank, files_world))
             if not g.requires_grad:
                 g.requires_grad = True
             sf_data[s] = (g, dg)

@@ -108,3 +108,96 @@ class _ForceContract(torch.autograd.Function):
 def force_contract(dE: torch.Tensor, dG: torch.Tensor) -> torch.Tensor:
     """F[...,a,:] = - sum_f dE[...,a,f] dG[...,a,f,:]   (differentiable w.r.t. dE)."""
     return _ForceContract.apply(dE, dG)
+
+
+class TrainStepPlan:
+    """Static buffers and the launch sequence of one training step for ONE batch shape, without an autograd graph:
+
+        K6 (e, dE/dg per species) -> K4c (forces) -> K8 (loss, dL/de, dL/df) -> K4c' (dL/d(dE/dg)) -> K7 (weight gradients)
+
+    i.e. bpnn.py:342-366 (forward, `_loss`, `loss.backward()`) in 2 + 4 * n_species launches.  The gradients are ADDED to
+    the `.grad` tensors of the parameters (views of a FlatGradients buffer that `run` zeroes first).  All buffers are
+    static, so `run` can be captured into a CUDA graph and replayed; `load` / `load_indexed` refill them.
+    float32 CUDA tensors only (the reference trains in float32: dataset.py:48, atomic_nn.py).
+    """
+
+    def __init__(self, nets, species, shapes, n_frames, device, e_coeff, f_coeff, flat_grads):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.species, self.nets, self.device, self.flat = list(species), list(nets), torch.device(device), flat_grads
+        self.n_frames, self.e_coeff, self.f_coeff = int(n_frames), float(e_coeff), float(f_coeff)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.n_atoms = [int(shapes[s][1]) for s in self.species]
+        self.n_feat = [int(shapes[s][2]) for s in self.species]
+        B = self.n_frames
+        self.g = {s: torch.empty(B, n, f, **f32) for s, n, f in zip(self.species, self.n_atoms, self.n_feat)}
+        self.dG = {s: torch.empty(B, n, f, 3, **f32) for s, n, f in zip(self.species, self.n_atoms, self.n_feat)}
+        self.e = [torch.empty(B * n, **f32) for n in self.n_atoms]
+        self.dE = [torch.empty(B * n, f, **f32) for n, f in zip(self.n_atoms, self.n_feat)]
+        self.f = [torch.empty(B * n, 3, **f32) for n in self.n_atoms]
+        self.ge = [torch.empty(B * n, **f32) for n in self.n_atoms]
+        self.gf = [torch.empty(B * n, 3, **f32) for n in self.n_atoms]
+        self.u = [torch.empty(B * n, f, **f32) for n, f in zip(self.n_atoms, self.n_feat)]
+        self.E = torch.empty(B, **f32)
+        self.F = torch.empty(B, sum(self.n_atoms), 3, **f32)
+        self.out = torch.zeros(3, **f32)   # (energy term, force term, total) of the last step
+        self.acc = torch.zeros(3, **f32)   # running sum over the steps of an epoch
+        self.ws = torch.zeros(int(self.lib.nnmd_loss_workspace_bytes(B)), dtype=torch.uint8, device=self.device)
+        self.graphs = None
+        # parameter / gradient pointer tables (the optimizer updates parameters in place: the pointers are stable)
+        self._keep = []
+        self.tables = []
+        for net in self.nets:
+            ws = [m.weight for m in net.model]
+            bs = [m.bias for m in net.model]
+            for p in ws + bs:
+                if p.dtype != torch.float32 or not p.is_cuda or p.grad is None or not p.is_contiguous():
+                    raise _lib.NnmdError("TrainStepPlan needs contiguous float32 CUDA parameters with FlatGradients views")
+            sizes, c_sizes = _sizes(ws)
+            self.tables.append((len(ws), c_sizes, _param_arrays(ws), _param_arrays(bs),
+                                _param_arrays([p.grad for p in ws]), _param_arrays([p.grad for p in bs])))
+        S = len(self.species)
+        self.c_natoms = (ctypes.c_int32 * S)(*self.n_atoms)
+        self.c_e, self.c_f = _param_arrays(self.e), _param_arrays(self.f)
+        self.c_ge, self.c_gf = _param_arrays(self.ge), _param_arrays(self.gf)
+
+    # ---- filling the static buffers
+    def load(self, g, dG, energy, forces):
+        for s in self.species:
+            self.g[s].copy_(g[s].detach())
+            self.dG[s].copy_(dG[s])
+        self.E.copy_(energy.reshape(-1))
+        self.F.copy_(forces)
+
+    def load_indexed(self, base, sel):
+        """Gather the frames `sel` (device int64) of a TrainAtomicDataset straight into the static buffers."""
+        for s in self.species:
+            gs, dgs = base.sf_data[s]
+            torch.index_select(gs.detach(), 0, sel, out=self.g[s])
+            torch.index_select(dgs, 0, sel, out=self.dG[s])
+        torch.index_select(base.energies.reshape(-1), 0, sel, out=self.E)
+        torch.index_select(base.forces, 0, sel, out=self.F)
+
+    # ---- the step
+    def run(self):
+        lib, st, F32 = self.lib, _lib.stream_ptr(), _lib.dtype_code(torch.float32)
+        self.flat.flat.zero_()
+        with torch.cuda.device(self.device):
+            for i, s in enumerate(self.species):
+                L, c_sizes, c_w, c_b, _, _ = self.tables[i]
+                rows = self.n_frames * self.n_atoms[i]
+                _lib.check(lib.nnmd_mlp_energy_grad(F32, _lib.MLP_EXACT, L, c_sizes, c_w, c_b, _lib.ptr(self.g[s]), rows,
+                                                    _lib.ptr(self.e[i]), _lib.ptr(self.dE[i]), st))
+                _lib.check(lib.nnmd_force_contract(F32, _lib.ptr(self.dE[i]), _lib.ptr(self.dG[s]), rows, self.n_feat[i],
+                                                   _lib.ptr(self.f[i]), st))
+            _lib.check(lib.nnmd_loss_mse(F32, len(self.species), self.c_natoms, self.c_e, self.c_f, _lib.ptr(self.E),
+                                         _lib.ptr(self.F), self.n_frames, self.e_coeff, self.f_coeff, self.c_ge, self.c_gf,
+                                         _lib.ptr(self.ws), _lib.ptr(self.out), st))
+            for i, s in enumerate(self.species):
+                L, c_sizes, c_w, c_b, c_gw, c_gb = self.tables[i]
+                rows = self.n_frames * self.n_atoms[i]
+                _lib.check(lib.nnmd_force_contract_backward(F32, _lib.ptr(self.gf[i]), _lib.ptr(self.dG[s]), rows,
+                                                            self.n_feat[i], _lib.ptr(self.u[i]), st))
+                _lib.check(lib.nnmd_mlp_train_backward(F32, L, c_sizes, c_w, c_b, _lib.ptr(self.g[s]), rows,
+                                                       _lib.ptr(self.ge[i]), _lib.ptr(self.u[i]), c_gw, c_gb, st))
+        self.acc.add_(self.out)

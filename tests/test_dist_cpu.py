@@ -39,6 +39,14 @@ def _worker(rank, world, port, out_dir):
     assert q1.grad.data_ptr() == fg.flat.data_ptr() and torch.allclose(q1.grad, torch.full((2, 3), 1.5))
     assert torch.allclose(q2.grad, torch.full((4,), 15.0))
     frames = list(dist.shard_frames(11))
+    # dataset build on pre-sharded frames: the target scaling uses the GLOBAL extrema (one MIN and one MAX all-reduce)
+    from nnmd_b200.nn.dataset import cache_name, scale_targets
+    e_all = torch.tensor([[3.0], [-1.0], [7.0], [2.0], [5.0]])
+    mine = dist.shard_frames(5)
+    e_s, f_s, emin, emax = scale_targets(e_all[mine.start:mine.stop], torch.ones(len(mine), 2, 3), presharded=True)
+    assert float(emin) == -1.0 and float(emax) == 7.0
+    assert torch.allclose(e_s, (e_all[mine.start:mine.stop] + 1.0) / 8.0) and torch.allclose(f_s, torch.full_like(f_s, 0.125))
+    assert cache_name("dg", "Cu", rank, world) == f"dg_Cu.rank{rank}of2.pt" and cache_name("g", "Cu", 0, 1) == "g_Cu.pt"
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), owned=shard.owned_idx.numpy(), local=local.numpy(),
              grad=p.grad.numpy(), frames=np.asarray(frames))
     td.destroy_process_group()

@@ -154,10 +154,150 @@ def test_cuda_graph_training_matches_eager(monkeypatch):
         for ep in range(3):
             losses.append(float(net._train_loop(ep, loader)[2]))
             sched.step()
-        assert (net._graph_state is not None and net._graph_state.get("graphs") is not None) == (mode == "graph")
+        assert len(net._plans) == 1 and all((pl.graphs is not None) == (mode == "graph") for pl in net._plans.values())
         finals[mode] = ([p.detach().clone() for p in net.atomic_nets[0].parameters()], losses, float(net.optim.param_groups[0]["lr"]))
     assert abs(finals["graph"][2] - 0.02 * 0.125) < 1e-9 and abs(finals["eager"][2] - 0.02 * 0.125) < 1e-9
     np.testing.assert_allclose(finals["graph"][1], finals["eager"][1], rtol=1e-4)
     for a, b in zip(finals["graph"][0], finals["eager"][0]):
         assert relerr(a.cpu(), b.cpu()) < 1e-4
     assert finals["graph"][1][-1] < finals["graph"][1][0]
+
+
+def _parser_dict(n_frames=7, seed=3):
+    """A dict shaped like `input_parser` output (reference: nnmd/io/input_parser.py:52-54,103-107), two species."""
+    rng = np.random.default_rng(seed)
+    a = 3.6
+    base = np.array([[i, j, k] for i in range(2) for j in range(2) for k in range(2)], dtype=np.float64) * a + 0.9
+    sfd = {"features": [2, 2, 4], "params": [[5.0, 0.5, 1.0], [5.0, 0.5, 2.5], [5.0, 0.05, 2.0, 1.0]], "n_features": 3}
+    frames = []
+    for _ in range(n_frames):
+        p = base + rng.normal(0, 0.08, base.shape)
+        frames.append({"A": {"positions": p[:5]}, "B": {"positions": p[5:]}, "forces": rng.normal(0, 1, (8, 3)),
+                       "energy": float(rng.normal(-20, 3))})
+    return {"reference_data": frames, "symmetry_functions_set": {"A": sfd, "B": sfd}, "unit_cell": np.eye(3) * 2 * a,
+            "pbc": np.array([True, True, True]), "n_atoms": 8}
+
+
+def test_make_atomic_dataset_one_pass_sharded_and_cached(tmp_path, monkeypatch):
+    """SURVEY 8f-2 / 8e: the dataset build keeps the reference's contract (dataset.py:33-123) in one pass per species;
+    frame shards reproduce the unsharded build block by block with GLOBAL target scaling; chunked passes and the cache
+    round trip change nothing."""
+    from nnmd_b200.features import calculate_sf
+    from nnmd_b200.nn import TrainAtomicDataset
+    monkeypatch.chdir(tmp_path)
+    d = _parser_dict()
+    full = TrainAtomicDataset.make_atomic_dataset(d, disable_tqdm=True)
+    assert sorted(os.listdir(tmp_path)) == ["dg_A.pt", "dg_B.pt", "g_A.pt", "g_B.pt"]
+    E = torch.tensor([fr["energy"] for fr in d["reference_data"]], dtype=torch.float32)
+    span = float(E.max() - E.min())
+    assert torch.allclose(full.energies.cpu().flatten(), (E - E.min()) / span, atol=1e-6)
+    F = torch.tensor(np.array([fr["forces"] for fr in d["reference_data"]]), dtype=torch.float32)
+    assert torch.allclose(full.forces.cpu(), F / span, rtol=1e-6)
+    cell = torch.tensor(d["unit_cell"], dtype=torch.float32, device=DEV)
+    pbc = torch.ones(3, device=DEV)
+    for s, sl in (("A", slice(0, 5)), ("B", slice(5, 8))):
+        cart = torch.tensor(np.array([fr[s]["positions"] for fr in d["reference_data"]]), dtype=torch.float32, device=DEV)
+        g, dg = calculate_sf(cart, cell, pbc, d["symmetry_functions_set"][s], disable_tqdm=True)
+        assert torch.equal(full.sf_data[s][0].detach(), g) and torch.equal(full.sf_data[s][1], dg)
+        assert full.sf_data[s][0].requires_grad and full.sf_data[s][0].shape == (7, sl.stop - sl.start, 3)
+    again = TrainAtomicDataset.make_atomic_dataset(d, saved=True)
+    chunked = TrainAtomicDataset.make_atomic_dataset(d, cache=False, frames_per_pass=3, disable_tqdm=True)
+    for s in "AB":
+        for k in (0, 1):
+            assert torch.equal(again.sf_data[s][k].detach(), full.sf_data[s][k].detach())
+            assert torch.equal(chunked.sf_data[s][k].detach(), full.sf_data[s][k].detach())
+    shards = [TrainAtomicDataset.make_atomic_dataset(d, shard=True, rank=r, world=2, disable_tqdm=True) for r in range(2)]
+    assert "g_A.rank1of2.pt" in os.listdir(tmp_path)
+    assert len(shards[0]) + len(shards[1]) == len(full) == 7
+    assert torch.equal(torch.cat([q.energies for q in shards]), full.energies)
+    assert torch.equal(torch.cat([q.forces for q in shards]), full.forces)
+    for s in "AB":
+        for k in (0, 1):
+            assert torch.equal(torch.cat([q.sf_data[s][k].detach() for q in shards]), full.sf_data[s][k].detach())
+    g0, dG0, e0, f0 = full[2]
+    assert set(g0) == {"A", "B"} and dG0["B"].shape == (3, 3, 3) and e0.shape == (1,) and f0.shape == (8, 3)
+
+
+@pytest.mark.parametrize("n_species", [1, 2])
+def test_fused_loss_kernel_and_step_plan_match_autograd(n_species):
+    """K8 and the graph-free step (K6 -> K4c -> K8 -> K4c' -> K7) against torch.autograd on the reference's formulas
+    (bpnn.py:196-215, 342-366): loss terms, dL/de, dL/df and every weight gradient."""
+    from nnmd_b200 import _lib
+    from nnmd_b200.dist import FlatGradients
+    from nnmd_b200.nn import AtomicNN
+    from nnmd_b200.nn.functional import TrainStepPlan
+    torch.manual_seed(7 + n_species)
+    B, ec, fc = 9, 1.3, 0.6
+    species = ["A", "B"][:n_species]
+    n_atoms, n_feat = [5, 3][:n_species], [6, 4][:n_species]
+    nets = [AtomicNN(f, [8, 5]).to(DEV) for f in n_feat]
+    g = {s: torch.rand(B, n, f, device=DEV) for s, n, f in zip(species, n_atoms, n_feat)}
+    dG = {s: torch.randn(B, n, f, 3, device=DEV) for s, n, f in zip(species, n_atoms, n_feat)}
+    E = torch.rand(B, 1, device=DEV)
+    F = torch.randn(B, sum(n_atoms), 3, device=DEV) * 0.1
+    # torch reference
+    es, fs = [], []
+    for net, s in zip(nets, species):
+        x = g[s].clone().requires_grad_(True)
+        e = net(x)
+        dE = torch.autograd.grad(e.sum(), x, create_graph=True)[0]
+        es.append(e)
+        fs.append(-torch.einsum("ijk,ijkl->ijl", dE, dG[s]))
+    e_all, f_all = torch.cat(es, dim=1), torch.cat(fs, dim=1)
+    le = ec * torch.mean((e_all.sum(dim=1) - E) ** 2)
+    lf = fc / 3 * torch.mean((f_all - F) ** 2)
+    params = [p for net in nets for p in net.parameters()]
+    ref_grads = torch.autograd.grad(le + lf, params)
+    # fused plan
+    flat = FlatGradients(params)
+    plan = TrainStepPlan(nets, species, {s: g[s].shape for s in species}, B, DEV, ec, fc, flat)
+    plan.load(g, dG, E, F)
+    plan.run()
+    plan.run()  # the loss workspace is reusable and the gradient buffer is re-zeroed: a second run gives the same numbers
+    torch.cuda.synchronize()
+    assert abs(float(plan.out[0] - le)) < 1e-5 * float(le) and abs(float(plan.out[1] - lf)) < 1e-5 * float(lf)
+    assert abs(float(plan.out[2] - (le + lf))) < 1e-5 * float(le + lf)
+    assert torch.allclose(plan.acc, 2 * plan.out, rtol=1e-6)
+    for p, r in zip(params, ref_grads):
+        assert relerr(p.grad.cpu(), r.cpu()) < 1e-3
+    # K8 alone: gradients w.r.t. the per-atom energies and forces
+    e_leaf = [e.detach().clone().requires_grad_(True) for e in es]
+    f_leaf = [f.detach().clone().requires_grad_(True) for f in fs]
+    loss = ec * torch.mean((torch.cat(e_leaf, 1).sum(dim=1) - E) ** 2) + fc / 3 * torch.mean((torch.cat(f_leaf, 1) - F) ** 2)
+    grads = torch.autograd.grad(loss, e_leaf + f_leaf)
+    for i in range(n_species):
+        assert relerr(plan.ge[i].view(B, -1).cpu(), grads[i].squeeze(-1).cpu()) < 1e-5
+        assert relerr(plan.gf[i].view(B, -1, 3).cpu(), grads[n_species + i].cpu()) < 1e-5
+    lib = _lib.load()
+    assert lib.nnmd_loss_workspace_bytes(B) >= 16 * B
+    bad = lib.nnmd_loss_mse(0, 0, None, None, None, None, None, B, 1.0, 1.0, None, None, None, None, None)
+    assert bad != 0 and b"species" in lib.nnmd_last_error()
+
+
+def test_fused_training_epoch_matches_the_autograd_path(monkeypatch):
+    """`_train_loop` on FrameBatches (index-gathered static buffers, CUDA graphs) follows the same trajectory as the
+    autograd path (NNMD_NO_FUSED_STEP=1), including a ragged last batch."""
+    from nnmd_b200.nn import BPNN, TrainAtomicDataset
+    from nnmd_b200.nn.bpnn import batch_loader
+    torch.manual_seed(11)
+    M, N, Fd = 23, 6, 7
+    g = torch.rand(M, N, Fd, device=DEV)
+    dg = torch.randn(M, N, Fd, 3, device=DEV)
+    E = torch.rand(M, 1, device=DEV)
+    Fr = torch.randn(M, N, 3, device=DEV) * 0.1
+    cfg = dict(atom_species=["X"], input_sizes=[Fd], hidden_sizes=[[10, 6]], learning_rate=0.01, l2_regularization=1e-4,
+               e_loss_coeff=1.0, f_loss_coeff=0.5, load_models=False, path="", optimizer="adam", batch_size=5, epochs=1)
+    results = []
+    for fused in (True, False):
+        monkeypatch.setenv("NNMD_NO_FUSED_STEP", "0" if fused else "1")
+        torch.manual_seed(5)
+        net = BPNN(dtype=torch.float32)
+        net.config(cfg)
+        ds = TrainAtomicDataset({"X": (g.clone().requires_grad_(True), dg)}, E, Fr, {})
+        loader = batch_loader(ds, 5, shuffle=False)
+        losses = [[float(v) for v in net._train_loop(ep, loader)] for ep in range(3)]
+        results.append((losses, [p.detach().clone() for p in net.atomic_nets[0].parameters()]))
+    (la, pa), (lb, pb) = results
+    assert np.allclose(la, lb, rtol=2e-4), (la, lb)
+    for a, b in zip(pa, pb):
+        assert relerr(a.cpu(), b.cpu()) < 2e-3

@@ -63,7 +63,7 @@ def main():
     from nnmd_b200 import dist
     from nnmd_b200.features import calculate_sf
     from nnmd_b200.nn import BPNN, TrainAtomicDataset
-    from nnmd_b200.nn.bpnn import batch_loader
+    from nnmd_b200.nn.bpnn import FrameBatches, batch_loader
     from nnmd_b200.features import calculate_params
     mine = dist.shard_frames(args.frames, rank, world)
     t0 = time.perf_counter()
@@ -113,16 +113,9 @@ def main():
     def run(n_steps):
         done = 0
         while done < n_steps:
-            class _Cap:
-                def __init__(self, it, n): self.it, self.n = it, n
-                def __len__(self): return self.n
-                def __iter__(self):
-                    for k, b in enumerate(self.it):
-                        if k >= self.n:
-                            break
-                        yield b
             n = min(len(loader), n_steps - done)
-            net._train_loop(0, _Cap(loader, n))
+            part = loader if n == len(loader) else FrameBatches(ds, torch.arange(n * per_rank_batch), per_rank_batch, True)
+            net._train_loop(0, part)
             done += n
     run(args.warmup)
     torch.cuda.synchronize()
