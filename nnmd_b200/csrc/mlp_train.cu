@@ -263,6 +263,10 @@ static int train_bwd_run(int n_layers, const int32_t *sizes, const void *const *
     return NNMD_OK;
 }
 
+// mlp_fast.cu: register-tiled kernel for two hidden layers of <= 64 units (negative return: shape not covered)
+int train_bwd_fast(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases, const void *x,
+                   int64_t n_rows, const void *ge, const void *u, void *const *gW, void *const *gb, cudaStream_t st);
+
 }  // namespace nnmd
 
 using namespace nnmd;
@@ -281,6 +285,10 @@ extern "C" int nnmd_mlp_train_backward(int dtype, int n_layers, const int32_t *s
     for (int l = 0; l < n_layers; ++l)
         if (!weights[l] || !biases[l] || !grad_weights[l] || !grad_biases[l]) return set_err(NNMD_ERR_INVALID, "mlp_train: null parameter pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NNMD_F32) {
+        const int rc = train_bwd_fast(n_layers, sizes, weights, biases, x, n_rows, ge, u, grad_weights, grad_biases, st);
+        if (rc >= 0) return rc;
+    }
     if (dtype == NNMD_F32) return train_bwd_run<float, 32>(n_layers, sizes, weights, biases, x, n_rows, ge, u, grad_weights, grad_biases, st);
     return train_bwd_run<double, 16>(n_layers, sizes, weights, biases, x, n_rows, ge, u, grad_weights, grad_biases, st);
 }
