@@ -195,6 +195,14 @@ int nnmd_loss_mse(int dtype, int n_species, const int32_t *n_atoms, const void *
                   const void *E, const void *F, int64_t n_frames, double e_coeff, double f_coeff, void *const *ge,
                   void *const *gf, void *ws, void *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Batch assembly for the training step (replaces the DataLoader collation of bpnn.py:234-236 on the cached
+ * tensors of dataset.py:33-123): dst[k][i, :] = src[k][sel[i], :] for n_arrays row-major arrays in one launch.
+ *   src / dst: host arrays of DEVICE pointers; row_bytes host int64[n_arrays] (multiples of 4); sel dev int64[n_sel]
+ * ------------------------------------------------------------------------------------- */
+int nnmd_gather_rows(int n_arrays, const void *const *src, void *const *dst, const int64_t *row_bytes,
+                     const int64_t *sel, int64_t n_sel, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,3 +140,59 @@ extern "C" int nnmd_loss_mse(int dtype, int n_species, const int32_t *n_atoms, c
     if (dtype == NNMD_F32) return loss_run<float>(n_species, n_atoms, e, f, E, F, n_frames, e_coeff, f_coeff, ge, gf, ws, out, st);
     return loss_run<double>(n_species, n_atoms, e, f, E, F, n_frames, e_coeff, f_coeff, ge, gf, ws, out, st);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batch assembly: rows `sel` of several arrays (descriptors, descriptor gradients, energies, forces of the cached
+// training set) are copied into the static buffers of the training step by ONE launch instead of one index_select
+// per array (reference: the DataLoader collation of bpnn.py:234-236).
+namespace nnmd {
+
+constexpr int GATHER_MAX_ARRAYS = 20;
+
+struct GatherArgs {
+    int n_arrays;
+    const unsigned char *src[GATHER_MAX_ARRAYS];
+    unsigned char *dst[GATHER_MAX_ARRAYS];
+    long long row_bytes[GATHER_MAX_ARRAYS];
+    const long long *sel;
+};
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs a) {
+    const long long row = a.sel[blockIdx.x];
+    for (int k = 0; k < a.n_arrays; ++k) {
+        const long long nb = a.row_bytes[k];
+        const unsigned char *s = a.src[k] + row * nb;
+        unsigned char *d = a.dst[k] + (long long)blockIdx.x * nb;
+        if (((nb | (long long)(size_t)s | (long long)(size_t)d) & 15) == 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+            uint4 *d4 = reinterpret_cast<uint4 *>(d);
+            for (long long i = threadIdx.x; i < nb / 16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+        } else {
+            const unsigned int *s1 = reinterpret_cast<const unsigned int *>(s);
+            unsigned int *d1 = reinterpret_cast<unsigned int *>(d);
+            for (long long i = threadIdx.x; i < nb / 4; i += blockDim.x) d1[i] = __ldg(s1 + i);
+        }
+    }
+}
+
+}  // namespace nnmd
+
+extern "C" int nnmd_gather_rows(int n_arrays, const void *const *src, void *const *dst, const int64_t *row_bytes,
+                                const int64_t *sel, int64_t n_sel, void *stream) {
+    if (n_arrays < 1 || n_arrays > GATHER_MAX_ARRAYS) return set_err(NNMD_ERR_INVALID, "gather: 1..%d arrays supported", GATHER_MAX_ARRAYS);
+    if (n_sel < 0 || n_sel > 0x7fffffffLL) return set_err(NNMD_ERR_INVALID, "gather: bad row count");
+    if (n_sel == 0) return NNMD_OK;
+    if (!src || !dst || !row_bytes || !sel) return set_err(NNMD_ERR_INVALID, "gather: null pointer");
+    GatherArgs a;
+    a.n_arrays = n_arrays;
+    for (int k = 0; k < n_arrays; ++k) {
+        if (!src[k] || !dst[k]) return set_err(NNMD_ERR_INVALID, "gather: null pointer for array %d", k);
+        if (row_bytes[k] <= 0 || row_bytes[k] % 4) return set_err(NNMD_ERR_INVALID, "gather: row size of array %d must be a positive multiple of 4 bytes", k);
+        a.src[k] = (const unsigned char *)src[k]; a.dst[k] = (unsigned char *)dst[k]; a.row_bytes[k] = row_bytes[k];
+    }
+    a.sel = (const long long *)sel;
+    cudaStream_t st = (cudaStream_t)stream;
+    gather_rows_kernel<<<unsigned(n_sel), 256, 0, st>>>(a);
+    NNMD_LAUNCH_CHECK("gather_rows_kernel");
+    return NNMD_OK;
+}

@@ -7,7 +7,8 @@
 //     floats, so that "atoms x units" products read one 16 B vector of atoms and one 16 B vector of weights per
 //     reduction step for 16 (TM = 64) FMAs, and the weight-gradient outer products (reduction over the atoms of the
 //     tile) read eight 16 B vectors for 64 FMAs;
-//   * the weights are staged once per block (W0^T, W1^T and W1, zero-padded to 64 units), the weight gradients are
+//   * the weights are staged once per block (W0^T, W1^T and W1, zero-padded to 64 units; the input axis is padded
+//     to a multiple of 16 only, which lets two blocks share an SM for <= 32 descriptors), the weight gradients are
 //     kept in registers across all the tiles of a block and leave with ONE atomicAdd per weight and block;
 //   * padded units carry zero weights, which makes every padded contribution vanish (sigmoid(0) only ever meets a
 //     zero weight), and atoms past the end of the last tile carry x = u = ge = 0 and contribute nothing.
@@ -24,7 +25,7 @@ constexpr int FT_H = 64;  // padded hidden width
 
 struct FastTrainArgs {
     int K0, H1, H2;
-    int K0B;  // padded input width: 64 or 128
+    int K0R;  // input rows held in shared memory: K0 rounded up to a multiple of 16
     const float *W0, *b0, *W1, *b1, *W2;
     float *gW0, *gb0, *gW1, *gb1, *gW2, *gb2;
     const float *x, *ge, *u;
@@ -80,9 +81,9 @@ __device__ __forceinline__ void gemm_atoms(const float *__restrict__ A, int K, c
     for (int j = 0; j < 4; ++j) epi(4 * tn + j, MM * tm, acc[j]);
 }
 
-// acc[i][j] += sum_m A[tn + 16 i][m] * B[kbase + tk + 16 j][m]   (rows strided by 16: conflict-free 16 B loads)
+// acc[i][j] += sum_m A[tn + 16 i][m] * B[kbase + tk + 16 j][m]   for j < nj  (rows strided by 16: conflict-free 16 B loads)
 template <int TM>
-__device__ __forceinline__ void outer_acc(const float *__restrict__ A, const float *__restrict__ B, int kbase, float (&acc)[4][4]) {
+__device__ __forceinline__ void outer_acc(const float *__restrict__ A, const float *__restrict__ B, int kbase, int nj, float (&acc)[4][4]) {
     constexpr int P = TM + 4;
     const int tk = threadIdx.x & 15, tn = threadIdx.x >> 4;
     const float *a = A + tn * P, *b = B + (kbase + tk) * P;
@@ -92,58 +93,57 @@ __device__ __forceinline__ void outer_acc(const float *__restrict__ A, const flo
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             av[i] = *reinterpret_cast<const float4 *>(a + 16 * i * P + m);
-            bv[i] = *reinterpret_cast<const float4 *>(b + 16 * i * P + m);
+            bv[i] = i < nj ? *reinterpret_cast<const float4 *>(b + 16 * i * P + m) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            if (j >= nj) continue;  // block-uniform
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int i = 0; i < 4; ++i) {
                 float s = acc[i][j];
                 s = fmaf(av[i].x, bv[j].x, s); s = fmaf(av[i].y, bv[j].y, s);
                 s = fmaf(av[i].z, bv[j].z, s); s = fmaf(av[i].w, bv[j].w, s);
                 acc[i][j] = s;
             }
+        }
     }
 }
 
-// sums[n] += sum_m A[n][m] (* w[m] when w != nullptr) for the 64 rows: one warp per row, eight rows per pass
-template <int TM>
-__device__ __forceinline__ void row_sums(const float *__restrict__ A, const float *__restrict__ w, float *__restrict__ sums) {
-    constexpr int P = TM + 4;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int n = warp; n < FT_H; n += FT_THREADS / 32) {
-        float s = 0.f;
+// sum over the TM atoms of a unit: the 16 lanes that share tn hold them (MM each)
+template <int MM>
+__device__ __forceinline__ float unit_sum(const float (&v)[MM]) {
+    float s = 0.f;
 #pragma unroll
-        for (int m = lane; m < TM; m += 32) s += w ? A[n * P + m] * w[m] : A[n * P + m];
-        s = warp_sum(s);
-        if (lane == 0) sums[n] += s;
-    }
+    for (int i = 0; i < MM; ++i) s += v[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
 }
 
 template <int TM, int NKG>
 __global__ void __launch_bounds__(FT_THREADS) mlp_train_fast_kernel(FastTrainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int P = TM + 4, MM = TM / 16, K0B = 64 * NKG;
+    constexpr int P = TM + 4, MM = TM / 16;
+    const int K0R = a.K0R;
     float *sm = reinterpret_cast<float *>(smem_raw);
     // weights
-    float *W0T = sm;                   // [K0B][64]   W0T[k][n] = W0[n][k]
-    float *W1T = W0T + K0B * FT_H;     // [64][64]    W1T[k][n] = W1[n][k]
+    float *W0T = sm;                   // [K0R][64]   W0T[k][n] = W0[n][k]
+    float *W1T = W0T + K0R * FT_H;     // [64][64]    W1T[k][n] = W1[n][k]
     float *W1N = W1T + FT_H * FT_H;    // [64][64]    W1N[n][k] = W1[n][k]
     float *W2s = W1N + FT_H * FT_H;    // [64]
     float *b0s = W2s + FT_H, *b1s = b0s + FT_H;
     float *gb0s = b1s + FT_H, *gb1s = gb0s + FT_H, *gw2s = gb1s + FT_H;  // block-level sums
     float *ges = gw2s + FT_H;          // [TM] dL/de of the tile's atoms
     // per-atom quantities of the tile, [unit][atom]
-    float *X = ges + TM;               // [K0B]
-    float *U = X + K0B * P;            // [K0B]  rho_0
-    float *H1 = U + K0B * P;           // [64]
+    float *X = ges + TM;               // [K0R]
+    float *U = X + K0R * P;            // [K0R]  rho_0
+    float *H1 = U + K0R * P;           // [64]
     float *R1 = H1 + FT_H * P;         // [64]   r_1, then S_0
     float *D0 = R1 + FT_H * P;         // [64]   delta_0, then zeta_0
     float *RHO1 = D0 + FT_H * P;       // [64]
     float *H2 = RHO1 + FT_H * P;       // [64]
     float *D1 = H2 + FT_H * P;         // [64]   delta_1, then zeta_1
-    float *RHO2 = D1 + FT_H * P;       // [64]
-    float *sm_end = RHO2 + FT_H * P;
+    float *sm_end = D1 + FT_H * P;
     const int tid = threadIdx.x;
     const int K0 = a.K0, H1n = a.H1, H2n = a.H2;
 
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(FT_THREADS) mlp_train_fast_kernel(FastTrainArg
         if (a.u) {
             // ---- 7. gW0 += delta_0 (x) rho_0
 #pragma unroll
-            for (int g = 0; g < NKG; ++g) outer_acc<TM>(D0, U, 64 * g, g0[g]);
+            for (int g = 0; g < NKG; ++g) outer_acc<TM>(D0, U, 64 * g, min(4, (K0R - 64 * g) / 16), g0[g]);
             // ---- 8. v_0 = W0 rho_0;  rho_1 = v_0 * s(h1);  S_0 = v_0 * r_1 * s(h1) (1 - 2 h1)  (overwrites r_1)
             gemm_atoms<TM>(U, K0, W0T, FT_H, [&](int n, int mm, const float (&v)[MM]) {
                 float h[MM], r[MM], rho[MM], S[MM];
@@ -230,38 +230,36 @@ __global__ void __launch_bounds__(FT_THREADS) mlp_train_fast_kernel(FastTrainArg
             });
             __syncthreads();
             // ---- 9. gW1 += delta_1 (x) rho_1
-            outer_acc<TM>(D1, RHO1, 0, g1);
+            outer_acc<TM>(D1, RHO1, 0, 4, g1);
             __syncthreads();  // step 10 overwrites delta_1
         } else {
             for (float *p = R1 + tid; p < R1 + FT_H * P; p += FT_THREADS) *p = 0.f;  // S_0 = 0, rho_1 = 0 (RHO1 stays zero)
             __syncthreads();
         }
         // ---- 10. v_1 = W1 rho_1;  rho_2 = v_1 * s(h2);  zeta_1 = W2 s(h2) (ge + v_1 (1 - 2 h2))  (overwrites delta_1)
+        //      11. gW2 += sum_m rho_2 + ge h2 ;  gb1 += sum_m zeta_1   (each unit has one owner thread: no race)
         gemm_atoms<TM>(RHO1, H1n, W1T, FT_H, [&](int n, int mm, const float (&v)[MM]) {
-            float h[MM], rho[MM], z[MM];
+            float h[MM], q[MM], z[MM];
             AtomVec<MM>::ld(H2 + n * P + mm, h);
             const float w2 = W2s[n];
 #pragma unroll
             for (int i = 0; i < MM; ++i) {
                 const float s = h[i] * (1.f - h[i]);
-                rho[i] = v[i] * s;
+                q[i] = v[i] * s + ges[mm + i] * h[i];
                 z[i] = w2 * s * (ges[mm + i] + v[i] * (1.f - 2.f * h[i]));
             }
-            AtomVec<MM>::st(RHO2 + n * P + mm, rho);
             AtomVec<MM>::st(D1 + n * P + mm, z);
+            const float sq = unit_sum<MM>(q), sz = unit_sum<MM>(z);
+            if ((tid & 15) == 0) { gw2s[n] += sq; gb1s[n] += sz; }
         });
-        __syncthreads();
-        // ---- 11. gW2 += sum_m rho_2 + ge h2 ;  gb2 += sum_m ge ;  gb1 += sum_m zeta_1
-        row_sums<TM>(RHO2, nullptr, gw2s);
-        row_sums<TM>(H2, ges, gw2s);
-        row_sums<TM>(D1, nullptr, gb1s);
-        if (tid == 0) {
+        if (tid == 0) {  // gb2 += sum_m ge
             float s = 0.f;
             for (int m = 0; m < TM; ++m) s += ges[m];
             gb2_acc += s;
         }
+        __syncthreads();
         // ---- 12. gW1 += zeta_1 (x) h1
-        outer_acc<TM>(D1, H1, 0, g1);
+        outer_acc<TM>(D1, H1, 0, 4, g1);
         // ---- 13. zeta_0[k] = (sum_n W1[n][k] zeta_1[n]) s(h1) + S_0   (overwrites delta_0; all readers of delta_0 are done)
         gemm_atoms<TM>(D1, H2n, W1N, FT_H, [&](int k, int mm, const float (&v)[MM]) {
             float h[MM], S[MM], z[MM];
@@ -270,12 +268,13 @@ __global__ void __launch_bounds__(FT_THREADS) mlp_train_fast_kernel(FastTrainArg
 #pragma unroll
             for (int i = 0; i < MM; ++i) z[i] = v[i] * h[i] * (1.f - h[i]) + S[i];
             AtomVec<MM>::st(D0 + k * P + mm, z);
+            const float sz = unit_sum<MM>(z);  // gb0 += sum_m zeta_0
+            if ((tid & 15) == 0) gb0s[k] += sz;
         });
         __syncthreads();
-        // ---- 14. gW0 += zeta_0 (x) x ;  gb0 += sum_m zeta_0
+        // ---- 14. gW0 += zeta_0 (x) x
 #pragma unroll
-        for (int g = 0; g < NKG; ++g) outer_acc<TM>(D0, X, 64 * g, g0[g]);
-        row_sums<TM>(D0, nullptr, gb0s);
+        for (int g = 0; g < NKG; ++g) outer_acc<TM>(D0, X, 64 * g, min(4, (K0R - 64 * g) / 16), g0[g]);
         __syncthreads();
     }
     // ---- write-back: one atomicAdd per weight and block
@@ -301,15 +300,15 @@ __global__ void __launch_bounds__(FT_THREADS) mlp_train_fast_kernel(FastTrainArg
     }
 }
 
-template <int TM, int NKG>
-static size_t fast_smem_bytes() {
-    constexpr int P = TM + 4, K0B = 64 * NKG;
-    return sizeof(float) * size_t(K0B * FT_H + 2 * FT_H * FT_H + 6 * FT_H + TM + 2 * K0B * P + 7 * FT_H * P);
+template <int TM>
+static size_t fast_smem_bytes(int K0R) {
+    constexpr int P = TM + 4;
+    return sizeof(float) * (size_t(K0R) * FT_H + 2 * FT_H * FT_H + 6 * FT_H + TM + 2 * size_t(K0R) * P + 6 * FT_H * P);
 }
 
 template <int TM, int NKG>
 static int fast_launch(const FastTrainArgs &a, cudaStream_t st) {
-    const size_t smem = fast_smem_bytes<TM, NKG>();
+    const size_t smem = fast_smem_bytes<TM>(a.K0R);
     auto kern = mlp_train_fast_kernel<TM, NKG>;
     NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int occ = 1;
@@ -330,18 +329,20 @@ int train_bwd_fast(int n_layers, const int32_t *sizes, const void *const *weight
     if (n_layers != 3 || sizes[1] > FT_H || sizes[2] > FT_H || sizes[0] > 128 || sizes[3] != 1) return -1;
     if (const char *env = getenv("NNMD_MLP_TRAIN_GENERIC")) if (env[0] == '1') return -1;
     FastTrainArgs a;
-    a.K0 = sizes[0]; a.H1 = sizes[1]; a.H2 = sizes[2]; a.K0B = sizes[0] <= 64 ? 64 : 128;
+    a.K0 = sizes[0]; a.H1 = sizes[1]; a.H2 = sizes[2]; a.K0R = (sizes[0] + 15) / 16 * 16;
     a.W0 = (const float *)weights[0]; a.W1 = (const float *)weights[1]; a.W2 = (const float *)weights[2];
     a.b0 = (const float *)biases[0]; a.b1 = (const float *)biases[1];
     a.gW0 = (float *)gW[0]; a.gW1 = (float *)gW[1]; a.gW2 = (float *)gW[2];
     a.gb0 = (float *)gb[0]; a.gb1 = (float *)gb[1]; a.gb2 = (float *)gb[2];
     a.x = (const float *)x; a.ge = (const float *)ge; a.u = (const float *)u; a.n_rows = n_rows;
-    // one block per SM either way: take the tile height with the shorter critical path (rounds x atoms per tile);
-    // wide inputs only fit with 32-atom tiles
+    // tile height: 32-atom tiles let two blocks share an SM while the input axis is short; otherwise take the height
+    // with the shorter critical path (rounds x atoms per tile); inputs wider than 64 only fit with 32-atom tiles
+    if (a.K0R > 64) return fast_launch<32, 2>(a, st);
     const int64_t sms = sm_count();
-    const int64_t path64 = ((n_rows + 63) / 64 + sms - 1) / sms * 64, path32 = ((n_rows + 31) / 32 + sms - 1) / sms * 32;
-    if (a.K0B == 64) return path32 < path64 ? fast_launch<32, 1>(a, st) : fast_launch<64, 1>(a, st);
-    return fast_launch<32, 2>(a, st);
+    const int64_t occ32 = fast_smem_bytes<32>(a.K0R) <= 112 * 1024 ? 2 : 1;
+    const int64_t path64 = ((n_rows + 63) / 64 + sms - 1) / sms * 64;
+    const int64_t path32 = ((n_rows + 31) / 32 + sms * occ32 - 1) / (sms * occ32) * 32;
+    return path32 <= path64 ? fast_launch<32, 1>(a, st) : fast_launch<64, 1>(a, st);
 }
 
 }  // namespace nnmd

@@ -170,13 +170,23 @@ class TrainStepPlan:
         self.F.copy_(forces)
 
     def load_indexed(self, base, sel):
-        """Gather the frames `sel` (device int64) of a TrainAtomicDataset straight into the static buffers."""
+        """Gather the frames `sel` (device int64) of a TrainAtomicDataset straight into the static buffers (one launch)."""
+        src, dst = [], []
         for s in self.species:
             gs, dgs = base.sf_data[s]
-            torch.index_select(gs.detach(), 0, sel, out=self.g[s])
-            torch.index_select(dgs, 0, sel, out=self.dG[s])
-        torch.index_select(base.energies.reshape(-1), 0, sel, out=self.E)
-        torch.index_select(base.forces, 0, sel, out=self.F)
+            src += [gs.detach(), dgs]
+            dst += [self.g[s], self.dG[s]]
+        src += [base.energies.reshape(-1), base.forces]
+        dst += [self.E, self.F]
+        for a, b in zip(src, dst):
+            if a.dtype != b.dtype or not a.is_contiguous() or a.shape[1:] != b.shape[1:] or a.device != b.device:
+                raise _lib.NnmdError("load_indexed: the cached tensors do not match the plan (float32, contiguous, same frame shape)")
+        n = len(src)
+        rows = (ctypes.c_int64 * n)(*[(a.numel() // max(a.shape[0], 1)) * a.element_size() for a in src])
+        sel = sel.contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nnmd_gather_rows(n, _param_arrays(src), _param_arrays(dst), rows, _lib.ptr(sel), sel.numel(),
+                                                 _lib.stream_ptr()))
 
     # ---- the step
     def run(self):
