@@ -9,6 +9,7 @@
 // produces 4 neurons of one atom per step, so a weight fetched once (warp-uniform, L1-resident) feeds 32 atoms.
 // NNMD_MLP_EXACT: fp32 / fp64 FMA arithmetic (parity path).  The tensor-core (TF32) variant lives in mlp_tc.cu.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -299,6 +300,11 @@ __global__ void __launch_bounds__(MLP2_THREADS, 1) mlp2_kernel(Mlp2Args a) {
 }
 
 // returns NNMD_OK after launching, or -1 when the network does not fit (caller falls back to v1)
+// mlp_fast.cu: tile kernel for two hidden layers of <= 64 units (negative return: shape not covered)
+int mlp_fwd_fast(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases, const void *x,
+                 int64_t n_rows, void *e, void *dEdx, cudaStream_t st);
+constexpr int64_t MLP_FAST_MAX_ROWS = INT64_MAX;  // measured faster than mlp2_kernel at 13.5k and at 1M rows
+
 static int mlp2_try(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases,
                     const void *x, int64_t n_rows, void *e, void *dEdx, cudaStream_t st) {
     Mlp2Args a;
@@ -383,6 +389,13 @@ extern "C" int nnmd_mlp_energy_grad(int dtype, int precision, int n_layers, cons
     }
     if (precision != NNMD_MLP_EXACT) return set_err(NNMD_ERR_INVALID, "mlp: bad precision %d", precision);
     if (dtype == NNMD_F32) {
+        // first choice: the tile kernel of mlp_fast.cu (weights in shared memory, register-tiled GEMMs); NNMD_MLP_FWD=v skips it
+        const char *env = getenv("NNMD_MLP_FWD");
+        const bool fast = env ? env[0] == 'f' : n_rows <= MLP_FAST_MAX_ROWS;
+        if (fast) {
+            const int rf = mlp_fwd_fast(n_layers, sizes, weights, biases, x, n_rows, e, dEdx, st);
+            if (rf >= 0) return rf;
+        }
         const int r = mlp2_try(n_layers, sizes, weights, biases, x, n_rows, e, dEdx, st);
         if (r >= 0) return r;
         return mlp_run<float>(n_layers, sizes, weights, biases, x, n_rows, e, dEdx, st);

@@ -54,10 +54,13 @@ template <> struct AtomVec<2> {
 
 // C[n][m] = sum_k A[k][m] * Bt[k][n]   for the 64 units n and the TM atoms m of the tile.
 // Thread (tm, tn): atoms MM*tm .. MM*tm+MM-1, units 4*tn .. 4*tn+3.  epi(n, m0, v[MM]) receives one unit at a time.
+// Threads whose units lie at or beyond `ncols` do nothing (the function contains no barrier).
 template <int TM, typename Epi>
-__device__ __forceinline__ void gemm_atoms(const float *__restrict__ A, int K, const float *__restrict__ Bt, int ldb, Epi epi) {
+__device__ __forceinline__ void gemm_atoms(const float *__restrict__ A, int K, const float *__restrict__ Bt, int ldb, Epi epi,
+                                           int ncols = FT_H) {
     constexpr int P = TM + 4, MM = TM / 16;
     const int tm = threadIdx.x & 15, tn = threadIdx.x >> 4;
+    if (4 * tn >= ncols) return;
     float acc[4][MM];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -343,6 +346,153 @@ int train_bwd_fast(int n_layers, const int32_t *sizes, const void *const *weight
     const int64_t path64 = ((n_rows + 63) / 64 + sms - 1) / sms * 64;
     const int64_t path32 = ((n_rows + 31) / 32 + sms * occ32 - 1) / (sms * occ32) * 32;
     return path32 <= path64 ? fast_launch<32, 1>(a, st) : fast_launch<64, 1>(a, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K6 for the same shapes: e = net(x) and dE/dx (reference: bpnn.py:343-349) with the tile machinery above.
+struct FastFwdArgs {
+    int K0, H1, H2, K0R;
+    const float *W0, *b0, *W1, *b1, *W2, *b2;
+    const float *x;
+    float *e, *dE;  // dE may be nullptr
+    int64_t n_rows;
+};
+
+template <int TM>
+__global__ void __launch_bounds__(FT_THREADS) mlp_fwd_fast_kernel(FastFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int P = TM + 4, MM = TM / 16;
+    const int K0R = a.K0R;
+    float *sm = reinterpret_cast<float *>(smem_raw);
+    float *W0T = sm;                    // [K0R][64]
+    float *W0N = W0T + K0R * FT_H;      // [64][K0R]   W0N[n][k] = W0[n][k]
+    float *W1T = W0N + FT_H * K0R;      // [64][64]
+    float *W1N = W1T + FT_H * FT_H;     // [64][64]
+    float *W2s = W1N + FT_H * FT_H, *b0s = W2s + FT_H, *b1s = b0s + FT_H;
+    float *ep = b1s + FT_H;             // [16][TM] partial energies (one row per tn)
+    float *X = ep + 16 * TM;            // [K0R], later dE/dx of the tile
+    float *H1 = X + K0R * P, *H2 = H1 + FT_H * P, *D1 = H2 + FT_H * P, *D0 = D1 + FT_H * P;
+    float *sm_end = D0 + FT_H * P;
+    const int tid = threadIdx.x, tn = tid >> 4;
+    const int K0 = a.K0, H1n = a.H1, H2n = a.H2;
+    for (float *p = sm + tid; p < sm_end; p += FT_THREADS) *p = 0.f;
+    __syncthreads();
+    for (int i = tid; i < H1n * K0; i += FT_THREADS) {
+        const int n = i / K0, k = i - n * K0;
+        const float w = __ldg(a.W0 + i);
+        W0T[k * FT_H + n] = w; W0N[n * K0R + k] = w;
+    }
+    for (int i = tid; i < H2n * H1n; i += FT_THREADS) {
+        const int n = i / H1n, k = i - n * H1n;
+        const float w = __ldg(a.W1 + i);
+        W1T[k * FT_H + n] = w; W1N[n * FT_H + k] = w;
+    }
+    for (int i = tid; i < H2n; i += FT_THREADS) { W2s[i] = __ldg(a.W2 + i); b1s[i] = __ldg(a.b1 + i); }
+    for (int i = tid; i < H1n; i += FT_THREADS) b0s[i] = __ldg(a.b0 + i);
+    const float b2 = __ldg(a.b2);
+    __syncthreads();
+    const int64_t n_tiles = (a.n_rows + TM - 1) / TM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t m0 = tile * TM;
+        const int valid = int(min(int64_t(TM), a.n_rows - m0));
+        for (int i = tid; i < TM * K0; i += FT_THREADS) {
+            const int m = i / K0, k = i - m * K0;
+            X[k * P + m] = m < valid ? __ldg(a.x + (m0 + m) * K0 + k) : 0.f;
+        }
+        __syncthreads();
+        gemm_atoms<TM>(X, K0, W0T, FT_H, [&](int n, int mm, const float (&v)[MM]) {
+            float o[MM];
+#pragma unroll
+            for (int i = 0; i < MM; ++i) o[i] = sigm_f(v[i] + b0s[n]);
+            AtomVec<MM>::st(H1 + n * P + mm, o);
+        });
+        __syncthreads();
+        {
+            float pe[MM];
+#pragma unroll
+            for (int i = 0; i < MM; ++i) pe[i] = 0.f;
+            gemm_atoms<TM>(H1, H1n, W1T, FT_H, [&](int n, int mm, const float (&v)[MM]) {
+                float o[MM], d[MM];
+                const float w2 = W2s[n];
+#pragma unroll
+                for (int i = 0; i < MM; ++i) {
+                    o[i] = sigm_f(v[i] + b1s[n]);
+                    d[i] = w2 * o[i] * (1.f - o[i]);
+                    pe[i] = fmaf(w2, o[i], pe[i]);
+                }
+                AtomVec<MM>::st(D1 + n * P + mm, d);
+            });
+            AtomVec<MM>::st(ep + tn * TM + MM * (tid & 15), pe);
+        }
+        __syncthreads();
+        for (int m = tid; m < valid; m += FT_THREADS) {
+            float s = b2;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) s += ep[r * TM + m];
+            a.e[m0 + m] = s;
+        }
+        if (a.dE) {
+            // delta_0 = ((delta_1 W1) * s(h1));  dE/dx[k] = sum_n delta_0[n] W0[n][k]
+            gemm_atoms<TM>(D1, H2n, W1N, FT_H, [&](int k, int mm, const float (&v)[MM]) {
+                float h[MM], d[MM];
+                AtomVec<MM>::ld(H1 + k * P + mm, h);
+#pragma unroll
+                for (int i = 0; i < MM; ++i) d[i] = v[i] * h[i] * (1.f - h[i]);
+                AtomVec<MM>::st(D0 + k * P + mm, d);
+            });
+            __syncthreads();
+            for (int c0 = 0; c0 < K0R; c0 += FT_H)
+                gemm_atoms<TM>(D0, H1n, W0N + c0, K0R, [&](int k, int mm, const float (&v)[MM]) {
+                    AtomVec<MM>::st(X + (c0 + k) * P + mm, v);
+                }, K0R - c0);
+            __syncthreads();
+            for (int i = tid; i < valid * K0; i += FT_THREADS) {
+                const int m = i / K0, k = i - m * K0;
+                a.dE[m0 * K0 + i] = X[k * P + m];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int TM>
+static size_t fwd_smem_bytes(int K0R) {
+    constexpr int P = TM + 4;
+    return sizeof(float) * (2 * size_t(K0R) * FT_H + 2 * FT_H * FT_H + 3 * FT_H + 16 * TM + size_t(K0R) * P + 4 * FT_H * P);
+}
+
+template <int TM>
+static int fwd_launch(const FastFwdArgs &a, cudaStream_t st) {
+    const size_t smem = fwd_smem_bytes<TM>(a.K0R);
+    auto kern = mlp_fwd_fast_kernel<TM>;
+    NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int occ = 1;
+    NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FT_THREADS, smem));
+    if (occ < 1) occ = 1;
+    const int64_t n_tiles = (a.n_rows + TM - 1) / TM;
+    const int64_t blocks = std::min<int64_t>(n_tiles, int64_t(sm_count()) * occ);
+    ProfScope prof(PROF_MLP, st);
+    kern<<<unsigned(blocks), FT_THREADS, smem, st>>>(a);
+    NNMD_LAUNCH_CHECK("mlp_fwd_fast_kernel");
+    return NNMD_OK;
+}
+
+// Negative return: shape not covered (the caller falls back to the other fp32 kernels).
+int mlp_fwd_fast(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases, const void *x,
+                 int64_t n_rows, void *e, void *dEdx, cudaStream_t st) {
+    if (n_layers != 3 || sizes[1] > FT_H || sizes[2] > FT_H || sizes[0] > 128 || sizes[3] != 1) return -1;
+    FastFwdArgs a;
+    a.K0 = sizes[0]; a.H1 = sizes[1]; a.H2 = sizes[2]; a.K0R = (sizes[0] + 15) / 16 * 16;
+    a.W0 = (const float *)weights[0]; a.W1 = (const float *)weights[1]; a.W2 = (const float *)weights[2];
+    a.b0 = (const float *)biases[0]; a.b1 = (const float *)biases[1]; a.b2 = (const float *)biases[2];
+    a.x = (const float *)x; a.e = (float *)e; a.dE = (float *)dEdx; a.n_rows = n_rows;
+    if (fwd_smem_bytes<64>(a.K0R) > 200 * 1024) return fwd_launch<32>(a, st);
+    const int64_t sms = sm_count();
+    const int64_t occ32 = std::max<int64_t>(1, (227 * 1024) / int64_t(fwd_smem_bytes<32>(a.K0R) + 1024));
+    const int64_t occ64 = std::max<int64_t>(1, (227 * 1024) / int64_t(fwd_smem_bytes<64>(a.K0R) + 1024));
+    const int64_t path64 = ((n_rows + 63) / 64 + sms * occ64 - 1) / (sms * occ64) * 64;
+    const int64_t path32 = ((n_rows + 31) / 32 + sms * occ32 - 1) / (sms * occ32) * 32;
+    return path32 <= path64 ? fwd_launch<32>(a, st) : fwd_launch<64>(a, st);
 }
 
 }  // namespace nnmd
