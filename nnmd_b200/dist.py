@@ -154,6 +154,9 @@ class FlatGradients:
             yield self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
+    def world_size(self) -> int:
+        return _world()[1]
+
     def allreduce(self, average: bool = True) -> None:
         rank, world = _world()
         if world == 1:

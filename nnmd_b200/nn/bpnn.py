@@ -228,23 +228,35 @@ class BPNN(torch.nn.Module):
         return plan
 
     def _step_plan(self, plan):
-        """Run one loaded plan: forward + backward (graph 1) | gradient all-reduce | optimizer (graph 2)."""
+        """Run one loaded plan.  One rank: the whole step is one CUDA graph.  Several ranks: forward + backward (graph 1) |
+        gradient all-reduce | optimizer (graph 2) -- capturing the NCCL all-reduce into the graph hung on this stack
+        (torch 2.11 / NCCL 2.28, 2 GPUs), so it stays between the graphs."""
         if self._graphs_ok and plan.graphs is None and self._opt_ready:
-            try:  # the optimizer state exists (one eager step was done): capture both halves
-                fwd_bwd, opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            multi = self._flat_grads.world_size() > 1
+            try:  # the optimizer state exists (one eager step was done): capture the step
                 torch.cuda.synchronize()
-                with torch.cuda.graph(fwd_bwd):
-                    plan.run()
-                with torch.cuda.graph(opt, pool=fwd_bwd.pool()):
-                    self.optim.step()
-                plan.graphs = (fwd_bwd, opt)
+                if not multi:  # one rank: forward + backward and optimizer in ONE graph
+                    whole = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(whole):
+                        plan.run()
+                        self.optim.step()
+                    plan.graphs = (whole,)
+                else:
+                    fwd_bwd, opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(fwd_bwd):
+                        plan.run()
+                    with torch.cuda.graph(opt, pool=fwd_bwd.pool()):
+                        self.optim.step()
+                    plan.graphs = (fwd_bwd, opt)
                 # a capture does not execute: fall through to the replay below
             except Exception as exc:  # capture not possible here: stay eager, loudly
                 print(f"nnmd_b200: CUDA-graph capture of the training step failed ({exc!r}); continuing without graphs")
                 self._graphs_ok = False
-        if plan.graphs is not None:
+        if plan.graphs is not None and len(plan.graphs) == 1:
             plan.graphs[0].replay()
-            self._flat_grads.allreduce()  # frames are sharded across ranks (no-op on 1 rank)
+        elif plan.graphs is not None:
+            plan.graphs[0].replay()
+            self._flat_grads.allreduce()  # frames are sharded across ranks
             plan.graphs[1].replay()
         else:
             plan.run()
