@@ -271,12 +271,22 @@ __global__ void __launch_bounds__(256) radial_kernel(RadArgs<T> a) {
         load_pos<T>(a.posw, gi, xa, ya, za);
         const int nn = stage_row<T, UNI>(a.posw, a.idx, a.offsets[row], a.offsets[row + 1], xa, ya, za, a.rc_max,
                                          inv_rc_max, T(0), nb, a.cap);
+        if (MODE != MODE_G) {  // fold the -2/d of the gradient into the staged vectors: u <- -2 u / d (d itself stays in .d)
+            for (int t = lane; t < nn; t += 32) {
+                const Q4<T> u = ld4<T>(nb.u4 + 4 * t);
+                const T sc = T(-2) * nb.invd[t];
+                st4<T>(nb.u4 + 4 * t, sc * u.a, sc * u.b, sc * u.c, u.d);
+            }
+            __syncwarp();
+        }
         T fx = 0, fy = 0, fz = 0;  // MODE_FORCE partial sums
         for (int f0 = 0; f0 < a.n; f0 += 32) {
             const int f = f0 + lane;
             const bool act = f < a.n;
             const T rc = act ? a.rc[f] : T(1), eta = act ? a.eta[f] : T(0), rs = act ? a.rs[f] : T(0);
             const T inv_rc = M<T>::rcp(rc);
+            const T nel2 = -eta * T(1.4426950408889634074);  // exp(-eta x) = 2^(nel2 x)
+            const T m2eta = T(-2) * eta;
             T val = 0, gx = 0, gy = 0, gz = 0;
             if (act) {
                 for (int t = 0; t < nn; ++t) {
@@ -293,15 +303,15 @@ __global__ void __launch_bounds__(256) radial_kernel(RadArgs<T> a) {
                         dfc = T(-0.5) * M<T>::pi() * inv_rc * s;
                     }
                     const T dr = d - rs;
-                    const T ex = M<T>::exp_fast(-eta * dr * dr);  // G1: eta = 0 -> 1
+                    const T ex = M<T>::exp2_fast(nel2 * dr * dr);  // G1: eta = 0 -> 1
                     val = M<T>::fma_(ex, fc, val);
                     if (MODE != MODE_G) {
-                        const T dphi = ex * (dfc - T(2) * eta * dr * fc);
-                        // own-atom gradient plus the identical term inside every neighbour's G_j
-                        const T sc = T(-2) * dphi * nb.invd[t];
-                        gx = M<T>::fma_(sc, u.a, gx);
-                        gy = M<T>::fma_(sc, u.b, gy);
-                        gz = M<T>::fma_(sc, u.c, gz);
+                        // own-atom gradient plus the identical term inside every neighbour's G_j: the staged
+                        // vector already carries -2/d
+                        const T dphi = ex * M<T>::fma_(m2eta * dr, fc, dfc);
+                        gx = M<T>::fma_(dphi, u.a, gx);
+                        gy = M<T>::fma_(dphi, u.b, gy);
+                        gz = M<T>::fma_(dphi, u.c, gz);
                     }
                 }
                 const int col = a.col[f];

@@ -169,7 +169,7 @@ class BPNN(torch.nn.Module):
             kwargs["lr"] = self.learning_rate
             self.optim = available_optimizers[name](**kwargs)
             self._graphs_ok = False
-        self._plans, self._opt_ready = {}, False
+        self._plans, self._opt_ready, self._acc_carry = {}, False, None
 
     # ------------------------------------------------------------------------------------------------- loss
     def _loss(self, e_nn, energies, f_nn, forces):
@@ -221,7 +221,8 @@ class BPNN(torch.nn.Module):
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 4:  # full batches plus the ragged last one; anything else is churn
-                self._plans.pop(next(iter(self._plans)))
+                old = self._plans.pop(next(iter(self._plans)))
+                self._acc_carry = old.acc.clone() if self._acc_carry is None else self._acc_carry + old.acc
             plan = TrainStepPlan(self.atomic_nets, self.species, shapes, n_frames, self.device, self.e_loss_coeff,
                                  self.f_loss_coeff, self._flat_grads)
             self._plans[key] = plan
@@ -281,11 +282,12 @@ class BPNN(torch.nn.Module):
         if train and getattr(self, "_flat_grads", None) is None:
             # gradients live in one flat buffer: a single in-place all-reduce per step when frames are sharded
             self._flat_grads = FlatGradients([p for net in self.atomic_nets for p in net.parameters()])
-            self._plans, self._opt_ready = {}, False
+            self._plans, self._opt_ready, self._acc_carry = {}, False, None
         if train and isinstance(loader, FrameBatches) and loader.base.energies.is_cuda \
                 and self._fused_ok({s: v[0] for s, v in loader.base.sf_data.items()}, {s: v[1] for s, v in loader.base.sf_data.items()}):
             # batches are gathered straight into the static buffers of the step (no per-batch tensors, no copies)
             shapes = {s: loader.base.sf_data[s][0].shape for s in self.species}
+            self._acc_carry = None  # loss sums of plans evicted during the epoch
             for plan in self._plans.values():
                 plan.acc.zero_()
             for sel in tqdm(loader.index_batches(self.device), desc=desc, total=len(loader)):
@@ -295,6 +297,8 @@ class BPNN(torch.nn.Module):
             for plan in self._plans.values():
                 tot += plan.acc
                 plan.acc.zero_()
+            if self._acc_carry is not None:
+                tot += self._acc_carry
             tot /= len(loader)
             return tot[0], tot[1], tot[2]
         for g, dG, energy, forces in tqdm(loader, desc=desc, total=len(loader)):

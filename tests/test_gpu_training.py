@@ -301,3 +301,26 @@ def test_fused_training_epoch_matches_the_autograd_path(monkeypatch):
     assert np.allclose(la, lb, rtol=2e-4), (la, lb)
     for a, b in zip(pa, pb):
         assert relerr(a.cpu(), b.cpu()) < 2e-3
+
+
+def test_gather_rows_matches_index_select():
+    """nnmd_gather_rows (batch assembly) on 16 B-aligned and unaligned rows, repeated and out-of-order indices."""
+    import ctypes
+    from nnmd_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(3)
+    src = [torch.randn(50, 8, 4, device=DEV), torch.randn(50, 7, 3, 3, device=DEV), torch.randn(50, device=DEV),
+           torch.randn(50, 5, 3, device=DEV, dtype=torch.float64)]
+    sel = torch.tensor([49, 0, 7, 7, 31, 2], device=DEV)
+    dst = [torch.empty((sel.numel(),) + tuple(t.shape[1:]), dtype=t.dtype, device=DEV) for t in src]
+    n = len(src)
+    P = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
+    rows = (ctypes.c_int64 * n)(*[(t.numel() // t.shape[0]) * t.element_size() for t in src])
+    _lib.check(lib.nnmd_gather_rows(n, P(src), P(dst), rows, _lib.ptr(sel), sel.numel(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    for a, b in zip(src, dst):
+        assert torch.equal(b, a.index_select(0, sel))
+    bad_rows = (ctypes.c_int64 * n)(6, 4, 4, 4)
+    assert lib.nnmd_gather_rows(n, P(src), P(dst), bad_rows, _lib.ptr(sel), sel.numel(), _lib.stream_ptr()) != 0
+    assert b"multiple of 4" in lib.nnmd_last_error()
+    assert lib.nnmd_gather_rows(n, P(src), P(dst), rows, _lib.ptr(sel), 0, _lib.stream_ptr()) == 0
