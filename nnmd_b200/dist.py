@@ -44,23 +44,42 @@ class SlabShard:
         return int(self.owned_idx.numel())
 
     @staticmethod
-    def slab_edges(x_wrapped: torch.Tensor, world: int) -> torch.Tensor:
-        """Equal-count boundaries on the wrapped x coordinate: edges[0] = -inf, edges[world] = +inf."""
+    def slab_edges(x_wrapped: torch.Tensor, world: int, rc: float | None = None) -> torch.Tensor:
+        """Slab boundaries on the wrapped x coordinate: edges[0] = -inf, edges[world] = +inf.
+
+        rc=None: equal atom counts.  rc given: equal WORK.  The reference never adds periodic images, so the
+        structure ends in free surfaces at both ends of the x axis and an atom closer than rc to one of them sees only the
+        fraction f(h) = 1 - (1 - h/rc)^2 (2 + h/rc) / 4 of its cutoff sphere (h = distance to the face); its angular work
+        (owned edges x closing third atoms) scales like f^2.  Boundaries are placed at equal cumulative f^2, which evens out
+        the ~6 % by which equal-count end slabs are cheaper than interior ones.
+        """
         xs = torch.sort(x_wrapped.double()).values
         n = xs.numel()
-        inner = [float(xs[(k * n) // world]) for k in range(1, world)]
+        if rc is None or n == 0:
+            inner = [float(xs[(k * n) // world]) for k in range(1, world)]
+        else:
+            t = (torch.minimum(xs - xs[0], xs[-1] - xs) / float(rc)).clamp(max=1.0)
+            f = 1.0 - (1.0 - t) ** 2 * (2.0 + t) / 4.0
+            cw = torch.cumsum(f * f, 0)
+            targets = cw[-1] * torch.arange(1, world, dtype=torch.float64) / world
+            pos = torch.searchsorted(cw, targets).clamp(max=n - 1)
+            inner = [float(xs[int(p)]) for p in pos]
         return torch.tensor([-float("inf")] + inner + [float("inf")], dtype=torch.float64)
 
     @classmethod
-    def from_global(cls, pos: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, rc: float, rank: int, world: int):
+    def from_global(cls, pos: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, rc: float, rank: int, world: int,
+                    balance: str = "work"):
         """Domain decomposition of a structure every rank can see (synthetic benchmarks, file-based inputs).
+        balance: "work" (default, see `slab_edges`) or "count" (equal atom counts).
 
         Ownership is decided on the WRAPPED x coordinate (the coordinate the kernels measure distances in);
         the positions that travel are the original ones, so every rank's K0 reproduces the single-GPU wrap bit for bit.
         """
         pos = pos.detach().cpu()
         xw = map_positions_pbc(pos, cell.detach().cpu().to(pos.dtype), pbc.detach().cpu().to(pos.dtype))[:, 0].double()
-        edges = cls.slab_edges(xw, world)
+        if balance not in ("work", "count"):
+            raise ValueError("balance must be 'work' or 'count'")
+        edges = cls.slab_edges(xw, world, rc if balance == "work" else None)
         lo, hi = edges[rank], edges[rank + 1]
         mine = torch.nonzero((xw >= lo) & (xw < hi)).flatten()
         send = []
