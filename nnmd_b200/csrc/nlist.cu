@@ -328,6 +328,32 @@ __device__ __forceinline__ bool is_pair(T xi, T yi, T zi, T xj, T yj, T zj, T rc
     return (d < rc) && (d > T(0));  // symm_funcs.py:29
 }
 
+// Rank sort of a staged row (unique keys, so the ranks are a permutation): rows of up to 128 entries keep their up to
+// four keys per lane in registers and read every key of the row ONCE; longer rows take one pass per 32 keys.
+__device__ __forceinline__ void rank_sort_row(const int *__restrict__ buf, int n, int32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    if (n <= 128) {
+        int v[4], r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] = lane + 32 * i < n ? buf[lane + 32 * i] : 0x7fffffff; r[i] = 0; }
+        for (int t = 0; t < n; ++t) {
+            const int b = buf[t];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[i] += (b < v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (lane + 32 * i < n) out[r[i]] = v[i];
+    } else {
+        for (int e = lane; e < n; e += 32) {
+            const int v = buf[e];
+            int r = 0;
+            for (int t = 0; t < n; ++t) r += (buf[t] < v);
+            out[r] = v;
+        }
+    }
+}
+
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ posw, const T *__restrict__ spos,
                                                          int64_t n_rows, int64_t n_atoms, int64_t n_centres,
@@ -393,12 +419,7 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
             const int n = min(n_found, max_row);
             const int64_t o = offsets[row];
             // rank sort: indices inside a row are unique (no periodic images), so ranks are a permutation
-            for (int e = lane; e < n; e += 32) {
-                const int v = buf[e];
-                int r = 0;
-                for (int t = 0; t < n; ++t) r += (buf[t] < v);
-                idx[o + r] = v;
-            }
+            rank_sort_row(buf, n, idx + o);
             __syncwarp();
         }
     }
@@ -533,12 +554,7 @@ __global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__
                 __syncwarp();
                 const int n = min(n_found, max_row);
                 const int64_t o = offsets[row];
-                for (int e = lane; e < n; e += 32) {  // rank sort (unique indices -> ranks are a permutation)
-                    const int v = buf[e];
-                    int rk = 0;
-                    for (int t = 0; t < n; ++t) rk += (buf[t] < v);
-                    idx[o + rk] = v;
-                }
+                rank_sort_row(buf, n, idx + o);  // unique indices -> ranks are a permutation
                 __syncwarp();
             }
         }
