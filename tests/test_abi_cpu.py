@@ -31,6 +31,16 @@ def test_compute_fails_loudly_without_cuda():
     from nnmd_b200.features import calculate_sf
     with pytest.raises(_lib.NnmdError, match="no CPU fallback"):
         calculate_sf(torch.zeros(1, 3, 3), torch.zeros(3, 3), torch.zeros(3), {"features": [1], "params": [[3.0]]})
+    # the atomic network and the fused training step have no CPU path either
+    from nnmd_b200.dist import FlatGradients
+    from nnmd_b200.nn import AtomicNN
+    from nnmd_b200.nn.functional import TrainStepPlan
+    net = AtomicNN(3, [4, 4])
+    with pytest.raises(_lib.NnmdError):
+        net.energy_and_grad(torch.zeros(2, 3))
+    flat = FlatGradients(list(net.parameters()))
+    with pytest.raises(_lib.NnmdError):
+        TrainStepPlan([net], ["X"], {"X": (2, 5, 3)}, 2, "cpu", 1.0, 1.0, flat)
 
 
 def test_calculate_params_matches_reference_vectors(golden_dir):
