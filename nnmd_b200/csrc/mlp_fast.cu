@@ -20,7 +20,13 @@
 
 namespace nnmd {
 
-constexpr int FT_THREADS = 256;
+#ifndef NNMD_FT_THREADS
+#define NNMD_FT_THREADS 256
+#endif
+constexpr int FT_THREADS = NNMD_FT_THREADS;  // 256 or 512
+constexpr int FT_TNS = FT_THREADS / 16;       // groups of 16 threads (one group = all atoms of a few units)
+constexpr int FT_UN = 64 / FT_TNS;            // units (GEMM) / rows (outer product) per thread: 4 or 2
+constexpr int FT_MINB = 2;                    // two blocks per SM whenever shared memory allows (caps registers at 128 / 64)
 constexpr int FT_H = 64;  // padded hidden width
 
 struct FastTrainArgs {
@@ -53,56 +59,54 @@ template <> struct AtomVec<2> {
 };
 
 // C[n][m] = sum_k A[k][m] * Bt[k][n]   for the 64 units n and the TM atoms m of the tile.
-// Thread (tm, tn): atoms MM*tm .. MM*tm+MM-1, units 4*tn .. 4*tn+3.  epi(n, m0, v[MM]) receives one unit at a time.
+// Thread (tm, tn): atoms MM*tm .. MM*tm+MM-1, units FT_UN*tn .. FT_UN*tn+FT_UN-1.  epi(n, m0, v[MM]) receives one unit at a time.
 // Threads whose units lie at or beyond `ncols` do nothing (the function contains no barrier).
 template <int TM, typename Epi>
 __device__ __forceinline__ void gemm_atoms(const float *__restrict__ A, int K, const float *__restrict__ Bt, int ldb, Epi epi,
                                            int ncols = FT_H) {
     constexpr int P = TM + 4, MM = TM / 16;
     const int tm = threadIdx.x & 15, tn = threadIdx.x >> 4;
-    if (4 * tn >= ncols) return;
-    float acc[4][MM];
+    if (FT_UN * tn >= ncols) return;
+    float acc[FT_UN][MM];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < FT_UN; ++j)
 #pragma unroll
         for (int i = 0; i < MM; ++i) acc[j][i] = 0.f;
-    const float *a = A + MM * tm, *b = Bt + 4 * tn;
+    const float *a = A + MM * tm, *b = Bt + FT_UN * tn;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-        float av[MM];
+        float av[MM], bv[FT_UN];
         AtomVec<MM>::ld(a + k * P, av);
-        const float4 bv = *reinterpret_cast<const float4 *>(b + size_t(k) * ldb);
+        AtomVec<FT_UN>::ld(b + size_t(k) * ldb, bv);
 #pragma unroll
-        for (int i = 0; i < MM; ++i) {
-            acc[0][i] = fmaf(av[i], bv.x, acc[0][i]);
-            acc[1][i] = fmaf(av[i], bv.y, acc[1][i]);
-            acc[2][i] = fmaf(av[i], bv.z, acc[2][i]);
-            acc[3][i] = fmaf(av[i], bv.w, acc[3][i]);
-        }
+        for (int j = 0; j < FT_UN; ++j)
+#pragma unroll
+            for (int i = 0; i < MM; ++i) acc[j][i] = fmaf(av[i], bv[j], acc[j][i]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) epi(4 * tn + j, MM * tm, acc[j]);
+    for (int j = 0; j < FT_UN; ++j) epi(FT_UN * tn + j, MM * tm, acc[j]);
 }
 
-// acc[i][j] += sum_m A[tn + 16 i][m] * B[kbase + tk + 16 j][m]   for j < nj  (rows strided by 16: conflict-free 16 B loads)
+// acc[i][j] += sum_m A[tn + FT_TNS i][m] * B[kbase + tk + 16 j][m]   for j < nj  (strided rows: conflict-free 16 B loads)
 template <int TM>
-__device__ __forceinline__ void outer_acc(const float *__restrict__ A, const float *__restrict__ B, int kbase, int nj, float (&acc)[4][4]) {
+__device__ __forceinline__ void outer_acc(const float *__restrict__ A, const float *__restrict__ B, int kbase, int nj,
+                                          float (&acc)[FT_UN][4]) {
     constexpr int P = TM + 4;
     const int tk = threadIdx.x & 15, tn = threadIdx.x >> 4;
     const float *a = A + tn * P, *b = B + (kbase + tk) * P;
 #pragma unroll 2
     for (int m = 0; m < TM; m += 4) {
-        float4 av[4], bv[4];
+        float4 av[FT_UN], bv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            av[i] = *reinterpret_cast<const float4 *>(a + 16 * i * P + m);
-            bv[i] = i < nj ? *reinterpret_cast<const float4 *>(b + 16 * i * P + m) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < FT_UN; ++i) av[i] = *reinterpret_cast<const float4 *>(a + FT_TNS * i * P + m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            bv[j] = j < nj ? *reinterpret_cast<const float4 *>(b + 16 * j * P + m) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (j >= nj) continue;  // block-uniform
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < FT_UN; ++i) {
                 float s = acc[i][j];
                 s = fmaf(av[i].x, bv[j].x, s); s = fmaf(av[i].y, bv[j].y, s);
                 s = fmaf(av[i].z, bv[j].z, s); s = fmaf(av[i].w, bv[j].w, s);
@@ -124,7 +128,7 @@ __device__ __forceinline__ float unit_sum(const float (&v)[MM]) {
 }
 
 template <int TM, int NKG>
-__global__ void __launch_bounds__(FT_THREADS) mlp_train_fast_kernel(FastTrainArgs a) {
+__global__ void __launch_bounds__(FT_THREADS, FT_MINB) mlp_train_fast_kernel(FastTrainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int P = TM + 4, MM = TM / 16;
     const int K0R = a.K0R;
@@ -161,9 +165,9 @@ __global__ void __launch_bounds__(FT_THREADS) mlp_train_fast_kernel(FastTrainArg
     for (int i = tid; i < H2n; i += FT_THREADS) { W2s[i] = __ldg(a.W2 + i); b1s[i] = __ldg(a.b1 + i); }
     for (int i = tid; i < H1n; i += FT_THREADS) b0s[i] = __ldg(a.b0 + i);
     float gb2_acc = 0.f;  // thread 0 only
-    float g1[4][4], g0[NKG][4][4];
+    float g1[FT_UN][4], g0[NKG][FT_UN][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < FT_UN; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             g1[i][j] = 0.f;
@@ -284,10 +288,10 @@ __global__ void __launch_bounds__(FT_THREADS) mlp_train_fast_kernel(FastTrainArg
     {
         const int tk = tid & 15, tn = tid >> 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < FT_UN; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int n = tn + 16 * i, k = tk + 16 * j;
+                const int n = tn + FT_TNS * i, k = tk + 16 * j;
                 if (n < H2n && k < H1n) atomicAdd(a.gW1 + n * H1n + k, g1[i][j]);
 #pragma unroll
                 for (int g = 0; g < NKG; ++g) {
@@ -359,7 +363,7 @@ struct FastFwdArgs {
 };
 
 template <int TM>
-__global__ void __launch_bounds__(FT_THREADS) mlp_fwd_fast_kernel(FastFwdArgs a) {
+__global__ void __launch_bounds__(FT_THREADS, FT_MINB) mlp_fwd_fast_kernel(FastFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int P = TM + 4, MM = TM / 16;
     const int K0R = a.K0R;
@@ -369,8 +373,8 @@ __global__ void __launch_bounds__(FT_THREADS) mlp_fwd_fast_kernel(FastFwdArgs a)
     float *W1T = W0N + FT_H * K0R;      // [64][64]
     float *W1N = W1T + FT_H * FT_H;     // [64][64]
     float *W2s = W1N + FT_H * FT_H, *b0s = W2s + FT_H, *b1s = b0s + FT_H;
-    float *ep = b1s + FT_H;             // [16][TM] partial energies (one row per tn)
-    float *X = ep + 16 * TM;            // [K0R], later dE/dx of the tile
+    float *ep = b1s + FT_H;             // [FT_TNS][TM] partial energies (one row per tn)
+    float *X = ep + FT_TNS * TM;            // [K0R], later dE/dx of the tile
     float *H1 = X + K0R * P, *H2 = H1 + FT_H * P, *D1 = H2 + FT_H * P, *D0 = D1 + FT_H * P;
     float *sm_end = D0 + FT_H * P;
     const int tid = threadIdx.x, tn = tid >> 4;
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(FT_THREADS) mlp_fwd_fast_kernel(FastFwdArgs a)
         for (int m = tid; m < valid; m += FT_THREADS) {
             float s = b2;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) s += ep[r * TM + m];
+            for (int r = 0; r < FT_TNS; ++r) s += ep[r * TM + m];
             a.e[m0 + m] = s;
         }
         if (a.dE) {
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(FT_THREADS) mlp_fwd_fast_kernel(FastFwdArgs a)
 template <int TM>
 static size_t fwd_smem_bytes(int K0R) {
     constexpr int P = TM + 4;
-    return sizeof(float) * (2 * size_t(K0R) * FT_H + 2 * FT_H * FT_H + 3 * FT_H + 16 * TM + size_t(K0R) * P + 4 * FT_H * P);
+    return sizeof(float) * (2 * size_t(K0R) * FT_H + 2 * FT_H * FT_H + 3 * FT_H + FT_TNS * TM + size_t(K0R) * P + 4 * FT_H * P);
 }
 
 template <int TM>
