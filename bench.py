@@ -338,7 +338,7 @@ def run_ours(args):
                        "atoms": n_atoms, "cells": args.cells, "mlp": [nf] + HIDDEN + [1], "mode": args.mode,
                        "mlp_precision": args.mlp, "pbc": "reference wrap-only (SURVEY Q1)", "mean_neighbours": mean_nbrs,
                        "l2": "256 MiB buffer written between timed steps; per-step working set (neighbour list + dG) is >1 GB",
-                       "parallelism": "single GPU" if world == 1 else f"x-slabs x{world}, halo rc, NCCL send/recv"},
+                       "parallelism": "single GPU" if world == 1 else f"x-slabs x{world} (equal-work boundaries), halo rc, NCCL send/recv"},
             "clocks": clocks.summary(), "gpu_launches": launches, "roofline": roofline}
     if e2e is not None:
         line["e2e"] = e2e
