@@ -185,7 +185,6 @@ def run_ours(args):
     nf = len(sfd["features"])
     pos, cell, pbc = fcc_cell(args.cells, dtype=torch.float32)
     n_atoms = pos.shape[0]
-    cell_d, pbc_d = cell.to(dev), pbc.to(dev)
     net = make_net(nf, dev)
     lib = _lib.load()
 
@@ -197,7 +196,8 @@ def run_ours(args):
     def step_device():
         # N>1: the halo exchange is part of every step (positions change every MD step)
         lp = shard.exchange_halo(dev) if world > 1 else local_pos
-        res = energy_forces(lp[None], cell_d, pbc_d, sfd, net, mode=args.mode, n_centres=n_owned,
+        # cell and pbc stay on the host: K0 takes them as kernel arguments (a device copy would cost a read-back per step)
+        res = energy_forces(lp[None], cell, pbc, sfd, net, mode=args.mode, n_centres=n_owned,
                             mlp_precision=args.mlp, check=False)
         if world > 1:
             td.all_reduce(res.energy)  # total energy of the structure
