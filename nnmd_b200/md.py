@@ -81,7 +81,8 @@ class VelocityVerlet:
         self.x = positions.detach().clone()
         self.v = velocities.detach().to(self.x).clone()
         self.mass, self.dt = float(mass), float(dt)
-        self.cell, self.pbc = cell.to(self.x), pbc.to(self.x)
+        # cell and pbc are kernel ARGUMENTS of K0: host copies avoid a device read-back in every step
+        self.cell, self.pbc = cell.detach().to("cpu", self.x.dtype), pbc.detach().to("cpu", self.x.dtype)
         self.sfd, self.net, self.mode = symm_funcs_data, net, mode
         self.energy, self.f = self._forces()
         self.steps = 0
