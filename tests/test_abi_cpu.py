@@ -89,3 +89,29 @@ def test_atomic_nn_state_dict_layout():
         AtomicNN(3, (4, 4))
     x = torch.rand(2, 5, 14)
     assert net(x).shape == (2, 5, 1)
+
+
+def test_bpnn_config_host_logic(tmp_path):
+    """Host side of BPNN.config / save_model (reference: bpnn.py:107-194, 556-565): optimizer table and its error text,
+    Xavier initialisation with zero biases, amsgrad and the reference's betas, checkpoint file names."""
+    from nnmd_b200.nn import BPNN
+    cfg = dict(atom_species=["A", "B"], input_sizes=[4, 6], hidden_sizes=[[5, 5], [7]], learning_rate=0.01, l2_regularization=1e-3,
+               e_loss_coeff=1.0, f_loss_coeff=2.0, load_models=False, path=str(tmp_path), optimizer="sgd", batch_size=4, epochs=1)
+    net = BPNN(dtype=torch.float32, use_cuda=False)
+    with pytest.raises(ValueError, match="Optimizer sgd is not available"):
+        net.config(cfg)
+    for name, betas in (("adam", (0.8, 0.9999)), ("adamw", (0.9, 0.999)), (None, (0.8, 0.9999))):
+        net = BPNN(dtype=torch.float32, use_cuda=False)
+        net.config(dict(cfg, optimizer=name))
+        grp = net.optim.param_groups[0]
+        assert grp["amsgrad"] is True and tuple(grp["betas"]) == betas and grp["weight_decay"] == 1e-3
+        assert [a.layer_sizes() for a in net.atomic_nets] == [[4, 5, 5, 1], [6, 7, 1]]
+        assert all(float(m.bias.detach().abs().max()) == 0.0 for a in net.atomic_nets for m in a.model)
+        assert isinstance(net.criterion, torch.nn.MSELoss) and net.species == ["A", "B"]
+    net.save_model(str(tmp_path))
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["atomic_nn_A.pt", "atomic_nn_B.pt"]
+    again = BPNN(dtype=torch.float32, use_cuda=False)
+    again.config(dict(cfg, optimizer="adam", load_models=True))
+    for a, b in zip(net.atomic_nets, again.atomic_nets):
+        for p, q in zip(a.parameters(), b.parameters()):
+            assert torch.equal(p, q)
