@@ -115,3 +115,32 @@ def test_bpnn_config_host_logic(tmp_path):
     for a, b in zip(net.atomic_nets, again.atomic_nets):
         for p, q in zip(a.parameters(), b.parameters()):
             assert torch.equal(p, q)
+
+
+def test_batch_loader_and_split_host_logic():
+    """FrameBatches reproduces DataLoader(dataset, batch_size, shuffle) semantics on the cached tensors (bpnn.py:234-236):
+    every frame exactly once per epoch, ragged last batch, Subset chains from train_val_test_split resolved to indices."""
+    from nnmd_b200.nn import TrainAtomicDataset, train_val_test_split
+    from nnmd_b200.nn.bpnn import FrameBatches, batch_loader
+    M = 23
+    g = torch.arange(M, dtype=torch.float32).view(M, 1, 1).expand(M, 3, 2).contiguous()
+    dg = torch.zeros(M, 3, 2, 3)
+    ds = TrainAtomicDataset({"X": (g, dg)}, torch.arange(M, dtype=torch.float32).view(M, 1), torch.zeros(M, 3, 3), {})
+    loader = batch_loader(ds, 5, shuffle=True)
+    assert isinstance(loader, FrameBatches) and len(loader) == 5
+    torch.manual_seed(0)
+    seen = []
+    for gb, dgb, e, f in loader:
+        assert gb["X"].shape[1:] == (3, 2) and dgb["X"].shape[1:] == (3, 2, 3) and f.shape[1:] == (3, 3)
+        assert torch.equal(gb["X"][:, 0, 0], e[:, 0])  # rows of every cached tensor move together
+        seen += e[:, 0].tolist()
+    assert sorted(seen) == list(range(M)) and seen != sorted(seen)
+    sizes = [int(s.numel()) for s in loader.index_batches("cpu")]
+    assert sizes == [5, 5, 5, 5, 3]
+    train, val, test = train_val_test_split(ds, (0.6, 0.2, 0.2))
+    parts = [batch_loader(p, 4, shuffle=False) for p in (train, val, test)]
+    assert all(isinstance(p, FrameBatches) for p in parts)
+    ids = [sorted(int(i) for b in p.index_batches("cpu") for i in b) for p in parts]
+    assert sorted(ids[0] + ids[1] + ids[2]) == list(range(M)) and [len(i) for i in ids] == [len(train), len(val), len(test)]
+    # anything that is not a TrainAtomicDataset (or a Subset chain of one) falls back to the stock DataLoader
+    assert isinstance(batch_loader(torch.utils.data.TensorDataset(torch.zeros(4, 2)), 2, shuffle=False), torch.utils.data.DataLoader)
