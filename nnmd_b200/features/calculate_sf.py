@@ -53,6 +53,7 @@ class SfPlan:
 
 
 _PLAN_CACHE: dict = {}
+_PLAN_CACHE_MAX = 64
 
 
 def get_plan(symm_funcs_data: dict, dtype: torch.dtype, device: torch.device) -> SfPlan:
@@ -63,6 +64,8 @@ def get_plan(symm_funcs_data: dict, dtype: torch.dtype, device: torch.device) ->
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         plan = SfPlan(symm_funcs_data["features"], symm_funcs_data["params"], dtype, dev)
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:  # parameter scans: drop the oldest table (callers holding it keep it alive)
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
         _PLAN_CACHE[key] = plan
     return plan
 
