@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/nnmd_b200.h"
@@ -31,6 +32,14 @@ int set_err(int code, const char *fmt, ...);
     } while (0)
 
 int sm_count();
+
+// Tuning / profiling knobs are read from the environment only by libraries built with -DNNMD_TUNING
+// (tools/build_variant.sh); the product library ignores them, so a stray exported variable cannot change results.
+#ifdef NNMD_TUNING
+inline const char *tuning_env(const char *name) { return getenv(name); }
+#else
+inline const char *tuning_env(const char *) { return nullptr; }
+#endif
 
 // ---- launch counter and optional per-kernel-class CUDA-event timing (bench.py's roofline leg) ----------
 extern std::atomic<long long> g_launches;

@@ -390,7 +390,7 @@ extern "C" int nnmd_mlp_energy_grad(int dtype, int precision, int n_layers, cons
     if (precision != NNMD_MLP_EXACT) return set_err(NNMD_ERR_INVALID, "mlp: bad precision %d", precision);
     if (dtype == NNMD_F32) {
         // first choice: the tile kernel of mlp_fast.cu (weights in shared memory, register-tiled GEMMs); NNMD_MLP_FWD=v skips it
-        const char *env = getenv("NNMD_MLP_FWD");
+        const char *env = tuning_env("NNMD_MLP_FWD");
         const bool fast = env ? env[0] == 'f' : n_rows <= MLP_FAST_MAX_ROWS;
         if (fast) {
             const int rf = mlp_fwd_fast(n_layers, sizes, weights, biases, x, n_rows, e, dEdx, st);

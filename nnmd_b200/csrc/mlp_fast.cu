@@ -334,7 +334,7 @@ static int fast_launch(const FastTrainArgs &a, cudaStream_t st) {
 int train_bwd_fast(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases, const void *x,
                    int64_t n_rows, const void *ge, const void *u, void *const *gW, void *const *gb, cudaStream_t st) {
     if (n_layers != 3 || sizes[1] > FT_H || sizes[2] > FT_H || sizes[0] > 128 || sizes[3] != 1) return -1;
-    if (const char *env = getenv("NNMD_MLP_TRAIN_GENERIC")) if (env[0] == '1') return -1;
+    if (const char *env = tuning_env("NNMD_MLP_TRAIN_GENERIC")) if (env[0] == '1') return -1;
     FastTrainArgs a;
     a.K0 = sizes[0]; a.H1 = sizes[1]; a.H2 = sizes[2]; a.K0R = (sizes[0] + 15) / 16 * 16;
     a.W0 = (const float *)weights[0]; a.W1 = (const float *)weights[1]; a.W2 = (const float *)weights[2];

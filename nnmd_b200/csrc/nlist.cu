@@ -622,7 +622,7 @@ extern "C" int nnmd_wrap_positions(int dtype, const void *pos, int64_t n_total, 
 }
 
 static bool use_cell_kernel() {
-    const char *env = getenv("NNMD_NLIST_ROWS");  // tuning knob: 1 = per-atom traversal (the first form of K1)
+    const char *env = tuning_env("NNMD_NLIST_ROWS");  // tuning knob: 1 = per-atom traversal (the first form of K1)
     return !(env && env[0] == '1');
 }
 

@@ -88,7 +88,7 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
         // fp32, lambda = +-1, 33..64 functions: 4 per lane on 16 lanes, so the two half-warps of the edge-centric
         // kernel work on two records at once (fewer shared-memory wavefronts and SFU ops per record)
         if (dtype == NNMD_F32 && pm1 && fpl == 2 && slots_for(2) > 16 && slots_for(4) <= 16) fpl = 4;
-        if (const char *env = getenv("NNMD_ANG_FPL")) {  // tuning knob: force the number of functions per lane
+        if (const char *env = tuning_env("NNMD_ANG_FPL")) {  // tuning knob: force the number of functions per lane
             const int want = atoi(env);
             if (want == 1 || want == 2 || want == 4) {
                 fpl = want;
@@ -124,7 +124,7 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
         // zeta ladder (what calculate_params emits): when every lane's two functions are separated by the same
         // step (to within the 6-decimal rounding of the table, <= 2e-6), the second power is the first one times
         // 2^(step * L), and 2^(step * L) does not depend on the lane: it moves into the triangle record.
-        const char *no_ladder = getenv("NNMD_NO_LADDER");  // tuning knob
+        const char *no_ladder = tuning_env("NNMD_NO_LADDER");  // tuning knob
         if (pm1 && fpl >= 2 && !(no_ladder && no_ladder[0] == '1')) {
             double sum = 0, lo = 1e300, hi = -1e300;
             int n = 0;
@@ -136,7 +136,7 @@ static int build_group(int dtype, int kind, double rc, double eta, const std::ve
                     }
             if (n > 0 && hi - lo <= 2e-6) { g.ladder = 1; g.ladder_step = sum / n; }
         }
-        const char *no_edge = getenv("NNMD_NO_EDGE");  // tuning knob
+        const char *no_edge = tuning_env("NNMD_NO_EDGE");  // tuning knob
         g.edge_path = (dtype == NNMD_F32 && pm1 && fpl == 4 && g.lanes == 16 && !(no_edge && no_edge[0] == '1')) ? 1 : 0;
         int r;
         if ((r = upload_real(dtype, zeta, &g.d_zeta))) return r;
@@ -908,8 +908,10 @@ static int sf_run(const nnmd_sf_plan *p, const T *posw, int64_t n_frames, int64_
         int r = launch_radial<T, MODE>(p, a, st);
         if (r) return r;
     }
+    // the first EDGE_WS_HEADER bytes of the scratch hold the row counter of the dynamically scheduled kernel: it belongs to
+    // the CALL (two calls that share a plan on different streams bring their own scratch, hence their own counter)
     const bool edge_ok = edge_offsets && edge_ws && p->edge_slots > 0 &&
-                         edge_ws_bytes >= n_edges * 2 * int64_t(p->edge_slots) * int64_t(sizeof(float));
+                         edge_ws_bytes >= EDGE_WS_HEADER + n_edges * 2 * int64_t(p->edge_slots) * int64_t(sizeof(float));
     for (const AngGroup &g : p->groups) {
         if constexpr (sizeof(T) == 4) {
             if (g.edge_path && edge_ok) {
@@ -918,8 +920,11 @@ static int sf_run(const nnmd_sf_plan *p, const T *posw, int64_t n_frames, int64_
                 e.edge_offsets = edge_offsets; e.cap = cap; e.kind = g.kind; e.ladder = g.ladder;
                 e.rc = float(g.rc); e.eta = float(g.eta); e.step = float(g.ladder_step);
                 e.zeta = (const float *)g.d_zeta; e.lam = (const float *)g.d_lam; e.coef = (const float *)g.d_coef; e.col = g.d_col;
-                e.nf = p->nf; e.nfa = p->edge_slots; e.ebase = g.edge_base; e.E = (float *)edge_ws;
-                e.G = G; e.dG = dG; e.w = w; e.force = force; e.flag = flag; e.row_counter = p->d_row_counter; e.dbg = 0;
+                e.nf = p->nf; e.nfa = p->edge_slots; e.ebase = g.edge_base; e.E = (float *)((char *)edge_ws + EDGE_WS_HEADER);
+                e.G = G; e.dG = dG; e.w = w; e.force = force; e.flag = flag; e.row_counter = (unsigned long long *)edge_ws;
+#ifdef NNMD_TUNING
+                e.dbg = 0;
+#endif
                 int r = launch_edge<MODE>(g, e, st);
                 if (r) return r;
                 continue;
@@ -990,17 +995,12 @@ extern "C" int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, cons
     if (r) { nnmd_sf_plan_destroy(p); return r; }
     for (AngGroup &g : p->groups)
         if (g.edge_path) { g.edge_base = p->edge_slots; p->edge_slots += g.n_slots; }
-    if (cudaMalloc((void **)&p->d_row_counter, sizeof(unsigned long long)) != cudaSuccess) {
-        nnmd_sf_plan_destroy(p);
-        return set_err(NNMD_ERR_CUDA, "plan: cudaMalloc failed");
-    }
     *out = p;
     return NNMD_OK;
 }
 
 extern "C" void nnmd_sf_plan_destroy(nnmd_sf_plan *p) {
     if (!p) return;
-    cudaFree(p->d_row_counter);
     cudaFree(p->rad.d_rc); cudaFree(p->rad.d_eta); cudaFree(p->rad.d_rs); cudaFree(p->rad.d_col);
     for (AngGroup &g : p->groups) { cudaFree(g.d_zeta); cudaFree(g.d_lam); cudaFree(g.d_coef); cudaFree(g.d_col); }
     delete p;
@@ -1021,7 +1021,8 @@ static int sf_args_ok(const nnmd_sf_plan *plan, const void *posw, int64_t n_fram
 extern "C" int64_t nnmd_sf_edge_scratch_bytes(const nnmd_sf_plan *plan, int64_t n_edges) {
     if (!plan || n_edges < 0 || plan->dtype != NNMD_F32) return 0;
     if (n_edges >= (int64_t(1) << 31)) return 0;  // slots are int32: beyond that the vertex-centric kernel is used
-    return n_edges * 2 * int64_t(plan->edge_slots) * int64_t(sizeof(float));
+    if (plan->edge_slots == 0) return 0;
+    return EDGE_WS_HEADER + n_edges * 2 * int64_t(plan->edge_slots) * int64_t(sizeof(float));
 }
 
 extern "C" int nnmd_sf_eval(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms,

@@ -21,6 +21,11 @@
 #pragma once
 // (included inside namespace nnmd)
 
+#ifdef NNMD_TUNING
+#define NNMD_EDGE_DBG(a) ((a).dbg)
+#else
+#define NNMD_EDGE_DBG(a) 0
+#endif
 struct EdgeArgs {
     const float *posw;
     int64_t n_rows, n_atoms, n_centres;
@@ -41,7 +46,9 @@ struct EdgeArgs {
     float *force;
     uint32_t *flag;
     unsigned long long *row_counter;  // dynamic row scheduling (zeroed before the launch)
-    int dbg;                          // profiling knob (NNMD_DBG): 1 = skip phase 2, 2 = skip phase 1 as well
+#ifdef NNMD_TUNING
+    int dbg;                          // profiling knob (NNMD_DBG, tuning builds only): 1 = skip phase 2, 2 = skip phase 1 as well
+#endif
 };
 
 // record: per lambda class (EREC_CLASS floats)  [ L0 L1 L2 eid | A0 A1 B0 B1 | A2 B2 V0a V0j | R0 R1 R2 . ]
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
             if (lane == 0) { prev0 = last_tj; prev1 = tj0_last; }
             // the queue is edge-major: a change of tj opens the next edge
             const bool first0 = has0 && tj0 != prev0, first1 = has1 && tj1 != prev1;
-            if (!(a.dbg & 2)) {
+            if (!(NNMD_EDGE_DBG(a) & 2)) {
                 if (has0) make_record_edge<WITH_PHI, LADDER>(nb, tj0, (pk0 >> 15) & 0x7fff, kind, step, inv_rc, eta, nb.epos[tj0],
                                                              recs + lane * EREC_STRIDE);
                 if (EBATCH > 32 && has1)
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
             // walk the batch edge by edge: `rest` holds the edge openings after record t (everything here is warp-uniform)
             unsigned long long rest = firsts & ~1ull;
             bool opens = (firsts & 1ull) != 0;
-            int t = (a.dbg & 1) ? cnt : 0;
+            int t = (NNMD_EDGE_DBG(a) & 1) ? cnt : 0;
             while (t < cnt) {
                 if (opens) {  // record t opens the next edge: retire the previous one
                     if (cur_tj >= 0) retire(cur_eid);
@@ -507,7 +514,9 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         if (occ < 1) occ = 1;
         int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * occ);
         NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
-        if (const char *env = getenv("NNMD_DBG")) a.dbg = atoi(env);
+#ifdef NNMD_TUNING
+        if (const char *env = tuning_env("NNMD_DBG")) a.dbg = atoi(env);
+#endif
         ProfScope prof(PROF_ANGULAR, st);
         kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
         NNMD_LAUNCH_CHECK("angular_edge4_kernel");

@@ -14,6 +14,7 @@ constexpr int ANG_BATCH = 32;     // triangles staged per batch
 constexpr int NB_FIELDS = 10;     // per-neighbour staged reals: ux uy uz d 1/d fc fc' psi psi' + edge slot (int)
 constexpr int EREC_STRIDE = 36;   // edge-centric record stride (36 mod 32 = 4: conflict-free 16 B accesses)
 constexpr int EREC_CLASS = 16;
+constexpr int64_t EDGE_WS_HEADER = 256;  // bytes at the head of the caller's edge scratch: per-call row counter
 
 // One launch of the angular kernel: functions that share (kind, rc, eta).
 struct AngGroup {
@@ -50,5 +51,4 @@ struct nnmd_sf_plan {
     nnmd::RadialTab rad;
     std::vector<nnmd::AngGroup> groups;
     int edge_slots = 0;  // function-axis length of the edge scratch (sum of n_slots over edge-path groups)
-    unsigned long long *d_row_counter = nullptr;  // work counter of the dynamically scheduled kernels
 };

@@ -149,13 +149,17 @@ def shard_frames(n_frames: int, rank: int | None = None, world: int | None = Non
 class FlatGradients:
     """All parameter gradients of the atomic networks as views of ONE contiguous buffer, so that the per-step
     collective is a single in-place all-reduce with no flatten / unflatten copies (the buffer is <= ~30k floats for the
-    shipped nets: the exchange is latency-bound)."""
+    shipped nets: the exchange is latency-bound).  One extra slot behind the gradients carries the number of frames of
+    the rank's batch through the same all-reduce: the global-batch gradient is sum_r b_r grad_r / sum_r b_r, which is
+    exact for ragged shards and lets a rank that ran out of batches take part with b_r = 0."""
 
     def __init__(self, params):
         self.params = [p for p in params]
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
-        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        self.buf = torch.zeros(n + 1, dtype=ref.dtype, device=ref.device)
+        self.flat = self.buf[:n]
+        self.count = self.buf[n:]  # (1,) frames behind the gradient: local before, global after `allreduce`
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -176,13 +180,20 @@ class FlatGradients:
     def world_size(self) -> int:
         return _world()[1]
 
-    def allreduce(self, average: bool = True) -> None:
+    def allreduce(self, n_frames: int | None = None) -> None:
+        """Global-batch gradient from per-rank batch-mean gradients.  n_frames = frames of THIS rank's batch (0 when the
+        rank has none left this step; None = equal batches everywhere, plain average).  No-op on one rank."""
         rank, world = _world()
         if world == 1:
             return
-        td.all_reduce(self.flat, op=td.ReduceOp.SUM)
-        if average:
+        if n_frames is None:
+            td.all_reduce(self.flat, op=td.ReduceOp.SUM)
             self.flat /= world
+            return
+        self.flat *= float(n_frames)
+        self.count.fill_(float(n_frames))
+        td.all_reduce(self.buf, op=td.ReduceOp.SUM)
+        self.flat /= self.count
 
 
 def allreduce_gradients(params, average: bool = True) -> None:

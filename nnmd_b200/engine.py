@@ -60,12 +60,12 @@ def virial(nl: NeighborList, forces: torch.Tensor, origin=None) -> torch.Tensor:
     return out
 
 
-def fused_force(plan: SfPlan, nl: NeighborList, w: torch.Tensor) -> torch.Tensor:
-    """K4b: forces from dE/dg_hat without a materialised dG."""
+def fused_force(plan: SfPlan, nl: NeighborList, w: torch.Tensor, edge: bool = True) -> torch.Tensor:
+    """K4b: forces from dE/dg_hat without a materialised dG (edge=False: vertex-centric angular kernel)."""
     lib = _lib.load()
     w2 = w.detach().reshape(-1, plan.nf).contiguous()
     out = torch.empty((nl.n_rows, 3), dtype=w.dtype, device=w.device)
-    ews = edge_scratch(plan, nl)
+    ews = edge_scratch(plan, nl) if edge else None
     with torch.cuda.device(w.device):
         _lib.check(lib.nnmd_sf_force(plan.handle, _lib.ptr(nl.posw), nl.n_frames, nl.n_atoms, nl.n_centres,
                                      _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(nl.edge_offsets),

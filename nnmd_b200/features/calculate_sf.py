@@ -9,6 +9,7 @@ All frames go through ONE pass of K0 (wrap) -> K1 (cell list) -> K2/K3 (radial/a
 from __future__ import annotations
 
 import ctypes
+import warnings
 import weakref
 
 import numpy as np
@@ -81,18 +82,21 @@ def edge_scratch(plan: SfPlan, nl: NeighborList):
     try:
         return torch.empty(need, dtype=torch.uint8, device=nl.posw.device)
     except torch.cuda.OutOfMemoryError:
+        warnings.warn(f"nnmd_b200: the {need / 2**30:.1f} GiB edge scratch of the edge-centric angular kernel does not fit; "
+                      "falling back to the vertex-centric kernel (same results, about twice the arithmetic)", RuntimeWarning)
         return None
 
 
-def raw_descriptors(plan: SfPlan, nl: NeighborList, with_grad: bool = True):
-    """K2+K3(+K4a): un-normalised G (n_rows,F) and dG (n_rows,F,3) for the rows of `nl`, plus the device flag word."""
+def raw_descriptors(plan: SfPlan, nl: NeighborList, with_grad: bool = True, edge: bool = True):
+    """K2+K3(+K4a): un-normalised G (n_rows,F) and dG (n_rows,F,3) for the rows of `nl`, plus the device flag word.
+    edge=False withholds the edge scratch, which makes the C side take the vertex-centric angular kernel."""
     lib = _lib.load()
     dev = nl.posw.device
     n_rows = nl.n_rows
     G = torch.empty((n_rows, plan.nf), dtype=plan.dtype, device=dev)
     dG = torch.empty((n_rows, plan.nf, 3), dtype=plan.dtype, device=dev) if with_grad else None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    ews = edge_scratch(plan, nl)
+    ews = edge_scratch(plan, nl) if edge else None
     with torch.cuda.device(dev):
         _lib.check(lib.nnmd_sf_eval(plan.handle, _lib.ptr(nl.posw), nl.n_frames, nl.n_atoms, nl.n_centres,
                                     _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(nl.edge_offsets),

@@ -84,14 +84,23 @@ class VelocityVerlet:
         # cell and pbc are kernel ARGUMENTS of K0: host copies avoid a device read-back in every step
         self.cell, self.pbc = cell.detach().to("cpu", self.x.dtype), pbc.detach().to("cpu", self.x.dtype)
         self.sfd, self.net, self.mode = symm_funcs_data, net, mode
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.x.device)  # sticky OR of every step's NaN flag word
         self.energy, self.f = self._forces()
         self.steps = 0
+        self.check()
 
     def _forces(self):
         res = energy_forces(self.x[None], self.cell, self.pbc, self.sfd, self.net, mode=self.mode, check=False)
+        self.flag |= res.flag  # device-side: no host sync inside the loop
         return res.energy[0], res.forces[0]
 
-    def step(self, n: int = 1):
+    def check(self) -> None:
+        """Raise the reference's ValueError (calculate_sf.py:106-109) if any step so far produced NaN descriptors, e.g. an
+        atom that lost all its neighbours.  One host sync; `step` calls it once at the end of its n steps."""
+        from .features.calculate_sf import raise_on_flag
+        raise_on_flag(self.flag)
+
+    def step(self, n: int = 1, check: bool = True):
         dt, m = self.dt, self.mass
         for _ in range(n):
             self.x += self.v * dt + self.f * (0.5 * dt * dt / m)
@@ -99,4 +108,6 @@ class VelocityVerlet:
             self.energy, self.f = self._forces()
             self.v += (f_old + self.f) * (0.5 * dt / m)
             self.steps += 1
+        if check:
+            self.check()
         return self.energy

@@ -20,6 +20,7 @@ import os
 import torch
 from torch.utils.data import DataLoader
 
+from .. import dist
 from .._util._logger import Logger
 from ..dist import FlatGradients
 from ..engine import force_contract
@@ -200,9 +201,26 @@ class BPNN(torch.nn.Module):
         e_nn, f_nn = self._energies_forces(g, dG)
         loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), energy, f_nn, forces)
         loss.backward()
-        self._flat_grads.allreduce()  # frames are sharded across ranks (no-op on 1 rank)
+        self._flat_grads.allreduce(int(energy.shape[0]))  # frames are sharded across ranks (no-op on 1 rank)
         self.optim.step()
         out.copy_(torch.stack([e_loss.detach(), f_loss.detach(), loss.detach()]))
+
+    def _train_step_empty(self):
+        """This rank has no batch left in a step the other ranks still take: zero gradient with weight 0, the SAME
+        collective and optimizer step as everybody else (the weights stay identical on all ranks, nobody hangs)."""
+        self._flat_grads.zero()
+        self._flat_grads.allreduce(0)
+        self.optim.step()
+
+    def _epoch_steps(self, n_local: int) -> int:
+        """Steps per epoch = the longest rank's batch count (one scalar all-reduce per epoch): per-rank frame shards can
+        differ by one frame, hence by one batch, and every step issues a collective."""
+        if dist._world()[1] == 1:
+            return n_local
+        import torch.distributed as td
+        t = torch.tensor([n_local], dtype=torch.int64, device=self.device)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return int(t.item())
 
     # ---- fused step: K6 -> K4c -> K8 -> K4c' -> K7 on static buffers, replayed from CUDA graphs
     def _fused_ok(self, g, dG) -> bool:
@@ -257,13 +275,15 @@ class BPNN(torch.nn.Module):
             plan.graphs[0].replay()
         elif plan.graphs is not None:
             plan.graphs[0].replay()
-            self._flat_grads.allreduce()  # frames are sharded across ranks
+            self._flat_grads.allreduce(plan.n_frames)  # frames are sharded across ranks: weighted by the batch sizes
             plan.graphs[1].replay()
         else:
             plan.run()
-            self._flat_grads.allreduce()
+            self._flat_grads.allreduce(plan.n_frames)
             self.optim.step()
             self._opt_ready = True
+        if self._flat_grads.world_size() > 1:  # this rank's share of the global-batch loss: out * b_r / sum_r b_r
+            self._acc_multi.addcdiv_(plan.out, self._flat_grads.count, value=float(plan.n_frames))
 
     def _train_step(self, g, dG, energy, forces, out):
         """One optimisation step on a batch given as tensors (DataLoader-style tuples)."""
@@ -275,14 +295,21 @@ class BPNN(torch.nn.Module):
         out.copy_(plan.out)
 
     def _run_epoch(self, loader, train: bool, desc: str):
+        """One pass over `loader`.  One rank: epoch loss = mean of the batch losses (bpnn.py:368-377).  Frames sharded over
+        several ranks: every rank takes the same number of steps (`_epoch_steps`), the gradient of a step is that of the
+        GLOBAL batch (`FlatGradients.allreduce`), and the logged losses are global too (training: mean over steps of the
+        global-batch loss; validation / test: frame-weighted mean), identical on every rank."""
         for net in self.atomic_nets:
             net.train(train)
+        world = dist._world()[1]
         tot = torch.zeros(3, device=self.device)
         out = torch.zeros(3, device=self.device)
         if train and getattr(self, "_flat_grads", None) is None:
             # gradients live in one flat buffer: a single in-place all-reduce per step when frames are sharded
             self._flat_grads = FlatGradients([p for net in self.atomic_nets for p in net.parameters()])
             self._plans, self._opt_ready, self._acc_carry = {}, False, None
+        n_steps = self._epoch_steps(len(loader))
+        self._acc_multi = torch.zeros(3, device=self.device)
         if train and isinstance(loader, FrameBatches) and loader.base.energies.is_cuda \
                 and self._fused_ok({s: v[0] for s, v in loader.base.sf_data.items()}, {s: v[1] for s, v in loader.base.sf_data.items()}):
             # batches are gathered straight into the static buffers of the step (no per-batch tensors, no copies)
@@ -290,10 +317,20 @@ class BPNN(torch.nn.Module):
             self._acc_carry = None  # loss sums of plans evicted during the epoch
             for plan in self._plans.values():
                 plan.acc.zero_()
-            for sel in tqdm(loader.index_batches(self.device), desc=desc, total=len(loader)):
+            batches = loader.index_batches(self.device)
+            for _ in tqdm(range(n_steps), desc=desc, total=n_steps):
+                sel = next(batches, None)
+                if sel is None:
+                    self._train_step_empty()
+                    continue
                 plan = self._plan_for(shapes, int(sel.numel()))
                 plan.load_indexed(loader.base, sel)
                 self._step_plan(plan)
+            if world > 1:
+                import torch.distributed as td
+                td.all_reduce(self._acc_multi)
+                tot = self._acc_multi / n_steps
+                return tot[0], tot[1], tot[2]
             for plan in self._plans.values():
                 tot += plan.acc
                 plan.acc.zero_()
@@ -301,17 +338,39 @@ class BPNN(torch.nn.Module):
                 tot += self._acc_carry
             tot /= len(loader)
             return tot[0], tot[1], tot[2]
-        for g, dG, energy, forces in tqdm(loader, desc=desc, total=len(loader)):
+        batches = iter(loader)
+        frames = torch.zeros(1, device=self.device)
+        for _ in tqdm(range(n_steps), desc=desc, total=n_steps):
+            item = next(batches, None)
+            if item is None:
+                if train:
+                    self._train_step_empty()
+                continue
+            g, dG, energy, forces = item
             energy = energy.to(device=self.device)
             forces = forces.to(device=self.device)
             if train:
                 self._train_step(g, dG, energy, forces, out)
+                if world > 1 and not self._fused_ok(g, dG):  # the fused step adds its share itself (`_step_plan`)
+                    self._acc_multi.addcdiv_(out, self._flat_grads.count, value=float(energy.shape[0]))
             else:
                 with torch.no_grad():
                     e_nn, f_nn = self._energies_forces(g, dG)
                     loss, e_loss, f_loss = self._loss(e_nn.sum(dim=1), energy, f_nn, forces)
                 out.copy_(torch.stack([e_loss, f_loss, loss]))
+                self._acc_multi += out * float(energy.shape[0])
+                frames += float(energy.shape[0])
             tot += out
+        if world > 1:
+            import torch.distributed as td
+            if train:
+                td.all_reduce(self._acc_multi)
+                tot = self._acc_multi / n_steps
+            else:
+                both = torch.cat([self._acc_multi, frames])
+                td.all_reduce(both)
+                tot = both[:3] / both[3]
+            return tot[0], tot[1], tot[2]
         tot /= len(loader)
         return tot[0], tot[1], tot[2]
 
@@ -360,7 +419,13 @@ class BPNN(torch.nn.Module):
         val_loader = batch_loader(val_dataset, batch_size, shuffle=True)
         test_loader = batch_loader(test_dataset, batch_size, shuffle=True)
         self.sched = torch.optim.lr_scheduler.ExponentialLR(self.optim, gamma=0.99)
-        self.net_log = Logger.get_logger("Net training info", "net.log")
+        if dist._world()[0] == 0:
+            self.net_log = Logger.get_logger("Net training info", "net.log")
+        else:  # the losses are global (identical on every rank): one writer
+            import logging
+            self.net_log = logging.getLogger("nnmd_b200.null")
+            self.net_log.addHandler(logging.NullHandler())
+            self.net_log.propagate = False
         self._describe_training(len(train_dataset), len(val_dataset), len(test_dataset), batch_size, epochs)
         curr_lr = float(self.optim.param_groups[0]["lr"])
         line = "{loss} E = {e_loss:e}, {loss} F = {f_loss:e}, {loss} total = {total:e} eV"

@@ -38,6 +38,23 @@ def _worker(rank, world, port, out_dir):
     fg.allreduce()
     assert q1.grad.data_ptr() == fg.flat.data_ptr() and torch.allclose(q1.grad, torch.full((2, 3), 1.5))
     assert torch.allclose(q2.grad, torch.full((4,), 15.0))
+    # ragged shards: rank 0 holds a batch of 3 frames, rank 1 a batch of 1 -> global-batch gradient (3*1 + 1*2)/4; and a
+    # step in which rank 1 has no batch left (weight 0) must complete on both ranks with rank 0's gradient alone
+    fg.zero()
+    q1.grad += float(rank + 1)
+    fg.allreduce(3 if rank == 0 else 1)
+    assert torch.allclose(q1.grad, torch.full((2, 3), 1.25)) and float(fg.count) == 4.0
+    fg.zero()
+    if rank == 0:
+        q2.grad += 7.0
+    fg.allreduce(2 if rank == 0 else 0)
+    assert torch.allclose(q2.grad, torch.full((4,), 7.0)) and float(fg.count) == 2.0
+    # per-epoch step count: 127 vs 128 frames in batches of 101 is 2 steps everywhere (a rank with an extra
+    # batch used to hang in the all-reduce)
+    from nnmd_b200.nn import BPNN
+    bp = BPNN(use_cuda=False)
+    n_local = -(-int((127 + rank) * 0.8) // 101)
+    assert bp._epoch_steps(n_local) == 2
     frames = list(dist.shard_frames(11))
     # dataset build on pre-sharded frames: the target scaling uses the GLOBAL extrema (one MIN and one MAX all-reduce)
     from nnmd_b200.nn.dataset import cache_name, scale_targets

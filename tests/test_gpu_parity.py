@@ -281,12 +281,12 @@ def test_large_cell_properties():
     assert edg < 1e-5
 
 
-def test_edge_centric_and_vertex_centric_kernels_agree(monkeypatch):
-    """The fp32 64-function group runs the edge-centric kernel pair (K3e + gather); NNMD_NO_EDGE=1 forces the
-    vertex-centric kernel.  Same G, dG and fused forces to fp32 round-off, and both within 1e-5 of the fp64 truth."""
+def test_edge_centric_and_vertex_centric_kernels_agree():
+    """The fp32 64-function group runs the edge-centric kernel pair (K3e + gather); withholding the edge scratch
+    (edge=False) forces the vertex-centric kernel.  Same G, dG and fused forces to fp32 round-off, and both within 1e-5
+    of the fp64 truth."""
     from nnmd_b200.engine import fused_force
-    from nnmd_b200.features import calculate_sf as csf_mod  # noqa: F401
-    from nnmd_b200.features.calculate_sf import _PLAN_CACHE, get_plan, raw_descriptors
+    from nnmd_b200.features.calculate_sf import get_plan, raw_descriptors
     from nnmd_b200.neighbor import build_neighbor_list
     from nnmd_b200.workloads import bench_table, fcc_cell
     from oracle import nl_oracle as O3
@@ -296,18 +296,15 @@ def test_edge_centric_and_vertex_centric_kernels_agree(monkeypatch):
     nl = build_neighbor_list(pos[None].to(DEV), cell.to(DEV), pbc.to(DEV), 6.0)
     assert nl.n_edges * 2 == nl.total and nl.edge_offsets is not None
     out = {}
-    for tag, env in (("edge", "0"), ("vertex", "1")):
-        monkeypatch.setenv("NNMD_NO_EDGE", env)
-        _PLAN_CACHE.clear()
-        plan = get_plan(sfd, torch.float32, nl.posw.device)
-        G, dG, flag = raw_descriptors(plan, nl)
-        Gv, _, _ = raw_descriptors(plan, nl, with_grad=False)
+    plan = get_plan(sfd, torch.float32, nl.posw.device)
+    for tag, edge in (("edge", True), ("vertex", False)):
+        G, dG, flag = raw_descriptors(plan, nl, edge=edge)
+        Gv, _, _ = raw_descriptors(plan, nl, with_grad=False, edge=edge)
         torch.manual_seed(3)
         w = torch.randn(nl.n_rows, plan.nf, device=DEV)
-        F = fused_force(plan, nl, w)
+        F = fused_force(plan, nl, w, edge=edge)
         assert int(flag.item()) == 0
         out[tag] = (G.cpu(), dG.cpu(), Gv.cpu(), F.cpu(), w.cpu())
-    _PLAN_CACHE.clear()
     p64 = nl.posw[:, :3].double().cpu()[None]
     z3 = torch.zeros(3, 3, dtype=torch.float64)
     G3, dG3, _ = O3.raw_descriptors(p64, z3, torch.zeros(3, dtype=torch.float64), sfd)
