@@ -90,13 +90,8 @@ class ClockSampler:
 
 
 def make_net(nf: int, device, dtype=torch.float32):
-    from nnmd_b200.nn import AtomicNN
-    torch.manual_seed(0)
-    net = AtomicNN(nf, list(HIDDEN))
-    for layer in net.model:  # the reference's initialisation (bpnn.py:149-157)
-        torch.nn.init.xavier_uniform_(layer.weight)
-        torch.nn.init.constant_(layer.bias, 0)
-    return net.to(device=device, dtype=dtype)
+    from nnmd_b200.workloads import bench_net
+    return bench_net(nf, device, dtype)
 
 
 # ------------------------------------------------------------------------------------------------- reference arm

@@ -49,19 +49,27 @@ class FrameBatches:
     def __len__(self):
         return (self.indices.numel() + self.batch_size - 1) // self.batch_size
 
+    def _epoch_order(self) -> torch.Tensor:
+        """Frame order of one epoch.  Consumes the global RNG exactly as `iter(DataLoader(ds, batch_size, shuffle=...))`
+        does -- one int64 draw for the iterator's base seed, and with shuffle one more that seeds a private generator
+        for the permutation (torch.utils.data: _BaseDataLoaderIter.__init__, RandomSampler.__iter__) -- so a sample
+        script sees the same batches, in the same order, as with the reference's DataLoader (bpnn.py:234-236)."""
+        idx = self.indices
+        torch.empty((), dtype=torch.int64).random_()
+        if self.shuffle and idx.numel() > 0:
+            gen = torch.Generator()
+            gen.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+            idx = idx[torch.randperm(idx.numel(), generator=gen)]
+        return idx
+
     def index_batches(self, device):
         """The frame indices of every batch of one epoch as device tensors (one host-to-device copy per epoch)."""
-        idx = self.indices
-        if self.shuffle:
-            idx = idx[torch.randperm(idx.numel())]
-        idx = idx.to(device)
+        idx = self._epoch_order().to(device)
         for s in range(0, idx.numel(), self.batch_size):
             yield idx[s:s + self.batch_size]
 
     def __iter__(self):
-        idx = self.indices
-        if self.shuffle:
-            idx = idx[torch.randperm(idx.numel())]
+        idx = self._epoch_order()
         for s in range(0, idx.numel(), self.batch_size):
             sel = idx[s:s + self.batch_size]
             g, dG = {}, {}

@@ -33,3 +33,17 @@ def fcc_cell(ncell: int, a: float = CU_LATTICE, sigma: float = 0.05, seed: int =
     pos = pos + sigma * torch.randn(pos.shape, generator=gen, dtype=torch.float64)
     cell = torch.eye(3, dtype=torch.float64) * (ncell * a)
     return pos.to(dtype), cell.to(dtype), torch.ones(3, dtype=dtype)
+
+
+BENCH_HIDDEN = [64, 64]
+
+
+def bench_net(nf: int, device, dtype=torch.float32):
+    """The atomic network of the bench workload: nf-64-64-1, the reference's initialisation (bpnn.py:149-157), seed 0."""
+    from .nn import AtomicNN
+    torch.manual_seed(0)
+    net = AtomicNN(nf, list(BENCH_HIDDEN))
+    for layer in net.model:
+        torch.nn.init.xavier_uniform_(layer.weight)
+        torch.nn.init.constant_(layer.bias, 0)
+    return net.to(device=device, dtype=dtype)

@@ -79,7 +79,155 @@ def fcc(ncell, a=3.615, sigma=0.05, seed=0):
     return pos, np.eye(3) * ncell * a
 
 
+def lj_energy_forces(pos, eps=0.05, sigma=2.7):
+    """Analytic Lennard-Jones energy and forces of a free cluster (targets for the synthetic training sets: SURVEY 8d)."""
+    d = pos[:, None, :] - pos[None, :, :]
+    r2 = (d ** 2).sum(-1) + np.eye(len(pos))
+    s6 = (sigma ** 2 / r2) ** 3
+    np.fill_diagonal(s6, 0.0)
+    e = 2.0 * eps * (s6 ** 2 - s6).sum()
+    coef = 24.0 * eps * (2.0 * s6 ** 2 - s6) / r2
+    return float(e), (coef[:, :, None] * d).sum(axis=1)
+
+
+def config_with_shipped_weights(net, cfg, spec):
+    """net.config(cfg) with load_models=True: the reference calls torch.load without map_location (bpnn.py:139-146), which
+    fails for the shipped CUDA-saved weights on a CPU-only box.  Same end state: configure without loading, then put the
+    global RNG where a real load_models=True run leaves it (after the nn.Linear default initialisation of the AtomicNN
+    constructor, before any Xavier draw) and load the state dict with map_location."""
+    state = torch.get_rng_state()
+    net.config(dict(cfg, load_models=False))
+    torch.set_rng_state(state)
+    AtomicNN(input_size=cfg["input_sizes"][0], hidden_sizes=cfg["hidden_sizes"][0], output_size=1)
+    net.atomic_nets[0].load_state_dict(torch.load(f"{cfg['path']}/atomic_nn_{spec}.pt", map_location="cpu"))
+    net.neural_net_data = dict(cfg)
+
+
+def reference_fit(net, train, val, test, batch_size, epochs, shuffle):
+    """The body of BPNN.fit (bpnn.py:217-306) without its logger / package-metadata dependencies: same loaders, same
+    scheduler, same call order (hence the same draws from the global RNG)."""
+    from torch.utils.data import DataLoader
+    tl = DataLoader(train, batch_size=batch_size, shuffle=shuffle)
+    vl = DataLoader(val, batch_size=batch_size, shuffle=shuffle)
+    sl = DataLoader(test, batch_size=batch_size, shuffle=shuffle)
+    net.sched = torch.optim.lr_scheduler.ExponentialLR(net.optim, gamma=0.99)
+    tr, va = [], []
+    for ep in range(epochs):
+        tr.append([v.item() for v in net._train_loop(ep, tl)])
+        va.append([v.item() for v in net._validate(ep, vl)])
+        net.sched.step()
+    te = [v.item() for v in net._test(sl)]
+    return np.asarray(tr), np.asarray(va), np.asarray(te)
+
+
+def make_train_li():
+    """BASELINE.json configs[2] at parity size: the Li sample's OWN parameter set (samples/li/input/symm_li_27.json),
+    network shape, optimizer settings (samples/li/input/input.yaml) and shipped weights as the starting point, on synthetic
+    27-atom bcc Li frames (the sample's .traj is a missing blob) with analytic LJ targets.  3 epochs of the unmodified
+    reference's _train_loop / _validate."""
+    import json
+    import yaml
+    with open("/root/reference/samples/li/input/symm_li_27.json") as fh:
+        sfd = _symmetry_functions_parser(json.load(fh))["Li"]
+    with open("/root/reference/samples/li/input/input.yaml") as fh:
+        cfg = yaml.safe_load(fh)["neural_network"]
+    a = 3.51
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0.5]])
+    grid = np.stack(np.meshgrid(*[np.arange(3)] * 3, indexing="ij"), -1).reshape(-1, 1, 3)
+    lat = ((grid + base[None]).reshape(-1, 3) * a)[:27] + 0.25 * a
+    gen = torch.Generator().manual_seed(17)
+    M = 24
+    cart = lat[None] + 0.08 * torch.randn(M, 27, 3, generator=gen, dtype=torch.float64).numpy()
+    cell, pbc = np.eye(3) * 3 * a, np.ones(3)
+    ef = [lj_energy_forces(c) for c in cart]
+    E = torch.tensor([[e] for e, _ in ef], dtype=torch.float32)
+    F = torch.tensor(np.array([f for _, f in ef]), dtype=torch.float32)
+    emin, emax = E.min(), E.max()      # dataset.py:85-87
+    E = (E - emin) / (emax - emin)
+    F = F / (emax - emin)
+    g, dg = ref_sf(cart, cell, pbc, sfd, torch.float32)
+    g, dg = torch.tensor(g), torch.tensor(dg)
+    feats, prm, is_int = pack(sfd)
+    out = dict(cart=cart, cell=cell, pbc=pbc, features=feats, params=prm, params_is_int=is_int, g=g.numpy(), dg=dg.numpy(),
+               e_ref=E.numpy(), f_ref=F.numpy())
+    cfg = dict(cfg, input_sizes=[len(sfd["features"])], path="/root/reference/samples/li/models_adamw", batch_size=8, epochs=3)
+    net = BPNN(dtype=torch.float32, use_cuda=False)
+    config_with_shipped_weights(net, cfg, "Li")
+    for k, v in net.atomic_nets[0].state_dict().items():
+        out["w0_" + k] = v.detach().clone().numpy()
+    ds = TrainAtomicDataset({"Li": (g.clone().requires_grad_(True), dg)}, E, F, {"Li": sfd})
+    tr, va, te = reference_fit(net, ds, ds, ds, 8, 3, shuffle=False)
+    out.update(losses_train=tr, losses_val=va, losses_test=te)
+    for k, v in net.atomic_nets[0].state_dict().items():
+        out["w3_" + k] = v.detach().numpy()
+    out["cfg_scalars"] = np.asarray([cfg["learning_rate"], cfg["l2_regularization"], cfg["e_loss_coeff"], cfg["f_loss_coeff"]])
+    np.savez_compressed(os.path.join(HERE, "train_li.npz"), **out, **META)
+    print("train_li", tr, va, te)
+
+
+def make_cu111_flow(n_frames=48, epochs=2):
+    """samples/cu111/train.py:15-66 executed by the unmodified reference (CPU, float32) on the first `n_frames` frames of
+    samples/gpaw/cu111.txt: the parser's output dict is stored as the fixture's INPUT, the dataset / split / training /
+    evaluation numbers as its expected OUTPUT.  Deviations forced by the reference's own defects: make_atomic_dataset
+    hard-codes "cuda" (dataset.py:48), so its body is executed here line by line on the CPU; fit() needs DEBUG / package
+    metadata, so its loop is `reference_fit`; predict() raises TypeError as shipped (bpnn.py:529-531), so
+    the energy / force evaluation is bpnn.py:537-544 on calculate_sf's output."""
+    import yaml
+    n_atoms, frames, cell, pbc = gpaw_parser("/root/reference/samples/gpaw/cu111.txt")
+    frames = frames[:n_frames]
+    with open("/root/reference/samples/cu111/input/input.yaml") as fh:
+        nn_cfg = yaml.safe_load(fh)["neural_network"]
+    N1, N2, N3, N4, N5 = 0, 25, 0, 0, 25        # train.py:19-26
+    params = calculate_params(38.0, N1, N2, N3, N4, N5)
+    sfd = {"params": params, "features": [1] * N1 + [2] * N2 + [3] * N3 + [4] * N4 + [5] * N5}
+    nn_cfg["input_sizes"] = [N1 + N2 + N3 + N4 + N5]
+    # dataset.py:55-101 on the CPU
+    cart = torch.tensor(np.array([fr["Cu"]["positions"] for fr in frames]), dtype=torch.float32)
+    E = torch.tensor(np.array([fr["energy"] for fr in frames]), dtype=torch.float32).unsqueeze(1)
+    F = torch.tensor(np.array([fr["forces"] for fr in frames]), dtype=torch.float32)
+    emin, emax = E.min(), E.max()
+    E = (E - emin) / (emax - emin)
+    F = F / (emax - emin)
+    cell_t, pbc_t = torch.tensor(np.asarray(cell), dtype=torch.float32), torch.tensor(np.asarray(pbc), dtype=torch.float32)
+    g, dg = calculate_sf(cart, cell_t, pbc_t, sfd, disable_tqdm=True)
+    torch.autograd.set_detect_anomaly(False)
+    g.requires_grad = True
+    ds = TrainAtomicDataset({"Cu": (g, dg)}, E, F, {"Cu": sfd})
+    from nnmd.nn import train_val_test_split
+    train, val, test = train_val_test_split(ds, (0.8, 0.1, 0.1))      # train.py:38-41
+    net = BPNN(dtype=torch.float32, use_cuda=False)
+    config_with_shipped_weights(net, dict(nn_cfg, path="/root/reference/samples/cu111/models_adamw"), "Cu")  # load_models: True
+    out = {"w0_" + k: v.detach().clone().numpy() for k, v in net.atomic_nets[0].state_dict().items()}
+    # energy + force evaluation with the shipped weights (bpnn.py:537-544), first 3 frames; a working predict() would
+    # go through calculate_sf, which reseeds the global RNG (calculate_sf.py:115): reproduce the side effect
+    torch.manual_seed(42)
+    gp = g[:3].detach().clone().requires_grad_(True)
+    e_at = net.atomic_nets[0](gp)
+    dE = torch.autograd.grad(e_at.sum(), gp)[0]
+    out["pred_e"] = e_at.sum(1).squeeze().detach().numpy()
+    out["pred_f"] = (-torch.einsum("ijk,ijkl->ijl", dE, dg[:3])).detach().numpy()
+    tr, va, te = reference_fit(net, train, val, test, nn_cfg["batch_size"], epochs, shuffle=True)
+    out.update(losses_train=tr, losses_val=va, losses_test=te,
+               split_train=np.asarray(train.indices), split_val=np.asarray(val.indices), split_test=np.asarray(test.indices))
+    for k, v in net.atomic_nets[0].state_dict().items():
+        out["w_end_" + k] = v.detach().numpy()
+    # the parser's output dict (input of the flow) and samples of the dataset tensors
+    out.update(positions=np.array([fr["Cu"]["positions"] for fr in frames]), forces=np.array([fr["forces"] for fr in frames]),
+               energy=np.array([fr["energy"] for fr in frames]), unit_cell=np.asarray(cell), pbc=np.asarray(pbc),
+               n_atoms=np.asarray(n_atoms), g_head=g[:2].detach().numpy(), dg_head=dg[:2].numpy(),
+               e_scaled=E.numpy(), f_scaled_head=F[:2].numpy(), epochs=np.asarray(epochs),
+               nn_cfg_json=np.asarray(__import__("json").dumps(nn_cfg)))
+    np.savez_compressed(os.path.join(HERE, "cu111_flow.npz"), **out, **META)
+    print("cu111_flow", tr, va, te, "split", train.indices[:5])
+
+
 def main():
+    if len(sys.argv) > 1:   # selected fixtures only: python make_golden.py li cu111flow
+        for what in sys.argv[1:]:
+            {"li": make_train_li, "cu111flow": make_cu111_flow}[what]()
+        return
+    make_train_li()
+    make_cu111_flow()
     torch.manual_seed(1)
     # ---- case 1: random cluster in a triclinic cell, pbc T,T,F, mixed G1/G2/G4/G5 ----------------
     cart = (torch.rand(3, 40, 3, dtype=torch.float64) * torch.tensor([12.0, 10, 5]) - 3).numpy()

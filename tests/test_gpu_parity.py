@@ -597,6 +597,57 @@ def test_million_atom_cell_properties():
     assert torch.equal(key, torch.sort(key).values) and torch.equal(torch.sort(key_t).values, key)
 
 
+@pytest.mark.parametrize("where", ["bulk", "corner"])
+def test_million_atom_cell_subblocks_against_oracle(where):
+    """BASELINE.json configs[3] at FULL size, directly against the fp64 O(N) oracle: the jittered 1,000,188-atom bench cell
+    goes through the fp32 CUDA path (K0..K6, K4c: the bench step with the bench network); a 36 A sub-block plus a halo of
+    rc is cut out of the SAME fp32-wrapped positions and evaluated by the oracle as a free cluster.  For the interior atoms
+    every neighbour and every closed triangle lies inside block + halo (closed triangles are mutual neighbours),
+    so the values must agree: neighbour counts exactly, G and dG to 1e-5 (worst column, normwise), per-atom energies to
+    1e-5, forces to 1e-4 eV/A.  "corner" = the block at the origin, whose atoms sit on the free surfaces wrap-only PBC
+    leaves; "bulk" = the middle of the cell."""
+    from nnmd_b200.engine import force_contract
+    from nnmd_b200.features.calculate_sf import get_plan, normalize, raw_descriptors
+    from nnmd_b200.neighbor import build_neighbor_list
+    from nnmd_b200.workloads import bench_net, bench_table, fcc_cell
+    from oracle import dense_oracle as O2
+    from oracle import nl_oracle as O3
+    sfd = bench_table()
+    pos, cell, pbc = fcc_cell(63, dtype=torch.float32)
+    nl = build_neighbor_list(pos[None].to(DEV), cell.to(DEV), pbc.to(DEV), 6.0)
+    plan = get_plan(sfd, torch.float32, torch.device(DEV))
+    G, dG, flag = raw_descriptors(plan, nl)
+    G_raw = G.clone()
+    g = normalize(G, flag, out=G)
+    net = bench_net(96, DEV)
+    e, dE = net.energy_and_grad(g, need_grad=True)
+    f = force_contract(dE, dG)
+    assert int(flag.item()) == 0
+    p = nl.posw[:, :3].double().cpu()
+    lo = 0.0 if where == "corner" else 96.0
+    size, rc = 36.0, 6.0
+    sel = ((p >= lo - rc) & (p < lo + size + rc)).all(dim=1)
+    idx = torch.nonzero(sel).flatten()
+    sub = p[idx]
+    inner = ((sub >= lo) & (sub < lo + size)).all(dim=1)
+    assert 3000 < int(inner.sum()) < int(sel.sum()) < 12000
+    z3 = torch.zeros(3, 3, dtype=torch.float64)
+    G3, dG3, cnt3 = O3.raw_descriptors(sub[None], z3, torch.zeros(3, dtype=torch.float64), sfd)
+    ii = idx[inner].to(DEV)
+    assert torch.equal(nl.counts().reshape(-1)[ii].cpu().to(torch.int32), cnt3[0][inner])
+    eg = col_relerr(G_raw[ii].cpu(), G3[0][inner], 1)
+    edg = col_relerr(dG[ii].cpu(), dG3[0][inner], 1)
+    g3 = G3[0][inner] / torch.linalg.vector_norm(G3[0][inner], dim=-1, keepdim=True)
+    Ws = [m.weight.detach().double().cpu() for m in net.model]
+    bs = [m.bias.detach().double().cpu() for m in net.model]
+    e_o, _, f_o = O2.energy_force(g3[None], dG3[0][inner][None], Ws, bs)
+    ee = relerr(e.view(-1)[ii].cpu(), e_o.reshape(-1))
+    ef = float((f.view(-1, 3)[ii].cpu().double() - f_o[0]).abs().max())
+    print(f"1M cell, {where} block: {int(inner.sum())} interior atoms of {int(sel.sum())}; G {eg:.2e} dG {edg:.2e} "
+          f"e {ee:.2e} F abs {ef:.2e} (max |F| {float(f_o.abs().max()):.3f})")
+    assert eg < 1e-5 and edg < 1e-5 and ee < 1e-5 and ef < 1e-4
+
+
 def test_md_callers_calculator_and_verlet():
     """The callers either side of the path: the calculator adaptor returns predict's numbers in the caller's
     atom order (species matched by symbol), and the device-resident integrator reproduces a hand-rolled velocity Verlet."""
