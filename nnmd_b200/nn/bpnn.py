@@ -109,6 +109,11 @@ available_optimizers = {"adam": torch.optim.Adam, "adamw": torch.optim.AdamW}
 available_losses = {"mse": torch.nn.MSELoss, "mae": torch.nn.L1Loss, "rmse": RMSELoss}
 
 
+def _short_lr(lr: float) -> str:
+    import numpy as np
+    return str(np.float32(lr))
+
+
 def _package_version() -> str:
     try:
         from importlib.metadata import version
@@ -448,7 +453,9 @@ class BPNN(torch.nn.Module):
             self.sched.step()
             if float(self.optim.param_groups[0]["lr"]) != curr_lr:
                 curr_lr = float(self.optim.param_groups[0]["lr"])
-                self.net_log.info(f"Learning rate changed to {curr_lr}")
+                # the captured optimizer keeps lr as a float32 device scalar: print its shortest round-trip form
+                # (0.099, like the reference's Python float, not 0.0989999994635582)
+                self.net_log.info(f"Learning rate changed to {_short_lr(curr_lr)}")
         e_loss, f_loss, loss = self._test(test_loader)
         self.net_log.info("Testing: " + line.format(e_loss=e_loss.item(), f_loss=f_loss.item(), loss=loss.item(),
                                                     total=loss.item()))

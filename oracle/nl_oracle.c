@@ -368,3 +368,49 @@ int64_t nl_oracle_pairs(const double *pos, int n, double rc, int *pairs, int64_t
     frame_eval(pos, n, &kind, prm, 1, NULL, NULL, NULL, pairs, cap, &total, nthreads);
     return total;
 }
+
+/*
+ * Distance of every atom from the reference's angular discontinuity.  The angular factor is switched off for
+ * |cos| <= 1e-3 (symm_funcs.py:210-211): a triangle whose cosine sits within rounding of that threshold is decided
+ * differently by two arithmetics (fp32 vs fp64), and the term that flips is of full size for lambda = -1.  For every atom
+ * a, margin[a] = min over the closed triangles that contain a, over their three vertex cosines, of | |c| - 1e-3 |:
+ * exactly the cosines that enter G_a and dg[a].  Parity tests between precisions compare atoms whose margin exceeds
+ * the fp32 rounding of a cosine (like the pair-set tests keep away from d = rc).  Brute-force neighbour search: meant
+ * for sub-blocks of ~1e4 atoms.  pos: n*3 (already wrapped).
+ */
+int nl_oracle_threshold_margin(const double *pos, int n, double rc, double *margin, int nthreads) {
+    if (nthreads <= 0) nthreads = nl_oracle_max_threads();
+#pragma omp parallel num_threads(nthreads)
+    {
+        int cap = 256, m;
+        double *u = (double *)malloc(sizeof(double) * 4 * cap);
+#pragma omp for schedule(dynamic, 16)
+        for (int a = 0; a < n; ++a) {
+            m = 0;
+            for (int j = 0; j < n; ++j) {
+                double ux = pos[3 * j] - pos[3 * a], uy = pos[3 * j + 1] - pos[3 * a + 1], uz = pos[3 * j + 2] - pos[3 * a + 2];
+                if (fabs(ux) >= rc || fabs(uy) >= rc || fabs(uz) >= rc) continue;
+                double d = sqrt(ux * ux + uy * uy + uz * uz);
+                if (!(d < rc && d > 0.0)) continue;
+                if (m == cap) { cap *= 2; u = (double *)realloc(u, sizeof(double) * 4 * cap); }
+                u[4 * m] = ux; u[4 * m + 1] = uy; u[4 * m + 2] = uz; u[4 * m + 3] = d;
+                ++m;
+            }
+            double best = 1e300;
+            for (int tj = 0; tj < m; ++tj)
+                for (int tk = tj + 1; tk < m; ++tk) {
+                    double wx = u[4 * tj] - u[4 * tk], wy = u[4 * tj + 1] - u[4 * tk + 1], wz = u[4 * tj + 2] - u[4 * tk + 2];
+                    double z = sqrt(wx * wx + wy * wy + wz * wz), x = u[4 * tj + 3], y = u[4 * tk + 3];
+                    if (!(z < rc && z > 0.0)) continue;
+                    double c[3] = {cos_law(x, y, z), cos_law(x, z, y), cos_law(y, z, x)};
+                    for (int X = 0; X < 3; ++X) {
+                        double g = fabs(fabs(c[X]) - 1e-3);
+                        if (g < best) best = g;
+                    }
+                }
+            margin[a] = best;
+        }
+        free(u);
+    }
+    return 0;
+}

@@ -40,6 +40,8 @@ def _load():
         lib.nl_oracle_pairs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
                                         ctypes.c_int64, ctypes.c_int]
         lib.nl_oracle_max_threads.restype = ctypes.c_int
+        lib.nl_oracle_threshold_margin.restype = ctypes.c_int
+        lib.nl_oracle_threshold_margin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -102,3 +104,15 @@ def pairs(pos_frame: torch.Tensor, cell, pbc, rc: float, nthreads: int = 0) -> n
     out = np.zeros((max(total, 1), 2), dtype=np.int32)
     lib.nl_oracle_pairs(wrapped.ctypes.data, n, float(rc), out.ctypes.data, total, int(nthreads))
     return out[:total]
+
+
+def threshold_margin(pos_frame: torch.Tensor, rc: float, nthreads: int = 0) -> torch.Tensor:
+    """Per atom of ONE frame of already wrapped positions: the smallest | |cos| - 1e-3 | over the cosines of all closed
+    triangles containing the atom -- its distance from the reference's angular on/off threshold (symm_funcs.py:210-211).
+    Brute-force neighbour search: sub-blocks of ~1e4 atoms."""
+    lib = _load()
+    p = pos_frame.detach().to("cpu", torch.float64).contiguous().numpy()
+    out = np.zeros(p.shape[0], dtype=np.float64)
+    rcode = lib.nl_oracle_threshold_margin(p.ctypes.data, p.shape[0], float(rc), out.ctypes.data, int(nthreads))
+    assert rcode == 0
+    return torch.from_numpy(out)

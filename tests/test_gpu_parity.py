@@ -605,7 +605,15 @@ def test_million_atom_cell_subblocks_against_oracle(where):
     every neighbour and every closed triangle lies inside block + halo (closed triangles are mutual neighbours),
     so the values must agree: neighbour counts exactly, G and dG to 1e-5 (worst column, normwise), per-atom energies to
     1e-5, forces to 1e-4 eV/A.  "corner" = the block at the origin, whose atoms sit on the free surfaces wrap-only PBC
-    leaves; "bulk" = the middle of the cell."""
+    leaves; "bulk" = the middle of the cell.
+
+    The reference's angular factor is DISCONTINUOUS: it is switched off for |cos| <= 1e-3 (symm_funcs.py:210-211, SURVEY
+    Q4).  A triangle whose cosine lies within fp32 rounding (~2e-7) of that threshold is decided differently in fp32 and
+    fp64, and the term that flips is of full size for lambda = -1 (measured: 2e-3 of the column maximum).  Among the ~1e7
+    triangle corners of a block a few always do; no fp32 evaluation -- the reference's own included -- can agree with an
+    fp64 one there.  So the comparison runs over the atoms whose closest cosine stays 2e-6 away from the threshold (the
+    oracle reports that margin; the same idea as keeping pair distances away from rc): they must be >= 95 % of the block,
+    and the others are still held to one flipped term (1e-2)."""
     from nnmd_b200.engine import force_contract
     from nnmd_b200.features.calculate_sf import get_plan, normalize, raw_descriptors
     from nnmd_b200.neighbor import build_neighbor_list
@@ -635,17 +643,27 @@ def test_million_atom_cell_subblocks_against_oracle(where):
     G3, dG3, cnt3 = O3.raw_descriptors(sub[None], z3, torch.zeros(3, dtype=torch.float64), sfd)
     ii = idx[inner].to(DEV)
     assert torch.equal(nl.counts().reshape(-1)[ii].cpu().to(torch.int32), cnt3[0][inner])
-    eg = col_relerr(G_raw[ii].cpu(), G3[0][inner], 1)
-    edg = col_relerr(dG[ii].cpu(), dG3[0][inner], 1)
+    margin = O3.threshold_margin(sub, rc)[inner]
+    clean = margin > 2e-6
+    assert float(clean.double().mean()) > 0.95
+    Gi, dGi = G_raw[ii].cpu(), dG[ii].cpu()
+    scale_g = G3[0][inner].abs().amax(dim=0)
+    scale_dg = dG3[0][inner].abs().amax(dim=(0, 2))
+    err_g = ((Gi.double() - G3[0][inner]).abs() / scale_g).amax(dim=1)                       # per atom, worst column
+    err_dg = ((dGi.double() - dG3[0][inner]).abs().amax(dim=2) / scale_dg).amax(dim=1)
     g3 = G3[0][inner] / torch.linalg.vector_norm(G3[0][inner], dim=-1, keepdim=True)
     Ws = [m.weight.detach().double().cpu() for m in net.model]
     bs = [m.bias.detach().double().cpu() for m in net.model]
     e_o, _, f_o = O2.energy_force(g3[None], dG3[0][inner][None], Ws, bs)
-    ee = relerr(e.view(-1)[ii].cpu(), e_o.reshape(-1))
-    ef = float((f.view(-1, 3)[ii].cpu().double() - f_o[0]).abs().max())
-    print(f"1M cell, {where} block: {int(inner.sum())} interior atoms of {int(sel.sum())}; G {eg:.2e} dG {edg:.2e} "
-          f"e {ee:.2e} F abs {ef:.2e} (max |F| {float(f_o.abs().max()):.3f})")
-    assert eg < 1e-5 and edg < 1e-5 and ee < 1e-5 and ef < 1e-4
+    err_e = (e.view(-1)[ii].cpu().double() - e_o.reshape(-1)).abs() / e_o.abs().max()
+    err_f = (f.view(-1, 3)[ii].cpu().double() - f_o[0]).abs().amax(dim=1)
+    print(f"1M cell, {where} block: {int(inner.sum())} interior atoms of {int(sel.sum())}, {int((~clean).sum())} within 2e-6 of the "
+          f"|cos| threshold; away from it: G {float(err_g[clean].max()):.2e} dG {float(err_dg[clean].max()):.2e} "
+          f"e {float(err_e[clean].max()):.2e} F abs {float(err_f[clean].max()):.2e} (max |F| {float(f_o.abs().max()):.3f}); "
+          f"at it: G {float(err_g.max()):.2e} dG {float(err_dg.max()):.2e} e {float(err_e.max()):.2e} F abs {float(err_f.max()):.2e}")
+    assert float(err_g[clean].max()) < 1e-5 and float(err_dg[clean].max()) < 1e-5
+    assert float(err_e[clean].max()) < 1e-5 and float(err_f[clean].max()) < 1e-4
+    assert float(err_g.max()) < 1e-2 and float(err_dg.max()) < 2e-2 and float(err_f.max()) < 1e-3
 
 
 def test_md_callers_calculator_and_verlet():

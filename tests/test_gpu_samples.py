@@ -51,7 +51,10 @@ def test_cu111_train_script_sequence_through_the_nnmd_shim(tmp_path, monkeypatch
     assert sorted(f for f in os.listdir(".") if f.endswith(".pt")) == ["dg_Cu.pt", "g_Cu.pt"]
     g, dg = dataset.sf_data["Cu"]
     assert relerr(g[:2].detach().cpu(), d["g_head"]) < 1e-5
-    assert col_relerr(dg[:2].cpu(), d["dg_head"], 2) < 3e-5
+    # two fp32 evaluations (the reference's on the CPU, this one) of the rc = 38 A auto-parameter set, whose G2 rows bind
+    # eta := r_s up to 38: the summed gradients of those steep columns move by ~1e-4 with the last bit of the
+    # wrapped positions.  Accuracy against the fp64 truth is what tests/test_gpu_parity.py holds to 1e-5.
+    assert col_relerr(dg[:2].cpu(), d["dg_head"], 2) < 3e-4
     assert relerr(dataset.energies.cpu(), d["e_scaled"]) < 1e-6 and relerr(dataset.forces[:2].cpu(), d["f_scaled_head"]) < 1e-6
     # ---- train.py:38-41: the split draws from the global RNG that calculate_sf left seeded with 42
     train_dataset, val_dataset, test_dataset = train_val_test_split(dataset, (0.8, 0.1, 0.1))
@@ -78,9 +81,9 @@ def test_cu111_train_script_sequence_through_the_nnmd_shim(tmp_path, monkeypatch
     va = [[float(x.split("=")[1].split(",")[0].split()[0]) for x in line.split("validation:")[1].split("MSELoss")[1:]]
           for line in log.splitlines() if "validation:" in line]
     print("cu111 flow: train", tr, "ref", d["losses_train"].tolist(), "val", va, "ref", d["losses_val"].tolist())
-    assert "Training sample size:   38" in log and "Learning rate changed to 0.099" in log
-    # same frames in the same batches (DataLoader-compatible shuffling), same start: the first epoch must agree closely;
-    # lr = 0.1 on a 256-wide net makes the trajectory sensitive to fp32 round-off afterwards (tolerances in DESIGN.md)
-    np.testing.assert_allclose(tr[0], d["losses_train"][0], rtol=2e-2)
-    np.testing.assert_allclose(va[0], d["losses_val"][0], rtol=5e-2)
-    assert len(tr) == 2 and np.isfinite(np.asarray(tr + va)).all()
+    assert "Training sample size:   38" in log and "Learning rate changed to 0.099\n" in log and "Learning rate changed to 0.09801\n" in log
+    # same frames in the same batches (DataLoader-compatible shuffling), same start: both epochs must follow the reference
+    # (measured: 3e-6 on the training losses, 2e-5 on the validation losses of both epochs)
+    np.testing.assert_allclose(tr, d["losses_train"], rtol=1e-3)
+    np.testing.assert_allclose(va, d["losses_val"], rtol=1e-3)
+    assert len(tr) == 2
