@@ -95,21 +95,32 @@ def make_net(nf: int, device, dtype=torch.float32):
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    """The reference's algorithm (dense O(N^2)/O(N^3) tensors + autograd, restated in oracle/dense_oracle.py) on the
-    host cores, on a bounded sample of the same lattice and the same 96-row table."""
-    from nnmd_b200.workloads import bench_table, fcc_cell
-    from oracle import dense_oracle as O2
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sfd = bench_table()
-    ncell = args.ref_cells
+def _reference_step_fn(ncell, sfd, net):
+    """One descriptor+energy+force pass of the reference's own CPU implementation on an ncell^3 block of the bench lattice:
+    the UNMODIFIED package staged in oracle/_ref (nnmd.features.calculate_sf, then bpnn.py:537-544: AtomicNN forward,
+    autograd dE/dg, einsum -- BPNN.predict itself raises TypeError as shipped) when it is staged, else
+    the dense restatement oracle/dense_oracle.py."""
+    from nnmd_b200.workloads import fcc_cell
     pos, cell, pbc = fcc_cell(ncell, dtype=torch.float32)
     n = pos.shape[0]
-    net = make_net(len(sfd["features"]), "cpu")
+    from oracle.build_ref import available, load_reference
+    if available():
+        load_reference()
+        from nnmd.features import calculate_sf as ref_calculate_sf
+        from nnmd.nn import AtomicNN as RefAtomicNN
+        ref_net = RefAtomicNN(len(sfd["features"]), list(HIDDEN))
+        ref_net.load_state_dict(net.state_dict())
+
+        def step():
+            g, dg = ref_calculate_sf(pos[None].clone(), cell, pbc, sfd, disable_tqdm=True)
+            torch.autograd.set_detect_anomaly(False)  # calculate_sf.py:42 switches it on globally
+            g = g.squeeze(0).requires_grad_(True)
+            e = ref_net(g)
+            dE = torch.autograd.grad(e.sum(), g)[0]
+            f = -torch.einsum("ij,ijk->ik", dE, dg.squeeze(0))       # bpnn.py:541-544, single frame
+            return float(e.sum()), f
+        return step, n, "reference"
+    from oracle import dense_oracle as O2
     Ws = [m.weight.detach() for m in net.model]
     bs = [m.bias.detach() for m in net.model]
 
@@ -117,25 +128,98 @@ def run_reference(args):
         g, dg = O2.descriptors(pos[None], cell, pbc, sfd, pow_mode="complex64")
         e, dE, f = O2.energy_force(g, dg, Ws, bs)
         return float(e.sum()), f
+    return step, n, "port"
 
-    for _ in range(args.warmup):
+
+def run_reference(args):
+    """`--impl reference`: the reference's dense O(N^2)/O(N^3) CPU path on all host cores, on the largest block of the
+    bench lattice (108 / 256 / 500 atoms) whose K + W steps fit the time budget; the reference cannot hold more than
+    ~500 atoms (N^3 temporaries), let alone the 1M-atom cell."""
+    from nnmd_b200.workloads import bench_table
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sfd = bench_table()
+    net = make_net(len(sfd["features"]), "cpu")
+    # calibrate on 108 atoms, then take the largest block that keeps (K + W) steps inside the budget (t ~ N^3)
+    step, n, kind = _reference_step_fn(3, sfd, net)
+    step()
+    t0 = time.perf_counter()
+    step()
+    t108 = time.perf_counter() - t0
+    ncell, warmup = 3, args.warmup
+    if args.ref_cells:
+        ncell = args.ref_cells
+    else:
+        for cand in (5, 4):
+            est = t108 * ((4 * cand ** 3) / 108.0) ** 3
+            w = args.warmup if est < 5.0 else 1   # a 20 s CPU step needs no three warm-ups; the line reports what was done
+            if est * (args.steps + w) <= args.ref_budget_s:
+                ncell, warmup = cand, w
+                break
+    if ncell != 3:
+        step, n, kind = _reference_step_fn(ncell, sfd, net)
+    for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = n / dt
-    sample = (f"{n}-atom ({ncell}^3 cells) block of the same jittered Cu fcc lattice, same 96-function table, fp32, "
-              f"dense O(N^3) torch restatement of the reference (oracle/dense_oracle.py, complex64 pow); the reference "
-              f"cannot hold the 1M-atom cell (N^3 temporaries)")
+    what = ("unmodified reference from oracle/_ref: nnmd.features.calculate_sf + AtomicNN + autograd + einsum (bpnn.py:537-544)"
+            if kind == "reference" else "dense torch restatement oracle/dense_oracle.py (complex64 pow); oracle/_ref is not staged")
+    sample = (f"{n}-atom ({ncell}^3 cells) block of the same jittered Cu fcc lattice, same 96-function table and network, fp32, "
+              f"{what}; 108-atom step {t108:.2f} s, cost grows as N^3, the reference cannot hold the 1M-atom cell")
+    sizes = [{"atoms": n, "functions": "32 G2 + 64 G4", "s_per_pass": dt, "atoms_per_s": value, "timed_steps": args.steps}]
+    if not args.no_ref_sizes:
+        sizes += reference_size_sweep(sfd, net, t108, skip_atoms=n, budget_s=max(args.ref_budget_s * 1.25 - dt * (args.steps + warmup), 30.0))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Cu fcc, rc=6 A, 32 G2 + 64 G4, MLP 96-64-64-1: descriptor+energy+force", "atoms": n},
-            "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
+                             "host_cpus": cores, "sizes": sizes,
+                             "law": "t ~ F_angular * N^3 (dense (B,N,N,N) temporaries, symm_funcs.py:181-219): the 1M-atom cell is "
+                                    "out of reach of the reference by ~9 orders of magnitude in memory alone"},
             "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def reference_size_sweep(sfd, net, t108, skip_atoms=0, budget_s=150.0):
+    """the reference's calculate_sf path at the sizes that fit, one pass each, same table and
+    seeded lattice -- the full 96-function set at N = 256; at N = 500 the 32 radial functions plus ONE angular function
+    (the full set is ~10 min per pass there) with the F * N^3 extrapolation; radial-only at N = 4000."""
+    from nnmd_b200.workloads import fcc_cell
+    from oracle.build_ref import available, load_reference
+    if not available():
+        return []
+    load_reference()
+    from nnmd.features import calculate_sf as ref_sf
+    out = []
+    t_start = time.perf_counter()
+
+    def one(ncell, feats, params, label):
+        pos, cell, pbc = fcc_cell(ncell, dtype=torch.float32)
+        t0 = time.perf_counter()
+        ref_sf(pos[None].clone(), cell, pbc, {"features": feats, "params": params}, disable_tqdm=True)
+        torch.autograd.set_detect_anomaly(False)
+        dt = time.perf_counter() - t0
+        return {"atoms": int(pos.shape[0]), "functions": label, "s_per_pass": dt, "atoms_per_s": pos.shape[0] / dt}
+
+    F, P = sfd["features"], sfd["params"]
+    rad = one(5, F[:32], P[:32], "32 G2")
+    r = one(5, F[:33], P[:33], "32 G2 + 1 G4")
+    r["extrapolated_full_set_s"] = rad["s_per_pass"] + 64 * (r["s_per_pass"] - rad["s_per_pass"])
+    out += [rad, r]
+    if time.perf_counter() - t_start < budget_s * 0.3:
+        out.append(one(10, F[:32], P[:32], "32 G2"))
+    # the full set at N = 256 costs ~18x the 108-atom pass (measured): only when the budget allows
+    if skip_atoms != 256 and t108 * 18.0 < budget_s - (time.perf_counter() - t_start):
+        out.append(one(4, F, P, "32 G2 + 64 G4"))
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------- ours
@@ -285,6 +369,31 @@ def run_ours(args):
     e2e = {"value": n_atoms / dt, "unit": "atoms/s", "h2d_bytes_per_step": int(host.numel() * 4) * world,
            "d2h_bytes_per_step": int(F.numel() * 4 + E.numel() * 4) * world, "api": api, "ms_per_step": dt * 1e3}
 
+    # ---- checksum of the structure the LAST timed step computed: must agree across N = 1, 2, 4, 8 to fp32 round-off
+    chk = torch.stack([res.forces.double().abs().sum(), *res.forces.double().sum(dim=(0, 1))])
+    if world > 1:
+        td.all_reduce(chk)  # res.energy was already reduced inside the step
+    checksum = {"energy": float(res.energy.double().sum()), "sum_abs_F": float(chk[0]), "sum_F": [float(v) for v in chk[1:]],
+                "atoms": n_atoms}
+
+    # ---- training-step throughput of configs[2] and configs[4] (frames sharded; one flat gradient all-reduce per step)
+    train = None
+    if not args.no_train:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_train
+        del flush_buf
+        torch.cuda.empty_cache()
+        train = {}
+        for cfg_name in ("li", "bin"):
+            dataset = bench_train.build_dataset(cfg_name, args.train_frames, dev, rank, world)
+            entry = bench_train.train_bench(cfg_name, dev, rank, world, args.train_frames, 500, args.train_steps, 5, "weak", dataset)
+            if world > 1:  # the reference's optimisation: global batch stays 500 frames
+                strong = bench_train.train_bench(cfg_name, dev, rank, world, args.train_frames, 500, args.train_steps, 5, "strong", dataset)
+                entry["strong"] = {k: strong[k] for k in ("global_batch_frames", "ms_per_step", "frames_per_s", "atoms_per_s")}
+            if world == 1 and rank == 0 and not args.no_cpu_baseline:
+                entry["cpu_baseline"] = bench_train.reference_train_baseline(cfg_name, *dataset)
+            train[cfg_name] = entry
+            del dataset
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (angular K3e): algorithmic bytes per centre atom
@@ -335,10 +444,22 @@ def run_ours(args):
                        "l2": "256 MiB buffer written between timed steps; per-step working set (neighbour list + dG) is >1 GB",
                        "parallelism": "single GPU" if world == 1 else f"x-slabs x{world} (equal-work boundaries), halo rc, NCCL send/recv"},
             "clocks": clocks.summary(), "gpu_launches": launches, "roofline": roofline}
+    line["checksum"] = checksum
+    if train is not None:
+        line["train"] = train
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_port(sfd)
+        try:  # the reference's own dense algorithm beside it, on the largest block that takes about a second
+            step, n_ref, kind = _reference_step_fn(3, sfd, make_net(nf, "cpu"))
+            step()
+            t0 = time.perf_counter()
+            step()
+            line["cpu_baseline"]["reference_dense"] = {"value": n_ref / (time.perf_counter() - t0), "unit": "atoms/s", "atoms": n_ref,
+                                                       "kind": kind, "note": "see `bench.py --impl reference` for N = 256 / 500"}
+        except Exception as exc:
+            line["cpu_baseline"]["reference_dense"] = {"unavailable": repr(exc)}
     print(json.dumps(line), flush=True)
 
 
@@ -352,7 +473,12 @@ def main():
     ap.add_argument("--mode", default="materialize", choices=["materialize", "fused"])
     ap.add_argument("--mlp", default="auto", choices=["auto", "exact", "tf32"],
                     help="atomic MLP kernel: auto = tensor cores (3xTF32, parity-tested to 1e-5) when the shape allows")
-    ap.add_argument("--ref-cells", type=int, default=3, help="reference arm sample: cells per edge (3 -> 108 atoms)")
+    ap.add_argument("--ref-cells", type=int, default=0, help="reference arm sample: cells per edge (3 -> 108, 4 -> 256, 5 -> 500 atoms; 0 = largest that fits --ref-budget-s)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="reference arm: time budget of the K + W steps (the single passes at other sizes get what is left of 1.25x this)")
+    ap.add_argument("--no-ref-sizes", action="store_true", help="reference arm: skip the N = 256 / 500 / 4000 single passes")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-throughput block")
+    ap.add_argument("--train-frames", type=int, default=8000)
+    ap.add_argument("--train-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tri-per-atom", type=float, default=1350.0,
                     help="closed triangles per atom of the workload (bulk fcc, rc=6: 1350) for the pipe-utilisation estimate")
