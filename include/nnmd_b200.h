@@ -39,6 +39,8 @@ extern "C" {
 /* bits of the device-side status word `flag` (uint32, dev) */
 #define NNMD_FLAG_NAN_G 1u  /* 0/0 or non-finite value in the normalised descriptors  (calculate_sf.py:106-107) */
 #define NNMD_FLAG_NAN_DG 2u /* non-finite value in the descriptor gradients           (calculate_sf.py:108-109) */
+#define NNMD_FLAG_OVERFLOW 4u /* a capacity-bound neighbour build (nnmd_nlist_build) did not fit the caller's buffers: the
+                                 list is incomplete and every K2..K4 kernel given this flag word returns without writing */
 
 /* symmetry-function kinds = nnmd/features/symm_funcs.py:6-15 (SymmetryFunction enum values) */
 #define NNMD_G1 1
@@ -91,6 +93,23 @@ int nnmd_nlist_count(int dtype, const void *posw, int64_t n_frames, int64_t n_at
 int nnmd_nlist_fill(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
                     const void *ws, const int64_t *offsets, int64_t max_row, int32_t *idx, void *stream);
 
+/* K1 without a host synchronisation: count + fill in one call into buffers of FIXED capacity (what a previous build
+ * needed, plus margin): idx int32[idx_cap], rows of at most max_row_cap entries, at most edge_cap owned edges.  When the
+ * structure outgrows a capacity the build sets NNMD_FLAG_OVERFLOW in `flag` (dev uint32) instead of writing out of bounds;
+ * the caller reads `flag` / `stats` whenever it next synchronises (e.g. with the NaN flag at the end of a step) and
+ * rebuilds with larger buffers.  This is what lets an MD step run with no host round trip and be replayed from a CUDA graph.
+ *   go   dev int32 or NULL.  *go == 0 turns every kernel of the build into a no-op: the previous list is REUSED.
+ * nnmd_skin_check decides it on the device (Verlet skin): the list is built with cutoff rc + skin and stays valid until some
+ * atom has moved more than skin / 2 from the positions of the last build (pos_ref, (n_total,4), updated when *go becomes 1;
+ * fill it with NaN to force the first build).  acc: dev uint32 scratch, zero it once.  n_builds: dev int64 counter or NULL.
+ * The K2..K4 kernels re-test every listed neighbour against the functions' own cutoff, so a skin list gives the SAME
+ * descriptors as an exact one (replaces the O(N^2) Python loop of nnmd/md/verlet.py:97-218, which has no list at all). */
+int nnmd_nlist_build(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc, void *ws,
+                     int64_t *offsets, int64_t *edge_offsets, int32_t *idx, int64_t idx_cap, int64_t max_row_cap,
+                     int64_t edge_cap, int64_t *stats, uint32_t *flag, const int32_t *go, void *stream);
+int nnmd_skin_check(int dtype, const void *posw, void *pos_ref, int64_t n_total, double skin, uint32_t *acc, int32_t *go,
+                    int64_t *n_builds, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Symmetry-function plan: the parameter table of one species
  *   replaces the per-call `symm_funcs_data` walk of calculate_sf.py:64-81
@@ -110,7 +129,7 @@ double nnmd_sf_plan_rc_max(const nnmd_sf_plan *plan);
  *   torch.autograd.grad of calculate_sf.py:85-90
  *   G   dev (n_rows, nf)    UN-normalised symmetry functions, column order = plan order
  *   dG  dev (n_rows, nf, 3) d(sum_i G_i,f)/d r_a  (SURVEY Q6), or NULL to skip
- *   flag dev uint32, OR-ed with NNMD_FLAG_NAN_DG
+ *   flag dev uint32, OR-ed with NNMD_FLAG_NAN_DG; when it carries NNMD_FLAG_OVERFLOW on entry the kernels do nothing
  * ------------------------------------------------------------------------------------- */
 int nnmd_sf_eval(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
                  const int64_t *offsets, const int32_t *idx, int64_t max_row, const int64_t *edge_offsets,
@@ -130,12 +149,19 @@ int nnmd_sf_normalize(int dtype, const void *G, int64_t n_rows, int nf, void *gh
  *   replaces the chain autograd.grad (calculate_sf.py:85-90) -> einsum (bpnn.py:353, :538-544)
  *   w      dev (n_rows, nf)  dE/dg_hat of the centre atom
  *   force  dev (n_rows, 3)   overwritten
- *   virial must be NULL here: use nnmd_virial on the returned forces (extension, the reference has no virial: SURVEY Q8)
+ *   virial dev (n_frames, 9) or NULL: W = - sum_a (p_a - centroid) (x) F_a of the forces just computed (extension, the
+ *          reference has no virial: SURVEY Q8; same as calling nnmd_virial afterwards with origin = NULL)
  * ------------------------------------------------------------------------------------- */
 int nnmd_sf_force(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
                   const int64_t *offsets, const int32_t *idx, int64_t max_row, const int64_t *edge_offsets,
                   int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes, const void *w, void *force, void *virial,
                   void *stream);
+
+/* same, with a status word: does nothing when *flag carries NNMD_FLAG_OVERFLOW (sync-free MD steps) */
+int nnmd_sf_force_flag(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,
+                       const int64_t *offsets, const int32_t *idx, int64_t max_row, const int64_t *edge_offsets,
+                       int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes, const void *w, void *force, void *virial,
+                       uint32_t *flag, void *stream);
 
 /* Virial of each frame from per-atom forces, W = - sum_a (p_a - o) (x) F_a, (n_frames, 9) row-major.
  *   The reference has no virial and never adds periodic images (Q1): every frame is a finite cluster, for which

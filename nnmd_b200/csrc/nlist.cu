@@ -20,6 +20,11 @@
 
 namespace nnmd {
 
+// Every kernel of the build takes `go`: a device flag (or NULL = always run).  *go == 0 turns the whole build into
+// no-ops, which is how a neighbour list is REUSED inside a fixed launch sequence (CUDA-graph replay of an MD step: the
+// list is rebuilt only when some atom has moved more than half the skin, decided on the device by skin_check_kernel).
+#define NNMD_GO_GUARD(go) do { if ((go) != nullptr && *(go) == 0) return; } while (0)
+
 // ------------------------------------------------------------------ workspace layout (host+device)
 struct GridHdr {
     long long bbox[6];  // order-preserving encoding of double: min xyz, max xyz
@@ -98,7 +103,8 @@ __device__ __forceinline__ double dec_double(long long k) {
     return __longlong_as_double(k >= 0 ? k : (k ^ 0x7fffffffffffffffLL));
 }
 
-__global__ void hdr_init_kernel(GridHdr *h) {
+__global__ void hdr_init_kernel(GridHdr *h, const int32_t *go) {
+    NNMD_GO_GUARD(go);
     if (threadIdx.x < 3) {
         h->bbox[threadIdx.x] = enc_double(1e300);
         h->bbox[3 + threadIdx.x] = enc_double(-1e300);
@@ -106,7 +112,8 @@ __global__ void hdr_init_kernel(GridHdr *h) {
 }
 
 template <typename T>
-__global__ void bbox_kernel(const T *__restrict__ posw, int64_t n, GridHdr *h) {
+__global__ void bbox_kernel(const T *__restrict__ posw, int64_t n, GridHdr *h, const int32_t *go) {
+    NNMD_GO_GUARD(go);
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
         T x, y, z;
@@ -132,7 +139,8 @@ __global__ void bbox_kernel(const T *__restrict__ posw, int64_t n, GridHdr *h) {
     }
 }
 
-__global__ void grid_setup_kernel(GridHdr *h, double rc, long long cap) {
+__global__ void grid_setup_kernel(GridHdr *h, double rc, long long cap, const int32_t *go) {
+    NNMD_GO_GUARD(go);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     long long nc[3];
     double ext[3];
@@ -182,7 +190,9 @@ __device__ __forceinline__ void cell_coords(const GridHdr *h, T x, T y, T z, int
 
 template <typename T>
 __global__ void bin_count_kernel(const T *__restrict__ posw, int64_t n_total, int64_t n_atoms, int64_t cap,
-                                 const GridHdr *__restrict__ h, int *__restrict__ cell_of, int *__restrict__ cell_cnt) {
+                                 const GridHdr *__restrict__ h, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
+                                 const int32_t *go) {
+    NNMD_GO_GUARD(go);
     const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (i >= n_total) return;
     T x, y, z;
@@ -198,7 +208,8 @@ __global__ void bin_count_kernel(const T *__restrict__ posw, int64_t n_total, in
 template <typename T>
 __global__ void bin_fill_kernel(const T *__restrict__ posw, int64_t n_total, int64_t n_atoms, int64_t cap,
                                 const int *__restrict__ cell_of, const int *__restrict__ cell_start,
-                                int *__restrict__ cursor, int *__restrict__ order, T *__restrict__ spos) {
+                                int *__restrict__ cursor, int *__restrict__ order, T *__restrict__ spos, const int32_t *go) {
+    NNMD_GO_GUARD(go);
     const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (i >= n_total) return;
     const int64_t frame = i / n_atoms;
@@ -250,7 +261,8 @@ __device__ __forceinline__ long long block_exclusive_scan(long long v, long long
     return res;
 }
 
-__global__ void scan_block_sums_kernel(const int *__restrict__ in, int64_t n, long long *__restrict__ block_sums) {
+__global__ void scan_block_sums_kernel(const int *__restrict__ in, int64_t n, long long *__restrict__ block_sums, const int32_t *go) {
+    NNMD_GO_GUARD(go);
     __shared__ long long sh[33];
     const int64_t base = int64_t(blockIdx.x) * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     long long v = 0;
@@ -263,7 +275,8 @@ __global__ void scan_block_sums_kernel(const int *__restrict__ in, int64_t n, lo
 }
 
 // single block: exclusive scan of block_sums in place; writes the grand total to block_sums[nb]
-__global__ void scan_top_kernel(long long *__restrict__ block_sums, int64_t nb) {
+__global__ void scan_top_kernel(long long *__restrict__ block_sums, int64_t nb, const int32_t *go) {
+    NNMD_GO_GUARD(go);
     __shared__ long long sh[33];
     long long carry = 0;
     for (int64_t s = 0; s < nb; s += blockDim.x) {
@@ -279,7 +292,8 @@ __global__ void scan_top_kernel(long long *__restrict__ block_sums, int64_t nb) 
 
 template <typename OutT>
 __global__ void scan_apply_kernel(const int *__restrict__ in, int64_t n, const long long *__restrict__ block_sums,
-                                  OutT *__restrict__ out, int64_t nb) {
+                                  OutT *__restrict__ out, int64_t nb, const int32_t *go) {
+    NNMD_GO_GUARD(go);
     __shared__ long long sh[33];
     const int64_t base = int64_t(blockIdx.x) * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     int item[SCAN_ITEMS];
@@ -300,17 +314,17 @@ __global__ void scan_apply_kernel(const int *__restrict__ in, int64_t n, const l
 }
 
 template <typename OutT>
-static int exclusive_scan(const int *in, int64_t n, OutT *out, long long *scratch, cudaStream_t st) {
+static int exclusive_scan(const int *in, int64_t n, OutT *out, long long *scratch, cudaStream_t st, const int32_t *go = nullptr) {
     const int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (nb == 0) {
         NNMD_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(OutT), st));
         return NNMD_OK;
     }
-    scan_block_sums_kernel<<<unsigned(nb), SCAN_THREADS, 0, st>>>(in, n, scratch);
+    scan_block_sums_kernel<<<unsigned(nb), SCAN_THREADS, 0, st>>>(in, n, scratch, go);
     NNMD_LAUNCH_CHECK("scan_block_sums_kernel");
-    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(scratch, nb);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(scratch, nb, go);
     NNMD_LAUNCH_CHECK("scan_top_kernel");
-    scan_apply_kernel<OutT><<<unsigned(nb), SCAN_THREADS, 0, st>>>(in, n, scratch, out, nb);
+    scan_apply_kernel<OutT><<<unsigned(nb), SCAN_THREADS, 0, st>>>(in, n, scratch, out, nb, go);
     NNMD_LAUNCH_CHECK("scan_apply_kernel");
     return NNMD_OK;
 }
@@ -364,7 +378,9 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
                                                          int *__restrict__ ecounts,
                                                          const int64_t *__restrict__ offsets, int max_row,
                                                          int32_t *__restrict__ idx,
-                                                         unsigned long long *__restrict__ stats) {
+                                                         unsigned long long *__restrict__ stats, int64_t idx_cap,
+                                                         const int32_t *go) {
+    NNMD_GO_GUARD(go);
     extern __shared__ int sh_rows[];  // FILL: warps * max_row candidate indices
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -419,7 +435,7 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
             const int n = min(n_found, max_row);
             const int64_t o = offsets[row];
             // rank sort: indices inside a row are unique (no periodic images), so ranks are a permutation
-            rank_sort_row(buf, n, idx + o);
+            if (o + n <= idx_cap) rank_sort_row(buf, n, idx + o);  // beyond the capacity: the overflow flag is raised elsewhere
             __syncwarp();
         }
     }
@@ -448,7 +464,9 @@ __global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__
                                                                      const int *__restrict__ cell_start, const int *__restrict__ order,
                                                                      T rc, int *__restrict__ counts, int *__restrict__ ecounts,
                                                                      const int64_t *__restrict__ offsets, int max_row,
-                                                                     int32_t *__restrict__ idx, unsigned long long *__restrict__ stats) {
+                                                                     int32_t *__restrict__ idx, unsigned long long *__restrict__ stats,
+                                                                     int64_t idx_cap, const int32_t *go) {
+    NNMD_GO_GUARD(go);
     extern __shared__ __align__(16) unsigned char cell_smem[];
     T *cpos = reinterpret_cast<T *>(cell_smem);                                  // CELL_MCAND x 4
     int *cidx = reinterpret_cast<int *>(cpos + 4 * CELL_MCAND);                  // CELL_MCAND global atom indices
@@ -554,7 +572,7 @@ __global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__
                 __syncwarp();
                 const int n = min(n_found, max_row);
                 const int64_t o = offsets[row];
-                rank_sort_row(buf, n, idx + o);  // unique indices -> ranks are a permutation
+                if (o + n <= idx_cap) rank_sort_row(buf, n, idx + o);  // unique indices -> ranks are a permutation
                 __syncwarp();
             }
         }
@@ -565,7 +583,8 @@ __global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__
 template <typename T, bool FILL>
 static int launch_cell_kernel(const T *spos, int64_t n_frames, int64_t n_atoms, int64_t n_centres, int64_t cap, const GridHdr *h,
                               const int *cell_start, const int *order, T rc, int *counts, int *ecounts, const int64_t *offsets,
-                              int max_row, int32_t *idx, unsigned long long *stats, cudaStream_t st) {
+                              int max_row, int32_t *idx, unsigned long long *stats, cudaStream_t st,
+                              int64_t idx_cap = INT64_MAX, const int32_t *go = nullptr) {
     const size_t smem = size_t(CELL_MCAND) * (4 * sizeof(T) + sizeof(int)) + (FILL ? size_t(CELL_WARPS) * max_row * sizeof(int) : 0);
     if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "neighbour row of %d entries exceeds shared memory", max_row);
     auto kern = nlist_cell_kernel<T, FILL>;
@@ -576,7 +595,7 @@ static int launch_cell_kernel(const T *spos, int64_t n_frames, int64_t n_atoms, 
     int64_t blocks = std::min<int64_t>(n_frames * std::max<int64_t>(cap, 1), int64_t(sm_count()) * occ * 4);
     if (blocks < 1) blocks = 1;
     kern<<<unsigned(blocks), CELL_WARPS * 32, smem, st>>>(spos, n_frames, n_atoms, n_centres, cap, h, cell_start, order, rc, counts,
-                                                         ecounts, offsets, max_row, idx, stats);
+                                                         ecounts, offsets, max_row, idx, stats, idx_cap, go);
     NNMD_LAUNCH_CHECK("nlist_cell_kernel");
     return NNMD_OK;
 }
@@ -626,9 +645,30 @@ static bool use_cell_kernel() {
     return !(env && env[0] == '1');
 }
 
+// small guarded helpers of the capacity-bound build
+__global__ void clear_i64_kernel(int64_t *p, int n, const int32_t *go) {
+    NNMD_GO_GUARD(go);
+    if (threadIdx.x < n) p[threadIdx.x] = 0;
+}
+__global__ void clear_i32_kernel(int *p, int64_t n, const int32_t *go) {
+    NNMD_GO_GUARD(go);
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) p[i] = 0;
+}
+// stats = {total pairs, longest row, owned edges}: totals come from the scans' last elements
+__global__ void stats_finish_kernel(int64_t *stats, const int64_t *offsets, const int64_t *edge_offsets, int64_t n_rows,
+                                    int64_t idx_cap, int64_t max_row_cap, int64_t edge_cap, uint32_t *flag, const int32_t *go) {
+    NNMD_GO_GUARD(go);
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    stats[0] = offsets[n_rows];
+    if (edge_offsets) stats[2] = edge_offsets[n_rows];
+    if (flag && (stats[0] > idx_cap || stats[1] > max_row_cap || (edge_offsets && stats[2] > edge_cap))) atomicOr(flag, NNMD_FLAG_OVERFLOW);
+}
+
 template <typename T>
 static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc, char *ws,
-                            int64_t *offsets, int64_t *edge_offsets, int64_t *stats, cudaStream_t st) {
+                            int64_t *offsets, int64_t *edge_offsets, int64_t *stats, cudaStream_t st,
+                            int64_t idx_cap = INT64_MAX, int64_t max_row_cap = INT64_MAX, int64_t edge_cap = INT64_MAX,
+                            uint32_t *flag = nullptr, const int32_t *go = nullptr) {
     const WsLayout L = ws_layout(n_frames, n_atoms, n_centres);
     const int64_t n_total = n_frames * n_atoms, n_rows = n_frames * n_centres;
     GridHdr *h = (GridHdr *)ws;
@@ -641,7 +681,8 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
     int *ecounts = (int *)(ws + L.off_ecounts);
     long long *scratch = (long long *)(ws + L.off_scan);
 
-    NNMD_CUDA_CHECK(cudaMemsetAsync(stats, 0, 3 * sizeof(int64_t), st));
+    clear_i64_kernel<<<1, 32, 0, st>>>(stats, 3, go);
+    NNMD_LAUNCH_CHECK("clear_i64_kernel");
     if (n_rows == 0 || n_total == 0) {
         NNMD_CUDA_CHECK(cudaMemsetAsync(offsets, 0, (n_rows + 1) * sizeof(int64_t), st));
         if (edge_offsets) NNMD_CUDA_CHECK(cudaMemsetAsync(edge_offsets, 0, (n_rows + 1) * sizeof(int64_t), st));
@@ -649,29 +690,32 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
     }
     const int sms = sm_count();
     ProfScope prof(PROF_NLIST, st);
-    hdr_init_kernel<<<1, 32, 0, st>>>(h);
+    hdr_init_kernel<<<1, 32, 0, st>>>(h, go);
     NNMD_LAUNCH_CHECK("hdr_init_kernel");
     {
         int64_t blocks = (n_total + 255) / 256;
         if (blocks > int64_t(sms) * 8) blocks = int64_t(sms) * 8;
-        bbox_kernel<T><<<unsigned(blocks), 256, 0, st>>>(posw, n_total, h);
+        bbox_kernel<T><<<unsigned(blocks), 256, 0, st>>>(posw, n_total, h, go);
         NNMD_LAUNCH_CHECK("bbox_kernel");
     }
-    grid_setup_kernel<<<1, 32, 0, st>>>(h, rc, (long long)L.cap);
+    grid_setup_kernel<<<1, 32, 0, st>>>(h, rc, (long long)L.cap, go);
     NNMD_LAUNCH_CHECK("grid_setup_kernel");
     // cursor doubles as the per-cell histogram, then is cleared to serve as the fill cursor
-    NNMD_CUDA_CHECK(cudaMemsetAsync(cursor, 0, 4 * (L.ncells_total + 1), st));
+    const unsigned cblocks = unsigned(std::min<int64_t>((L.ncells_total + 1 + 255) / 256, int64_t(sms) * 8));
+    clear_i32_kernel<<<cblocks, 256, 0, st>>>(cursor, L.ncells_total + 1, go);
+    NNMD_LAUNCH_CHECK("clear_i32_kernel");
     const unsigned ablocks = unsigned((n_total + 255) / 256);
-    bin_count_kernel<T><<<ablocks, 256, 0, st>>>(posw, n_total, n_atoms, L.cap, h, cell_of, cursor);
+    bin_count_kernel<T><<<ablocks, 256, 0, st>>>(posw, n_total, n_atoms, L.cap, h, cell_of, cursor, go);
     NNMD_LAUNCH_CHECK("bin_count_kernel");
-    int rcode = exclusive_scan<int>(cursor, L.ncells_total, cell_start, scratch, st);
+    int rcode = exclusive_scan<int>(cursor, L.ncells_total, cell_start, scratch, st, go);
     if (rcode) return rcode;
-    NNMD_CUDA_CHECK(cudaMemsetAsync(cursor, 0, 4 * (L.ncells_total + 1), st));
-    bin_fill_kernel<T><<<ablocks, 256, 0, st>>>(posw, n_total, n_atoms, L.cap, cell_of, cell_start, cursor, order, spos);
+    clear_i32_kernel<<<cblocks, 256, 0, st>>>(cursor, L.ncells_total + 1, go);
+    NNMD_LAUNCH_CHECK("clear_i32_kernel");
+    bin_fill_kernel<T><<<ablocks, 256, 0, st>>>(posw, n_total, n_atoms, L.cap, cell_of, cell_start, cursor, order, spos, go);
     NNMD_LAUNCH_CHECK("bin_fill_kernel");
     if (use_cell_kernel()) {
         rcode = launch_cell_kernel<T, false>(spos, n_frames, n_atoms, n_centres, L.cap, h, cell_start, order, T(rc), counts,
-                                             ecounts, nullptr, 0, nullptr, (unsigned long long *)stats, st);
+                                             ecounts, nullptr, 0, nullptr, (unsigned long long *)stats, st, INT64_MAX, go);
         if (rcode) return rcode;
     } else {
         const int wpb = 8;
@@ -679,24 +723,25 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
         if (blocks > int64_t(sms) * 16) blocks = int64_t(sms) * 16;
         nlist_rows_kernel<T, false><<<unsigned(blocks), wpb * 32, 0, st>>>(
             posw, spos, n_rows, n_atoms, n_centres, L.cap, h, cell_of, cell_start, order, T(rc), counts, ecounts, nullptr, 0,
-            nullptr, (unsigned long long *)stats);
+            nullptr, (unsigned long long *)stats, INT64_MAX, go);
         NNMD_LAUNCH_CHECK("nlist_rows_kernel<count>");
     }
-    rcode = exclusive_scan<int64_t>(counts, n_rows, offsets, scratch, st);
+    rcode = exclusive_scan<int64_t>(counts, n_rows, offsets, scratch, st, go);
     if (rcode) return rcode;
-    // stats[0] = total = offsets[n_rows]
-    NNMD_CUDA_CHECK(cudaMemcpyAsync(stats, offsets + n_rows, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     if (edge_offsets) {
-        rcode = exclusive_scan<int64_t>(ecounts, n_rows, edge_offsets, scratch, st);
+        rcode = exclusive_scan<int64_t>(ecounts, n_rows, edge_offsets, scratch, st, go);
         if (rcode) return rcode;
-        NNMD_CUDA_CHECK(cudaMemcpyAsync(stats + 2, edge_offsets + n_rows, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     }
+    // stats[0] = total = offsets[n_rows], stats[2] = owned edges; raises NNMD_FLAG_OVERFLOW against the caller's capacities
+    stats_finish_kernel<<<1, 32, 0, st>>>(stats, offsets, edge_offsets, n_rows, idx_cap, max_row_cap, edge_cap, flag, go);
+    NNMD_LAUNCH_CHECK("stats_finish_kernel");
     return NNMD_OK;
 }
 
 template <typename T>
 static int nlist_fill_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
-                           const char *ws, const int64_t *offsets, int64_t max_row, int32_t *idx, cudaStream_t st) {
+                           const char *ws, const int64_t *offsets, int64_t max_row, int32_t *idx, cudaStream_t st,
+                           int64_t idx_cap = INT64_MAX, const int32_t *go = nullptr) {
     const WsLayout L = ws_layout(n_frames, n_atoms, n_centres);
     const int64_t n_rows = n_frames * n_centres;
     if (n_rows == 0 || max_row == 0) return NNMD_OK;
@@ -708,7 +753,7 @@ static int nlist_fill_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int
     if (use_cell_kernel()) {
         ProfScope prof(PROF_NLIST, st);
         return launch_cell_kernel<T, true>(spos, n_frames, n_atoms, n_centres, L.cap, h, cell_start, order, T(rc), nullptr, nullptr,
-                                           offsets, int(max_row), idx, nullptr, st);
+                                           offsets, int(max_row), idx, nullptr, st, idx_cap, go);
     }
     int wpb = 8;
     while (wpb > 1 && size_t(wpb) * max_row * 4 > 160 * 1024) wpb >>= 1;
@@ -721,9 +766,39 @@ static int nlist_fill_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int
     if (blocks > int64_t(sms) * 16) blocks = int64_t(sms) * 16;
     ProfScope prof(PROF_NLIST, st);
     kern<<<unsigned(blocks), wpb * 32, smem, st>>>(posw, spos, n_rows, n_atoms, n_centres, L.cap, h, cell_of, cell_start,
-                                                   order, T(rc), nullptr, nullptr, offsets, int(max_row), idx, nullptr);
+                                                   order, T(rc), nullptr, nullptr, offsets, int(max_row), idx, nullptr, idx_cap, go);
     NNMD_LAUNCH_CHECK("nlist_rows_kernel<fill>");
     return NNMD_OK;
+}
+
+// ------------------------------------------------------------------ Verlet-skin reuse decision (device side)
+// acc: one uint32 holding the bit pattern of the largest squared displacement (non-negative floats order like uints)
+template <typename T>
+__global__ void skin_max_kernel(const T *__restrict__ posw, const T *__restrict__ ref, int64_t n, unsigned *__restrict__ acc) {
+    float worst = 0.f;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        T x, y, z, rx, ry, rz;
+        load_pos<T>(posw, i, x, y, z);
+        load_pos<T>(ref, i, rx, ry, rz);
+        const double dx = double(x) - double(rx), dy = double(y) - double(ry), dz = double(z) - double(rz);
+        const float d2 = float(dx * dx + dy * dy + dz * dz);
+        worst = (d2 == d2) ? fmaxf(worst, d2) : 3.0e38f;  // NaN (uninitialised reference) forces a rebuild
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if (lane_id() == 0) atomicMax(acc, __float_as_uint(worst));
+}
+__global__ void skin_decide_kernel(unsigned *acc, float thr2, int32_t *go, int64_t *n_builds) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int g = __uint_as_float(*acc) > thr2 ? 1 : 0;
+    *go = g;
+    *acc = 0u;
+    if (n_builds && g) *n_builds += 1;
+}
+template <typename T>
+__global__ void skin_copy_kernel(const T *__restrict__ posw, T *__restrict__ ref, int64_t n4, const int32_t *go) {
+    NNMD_GO_GUARD(go);
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) ref[i] = posw[i];
 }
 
 static int nlist_args_ok(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
@@ -758,4 +833,44 @@ extern "C" int nnmd_nlist_fill(int dtype, const void *posw, int64_t n_frames, in
     if (dtype == NNMD_F32)
         return nlist_fill_impl<float>((const float *)posw, n_frames, n_atoms, n_centres, rc, (const char *)ws, offsets, max_row, idx, (cudaStream_t)stream);
     return nlist_fill_impl<double>((const double *)posw, n_frames, n_atoms, n_centres, rc, (const char *)ws, offsets, max_row, idx, (cudaStream_t)stream);
+}
+
+extern "C" int nnmd_nlist_build(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
+                                void *ws, int64_t *offsets, int64_t *edge_offsets, int32_t *idx, int64_t idx_cap,
+                                int64_t max_row_cap, int64_t edge_cap, int64_t *stats, uint32_t *flag, const int32_t *go,
+                                void *stream) {
+    int r = nlist_args_ok(dtype, posw, n_frames, n_atoms, n_centres, rc, ws);
+    if (r) return r;
+    if (!offsets || !stats || !flag || (idx_cap > 0 && !idx)) return set_err(NNMD_ERR_INVALID, "nlist_build: null pointer");
+    if (idx_cap < 0 || max_row_cap < 1 || edge_cap < 0) return set_err(NNMD_ERR_INVALID, "nlist_build: bad capacities");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NNMD_F32) {
+        r = nlist_count_impl<float>((const float *)posw, n_frames, n_atoms, n_centres, rc, (char *)ws, offsets, edge_offsets, stats, st,
+                                    idx_cap, max_row_cap, edge_cap, flag, go);
+        if (r) return r;
+        return nlist_fill_impl<float>((const float *)posw, n_frames, n_atoms, n_centres, rc, (const char *)ws, offsets, max_row_cap, idx, st, idx_cap, go);
+    }
+    r = nlist_count_impl<double>((const double *)posw, n_frames, n_atoms, n_centres, rc, (char *)ws, offsets, edge_offsets, stats, st,
+                                 idx_cap, max_row_cap, edge_cap, flag, go);
+    if (r) return r;
+    return nlist_fill_impl<double>((const double *)posw, n_frames, n_atoms, n_centres, rc, (const char *)ws, offsets, max_row_cap, idx, st, idx_cap, go);
+}
+
+extern "C" int nnmd_skin_check(int dtype, const void *posw, void *pos_ref, int64_t n_total, double skin, uint32_t *acc,
+                               int32_t *go, int64_t *n_builds, void *stream) {
+    if (dtype != NNMD_F32 && dtype != NNMD_F64) return set_err(NNMD_ERR_INVALID, "skin_check: bad dtype %d", dtype);
+    if (n_total < 0 || !(skin >= 0.0)) return set_err(NNMD_ERR_INVALID, "skin_check: bad arguments");
+    if (!acc || !go || (n_total > 0 && (!posw || !pos_ref))) return set_err(NNMD_ERR_INVALID, "skin_check: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = unsigned(std::max<int64_t>(1, std::min<int64_t>((n_total + 255) / 256, int64_t(sm_count()) * 8)));
+    const float thr2 = float(0.25 * skin * skin);  // an atom that moved more than skin / 2
+    if (dtype == NNMD_F32) skin_max_kernel<float><<<blocks, 256, 0, st>>>((const float *)posw, (const float *)pos_ref, n_total, acc);
+    else skin_max_kernel<double><<<blocks, 256, 0, st>>>((const double *)posw, (const double *)pos_ref, n_total, acc);
+    NNMD_LAUNCH_CHECK("skin_max_kernel");
+    skin_decide_kernel<<<1, 32, 0, st>>>(acc, thr2, go, n_builds);
+    NNMD_LAUNCH_CHECK("skin_decide_kernel");
+    if (dtype == NNMD_F32) skin_copy_kernel<float><<<blocks, 256, 0, st>>>((const float *)posw, (float *)pos_ref, n_total * 4, go);
+    else skin_copy_kernel<double><<<blocks, 256, 0, st>>>((const double *)posw, (double *)pos_ref, n_total * 4, go);
+    NNMD_LAUNCH_CHECK("skin_copy_kernel");
+    return NNMD_OK;
 }

@@ -257,6 +257,7 @@ struct RadArgs {
 // per-function work is one exponential and a handful of FMAs.
 template <typename T, int MODE, bool UNI>
 __global__ void __launch_bounds__(256) radial_kernel(RadArgs<T> a) {
+    if (a.flag != nullptr && (*a.flag & NNMD_FLAG_OVERFLOW)) return;  // incomplete neighbour list (capacity-bound build)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     T *base = reinterpret_cast<T *>(smem_raw) + size_t(warp) * NB_FIELDS * a.cap;
@@ -618,6 +619,7 @@ __device__ __forceinline__ void phase2_ladder(const float *__restrict__ recs, in
 
 template <typename T, int FPL, int MODE>
 __global__ void __launch_bounds__(128, NNMD_ANG_MINB) angular_kernel(AngArgs<T> a) {
+    if (a.flag != nullptr && (*a.flag & NNMD_FLAG_OVERFLOW)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     // per-warp shared memory: records | neighbour fields | pair queue
@@ -1045,17 +1047,32 @@ extern "C" int nnmd_sf_force(const nnmd_sf_plan *plan, const void *posw, int64_t
                              int64_t n_centres, const int64_t *offsets, const int32_t *idx, int64_t max_row,
                              const int64_t *edge_offsets, int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes,
                              const void *w, void *force, void *virial, void *stream) {
+    return nnmd_sf_force_flag(plan, posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, edge_offsets, n_edges, edge_ws,
+                              edge_ws_bytes, w, force, virial, nullptr, stream);
+}
+
+extern "C" int nnmd_sf_force_flag(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms,
+                                  int64_t n_centres, const int64_t *offsets, const int32_t *idx, int64_t max_row,
+                                  const int64_t *edge_offsets, int64_t n_edges, void *edge_ws, int64_t edge_ws_bytes,
+                                  const void *w, void *force, void *virial, uint32_t *flag, void *stream) {
     int r = sf_args_ok(plan, posw, n_frames, n_atoms, n_centres, offsets, idx, max_row);
     if (r) return r;
-    if (virial) return set_err(NNMD_ERR_INVALID, "sf_force: virial output is not implemented yet");
     const int64_t n_rows = n_frames * n_centres;
     if (n_rows > 0 && (!w || !force)) return set_err(NNMD_ERR_INVALID, "sf_force: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t es = plan->dtype == NNMD_F32 ? 4 : 8;
     if (n_rows > 0) NNMD_CUDA_CHECK(cudaMemsetAsync(force, 0, size_t(n_rows) * 3 * es, st));
     if (plan->dtype == NNMD_F32)
-        return sf_run<float, MODE_FORCE>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, edge_offsets, n_edges, edge_ws, edge_ws_bytes, nullptr, nullptr, (const float *)w, (float *)force, nullptr, st);
-    return sf_run<double, MODE_FORCE>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, 0, nullptr, 0, nullptr, nullptr, (const double *)w, (double *)force, nullptr, st);
+        r = sf_run<float, MODE_FORCE>(plan, (const float *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, edge_offsets, n_edges, edge_ws, edge_ws_bytes, nullptr, nullptr, (const float *)w, (float *)force, flag, st);
+    else
+        r = sf_run<double, MODE_FORCE>(plan, (const double *)posw, n_frames, n_atoms, n_centres, offsets, idx, max_row, nullptr, 0, nullptr, 0, nullptr, nullptr, (const double *)w, (double *)force, flag, st);
+    if (r || !virial || n_frames == 0) return r;
+    // virial of the forces just computed (frame centroid as origin), scratch from the stream-ordered allocator
+    void *ws = nullptr;
+    NNMD_CUDA_CHECK(cudaMallocAsync(&ws, size_t(nnmd_virial_workspace_bytes(n_frames)), st));
+    r = nnmd_virial(plan->dtype, posw, force, n_frames, n_atoms, n_centres, nullptr, ws, virial, stream);
+    cudaFreeAsync(ws, st);
+    return r;
 }
 
 extern "C" int64_t nnmd_virial_workspace_bytes(int64_t n_frames) { return n_frames < 0 ? -1 : n_frames * 12 * int64_t(sizeof(double)); }

@@ -121,6 +121,7 @@ constexpr int EBATCH = NNMD_EDGE_EBATCH;  // (edge, third atom) records built pe
 #endif
 template <bool WITH_PHI, bool LADDER>
 __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(EdgeArgs a) {
+    if (a.flag != nullptr && (*a.flag & NNMD_FLAG_OVERFLOW)) return;  // incomplete neighbour list (capacity-bound build)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using MF = M<float>;
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -388,6 +389,7 @@ template <int MODE>
 #define NNMD_GATHER_MINB 1
 #endif
 __global__ void __launch_bounds__(256, NNMD_GATHER_MINB) edge_gather_kernel(EdgeArgs a) {
+    if (a.flag != nullptr && (*a.flag & NNMD_FLAG_OVERFLOW)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int half = lane >> 4, l16 = lane & 15;

@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from .features.calculate_sf import SfPlan, edge_scratch, get_plan, normalize, raise_on_flag, raw_descriptors
-from .neighbor import NeighborList, build_from_wrapped, wrap_positions
+from .neighbor import NeighborList, NeighborWorkspace, build_from_wrapped, wrap_positions
 
 
 @dataclass
@@ -60,36 +60,47 @@ def virial(nl: NeighborList, forces: torch.Tensor, origin=None) -> torch.Tensor:
     return out
 
 
-def fused_force(plan: SfPlan, nl: NeighborList, w: torch.Tensor, edge: bool = True) -> torch.Tensor:
-    """K4b: forces from dE/dg_hat without a materialised dG (edge=False: vertex-centric angular kernel)."""
+def fused_force(plan: SfPlan, nl: NeighborList, w: torch.Tensor, edge: bool = True, with_virial: bool = False, workspace=None):
+    """K4b: forces from dE/dg_hat without a materialised dG (edge=False: vertex-centric angular kernel).
+    with_virial=True also returns the per-frame virial (n_frames, 3, 3) of those forces from the same call."""
     lib = _lib.load()
     w2 = w.detach().reshape(-1, plan.nf).contiguous()
     out = torch.empty((nl.n_rows, 3), dtype=w.dtype, device=w.device)
-    ews = edge_scratch(plan, nl) if edge else None
+    vir = torch.empty((nl.n_frames, 3, 3), dtype=w.dtype, device=w.device) if with_virial else None
+    ews = edge_scratch(plan, nl, workspace) if edge else None
     with torch.cuda.device(w.device):
-        _lib.check(lib.nnmd_sf_force(plan.handle, _lib.ptr(nl.posw), nl.n_frames, nl.n_atoms, nl.n_centres,
-                                     _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(nl.edge_offsets),
-                                     nl.n_edges, _lib.ptr(ews), 0 if ews is None else ews.numel(), _lib.ptr(w2),
-                                     _lib.ptr(out), None, _lib.stream_ptr()))
-    return out
+        _lib.check(lib.nnmd_sf_force_flag(plan.handle, _lib.ptr(nl.posw), nl.n_frames, nl.n_atoms, nl.n_centres,
+                                          _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(nl.edge_offsets),
+                                          nl.n_edges, _lib.ptr(ews), 0 if ews is None else ews.numel(), _lib.ptr(w2),
+                                          _lib.ptr(out), _lib.ptr(vir), _lib.ptr(nl.status), _lib.stream_ptr()))
+    return (out, vir) if with_virial else out
 
 
 def energy_forces(cart: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, symm_funcs_data: dict, net,
                   mode: str = "materialize", mlp_precision: str = "auto", n_centres: int | None = None,
-                  check: bool = True) -> EvalResult:
-    """Evaluate one species: cart (B,N,3) on the GPU -> energies and reference-semantic forces."""
+                  check: bool = True, workspace: NeighborWorkspace | None = None) -> EvalResult:
+    """Evaluate one species: cart (B,N,3) on the GPU -> energies and reference-semantic forces.
+
+    workspace: a NeighborWorkspace for repeated evaluations of the same system (MD, the sharded bench step): the neighbour
+    build then runs without a host synchronisation into static buffers (and reuses the list inside its skin); with
+    check=False the whole call only enqueues work -- poll `workspace.validate()` / the returned flag when convenient."""
     _lib.require_cuda()
     if cart.dim() == 2:
         cart = cart.unsqueeze(0)
     B, N, _ = cart.shape
     plan = get_plan(symm_funcs_data, cart.dtype, cart.device)
     posw = wrap_positions(cart, cell, pbc)
-    nl = build_from_wrapped(posw, B, N, plan.rc_max, n_centres)
+    if workspace is not None:
+        if (workspace.n_frames, workspace.n_atoms, workspace.n_centres) != (B, N, N if n_centres is None else int(n_centres)):
+            raise ValueError("energy_forces: the NeighborWorkspace was made for another system size")
+        nl = workspace.build(posw)
+    else:
+        nl = build_from_wrapped(posw, B, N, plan.rc_max, n_centres)
     nc = nl.n_centres
     if mode == "materialize":
-        G, dG, flag = raw_descriptors(plan, nl, with_grad=True)
+        G, dG, flag = raw_descriptors(plan, nl, with_grad=True, workspace=workspace)
     elif mode == "fused":
-        G, dG, flag = raw_descriptors(plan, nl, with_grad=False)
+        G, dG, flag = raw_descriptors(plan, nl, with_grad=False, workspace=workspace)
     else:
         raise ValueError(f"unknown mode {mode!r}")
     g = normalize(G, flag, out=G)
@@ -97,7 +108,7 @@ def energy_forces(cart: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, sym
     if mode == "materialize":
         f = force_contract(dE, dG)
     else:
-        f = fused_force(plan, nl, dE)
+        f = fused_force(plan, nl, dE, workspace=workspace)
     if check:
         raise_on_flag(flag)
     e_atoms = e.view(B, nc)

@@ -10,6 +10,7 @@ from .symm_funcs import (
 )
 from .calculate_sf import calculate_sf
 from .auto_params import calculate_params
+from .autograd import symmetry_functions
 
 __all__ = [
     "calculate_sf",
@@ -21,4 +22,5 @@ __all__ = [
     "g4_function",
     "g5_function",
     "calculate_distances",
+    "symmetry_functions",
 ]

@@ -71,15 +71,18 @@ def get_plan(symm_funcs_data: dict, dtype: torch.dtype, device: torch.device) ->
     return plan
 
 
-def edge_scratch(plan: SfPlan, nl: NeighborList):
+def edge_scratch(plan: SfPlan, nl: NeighborList, workspace=None):
     """Scratch for the edge-centric angular kernel (Phi/Gamma per owned edge), or None when the plan does not use it
-    or the buffer does not fit: the C side then runs the vertex-centric kernel (no scratch, ~2x the arithmetic)."""
+    or the buffer does not fit: the C side then runs the vertex-centric kernel (no scratch, ~2x the arithmetic).
+    workspace: a NeighborWorkspace that keeps the scratch between steps (static buffers for CUDA-graph replay)."""
     if nl.edge_offsets is None or nl.n_edges == 0:
         return None
     need = int(_lib.load().nnmd_sf_edge_scratch_bytes(plan.handle, nl.n_edges))
     if need == 0:
         return None
     try:
+        if workspace is not None:
+            return workspace.edge_scratch(need)
         return torch.empty(need, dtype=torch.uint8, device=nl.posw.device)
     except torch.cuda.OutOfMemoryError:
         warnings.warn(f"nnmd_b200: the {need / 2**30:.1f} GiB edge scratch of the edge-centric angular kernel does not fit; "
@@ -87,16 +90,18 @@ def edge_scratch(plan: SfPlan, nl: NeighborList):
         return None
 
 
-def raw_descriptors(plan: SfPlan, nl: NeighborList, with_grad: bool = True, edge: bool = True):
+def raw_descriptors(plan: SfPlan, nl: NeighborList, with_grad: bool = True, edge: bool = True, workspace=None):
     """K2+K3(+K4a): un-normalised G (n_rows,F) and dG (n_rows,F,3) for the rows of `nl`, plus the device flag word.
-    edge=False withholds the edge scratch, which makes the C side take the vertex-centric angular kernel."""
+    edge=False withholds the edge scratch, which makes the C side take the vertex-centric angular kernel.
+    A capacity-bound list (NeighborWorkspace) brings its own sticky status word, which is used as the flag: the kernels
+    return at once when it carries FLAG_OVERFLOW."""
     lib = _lib.load()
     dev = nl.posw.device
     n_rows = nl.n_rows
     G = torch.empty((n_rows, plan.nf), dtype=plan.dtype, device=dev)
     dG = torch.empty((n_rows, plan.nf, 3), dtype=plan.dtype, device=dev) if with_grad else None
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    ews = edge_scratch(plan, nl) if edge else None
+    flag = nl.status if nl.status is not None else torch.zeros(1, dtype=torch.int32, device=dev)
+    ews = edge_scratch(plan, nl, workspace) if edge else None
     with torch.cuda.device(dev):
         _lib.check(lib.nnmd_sf_eval(plan.handle, _lib.ptr(nl.posw), nl.n_frames, nl.n_atoms, nl.n_centres,
                                     _lib.ptr(nl.offsets), _lib.ptr(nl.idx), nl.max_row, _lib.ptr(nl.edge_offsets),
@@ -117,6 +122,8 @@ def normalize(G: torch.Tensor, flag: torch.Tensor, out: torch.Tensor | None = No
 
 def raise_on_flag(flag: torch.Tensor) -> None:
     bits = int(flag.item())
+    if bits & _lib.FLAG_OVERFLOW:
+        raise _lib.NnmdError("the neighbour list outgrew its NeighborWorkspace (call workspace.validate() and repeat the step)")
     if bits & _lib.FLAG_NAN_G:
         raise ValueError("NaN values in the symmetry functions")
     if bits & _lib.FLAG_NAN_DG:

@@ -29,6 +29,10 @@ class NeighborList:
     max_row: int
     edge_offsets: torch.Tensor | None = None   # int64 (n_rows+1): prefix sums of per-row neighbours with a larger index
     n_edges: int = 0
+    # capacity-bound lists (NeighborWorkspace): `total`, `max_row`, `n_edges` above are CAPACITIES, the true values sit in
+    # `stats` on the device, and `status` is the sticky flag word every later kernel of the step reads and ORs into
+    status: torch.Tensor | None = None         # int32 (1,) device: NNMD_FLAG_* bits
+    stats: torch.Tensor | None = None          # int64 (3,) device: total pairs, longest row, owned edges
 
     @property
     def n_rows(self) -> int:
@@ -43,7 +47,7 @@ class NeighborList:
         rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.idx.device), cnt)
         frame = rows // self.n_centres
         i = rows - frame * self.n_centres
-        j = self.idx.to(torch.int64) - frame * self.n_atoms
+        j = self.idx[:rows.numel()].to(torch.int64) - frame * self.n_atoms  # capacity-bound lists: idx is longer than the list
         return torch.stack([frame, i, j], dim=1)
 
 
@@ -110,3 +114,104 @@ def build_neighbor_list(cart: torch.Tensor, cell: torch.Tensor, pbc: torch.Tenso
         raise ValueError(f"cartesians must have shape (n_batch, n_atoms, 3), got {tuple(cart.shape)}")
     posw = wrap_positions(cart, cell, pbc)
     return build_from_wrapped(posw, cart.shape[0], cart.shape[1], rc, n_centres)
+
+
+class NeighborWorkspace:
+    """Persistent buffers of a capacity-bound neighbour build: K1 with NO host synchronisation (nnmd_nlist_build).
+
+    The first `build` sizes the buffers from an exact count (one sync, like `build_from_wrapped`) times `margin`; every
+    later `build` only enqueues kernels.  A structure that outgrows a capacity raises NNMD_FLAG_OVERFLOW in `status`
+    instead of writing out of bounds, the K2..K4 kernels of that step then do nothing, and `validate()` -- called whenever
+    the caller synchronises anyway, e.g. when it reads the NaN flag -- regrows the buffers and asks for the step again.
+    skin > 0: the list is built with cutoff rc + skin and REUSED until an atom has moved more than skin / 2 (decided on the
+    device by nnmd_skin_check, no sync); the descriptor kernels re-test every neighbour against their own cutoffs, so the
+    results do not depend on the skin.  All buffers are static, so a whole MD step can be captured in a CUDA graph.
+    """
+
+    def __init__(self, n_frames: int, n_atoms: int, rc: float, dtype: torch.dtype, device, n_centres: int | None = None,
+                 skin: float = 0.0, margin: float = 1.25):
+        self.lib = _lib.load()
+        self.n_frames, self.n_atoms = int(n_frames), int(n_atoms)
+        self.n_centres = self.n_atoms if n_centres is None else int(n_centres)
+        self.rc, self.skin, self.margin = float(rc), float(skin), float(margin)
+        self.dtype, self.device = dtype, torch.device(device)
+        self.code = _lib.dtype_code(dtype)
+        dev = self.device
+        n_rows = self.n_frames * self.n_centres
+        with torch.cuda.device(dev):
+            self.ws = torch.empty(max(int(self.lib.nnmd_nlist_workspace_bytes(self.n_frames, self.n_atoms)), 1), dtype=torch.uint8, device=dev)
+        self.offsets = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+        self.edge_offsets = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+        self.stats = torch.zeros(3, dtype=torch.int64, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.go = torch.ones(1, dtype=torch.int32, device=dev)
+        self.acc = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.n_builds = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.pos_ref = torch.full((self.n_frames * self.n_atoms, 4), float("nan"), dtype=dtype, device=dev) if self.skin > 0 else None
+        self.idx = None
+        self.idx_cap = self.max_row_cap = self.edge_cap = 0
+        self._scratch = {}
+
+    # ---- capacities
+    def _size_from(self, total: int, max_row: int, n_edges: int) -> None:
+        m = self.margin
+        self.idx_cap = max(int(total * m) + 1024, 1)
+        # rows get 10 % head room only: the longest row sizes the per-warp shared memory of K2/K3 (a 25 % margin on the
+        # 80-entry rows of bulk Cu would cost the angular kernel one of its four resident blocks per SM)
+        self.max_row_cap = (max(max_row + max(4, (max_row + 9) // 10), 8) + 3) & ~3
+        self.edge_cap = max(int(n_edges * m) + 512, 1)
+        self.idx = torch.empty(self.idx_cap, dtype=torch.int32, device=self.device)
+        self._scratch = {}
+
+    def _enqueue(self, posw: torch.Tensor, go) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nnmd_nlist_build(self.code, _lib.ptr(posw), self.n_frames, self.n_atoms, self.n_centres,
+                                                 self.rc + self.skin, _lib.ptr(self.ws), _lib.ptr(self.offsets), _lib.ptr(self.edge_offsets),
+                                                 _lib.ptr(self.idx), self.idx_cap, self.max_row_cap, self.edge_cap, _lib.ptr(self.stats),
+                                                 _lib.ptr(self.status), _lib.ptr(go), _lib.stream_ptr()))
+
+    def build(self, posw: torch.Tensor) -> NeighborList:
+        """Neighbour list of the wrapped positions (n_total, 4).  Sync-free after the first call."""
+        if posw.dtype != self.dtype or posw.shape[0] != self.n_frames * self.n_atoms:
+            raise ValueError("NeighborWorkspace.build: positions do not match the workspace (dtype / atom count)")
+        if self.idx is None:  # first build: exact sizes (one sync), then capacities with margin
+            nl = build_from_wrapped(posw, self.n_frames, self.n_atoms, self.rc + self.skin, self.n_centres)
+            self._size_from(nl.total, nl.max_row, nl.n_edges)
+            self._enqueue(posw, None)
+            if self.pos_ref is not None:
+                self.pos_ref.copy_(posw)
+            self.n_builds += 1
+        elif self.skin > 0:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.nnmd_skin_check(self.code, _lib.ptr(posw), _lib.ptr(self.pos_ref), posw.shape[0], self.skin,
+                                                    _lib.ptr(self.acc), _lib.ptr(self.go), _lib.ptr(self.n_builds), _lib.stream_ptr()))
+            self._enqueue(posw, self.go)
+        else:
+            self._enqueue(posw, None)
+        return NeighborList(posw, self.offsets, self.idx, self.n_frames, self.n_atoms, self.n_centres, self.rc + self.skin,
+                            self.idx_cap, self.max_row_cap, self.edge_offsets, self.edge_cap, self.status, self.stats)
+
+    def edge_scratch(self, nbytes: int) -> torch.Tensor:
+        """Static scratch of the edge-centric angular kernel for the current capacities (reused across steps)."""
+        buf = self._scratch.get(nbytes)
+        if buf is None:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._scratch = {nbytes: buf}
+        return buf
+
+    def validate(self) -> bool:
+        """One host sync: True when every build since the last call fit.  On overflow the buffers are regrown from the
+        recorded demand, the flag is cleared and False is returned: the caller repeats the step(s)."""
+        bits = int(self.status.item())
+        if not bits & _lib.FLAG_OVERFLOW:
+            return True
+        total, max_row, n_edges = (int(v) for v in self.stats.tolist())
+        self._size_from(max(total, self.idx_cap), max(max_row, self.max_row_cap), max(n_edges, self.edge_cap))
+        self.status.bitwise_and_(~_lib.FLAG_OVERFLOW)
+        if self.pos_ref is not None:
+            self.pos_ref.fill_(float("nan"))  # force the next skin check to rebuild
+        return False
+
+    def true_sizes(self):
+        """(total pairs, longest row, owned edges) of the last build: one host sync."""
+        return tuple(int(v) for v in self.stats.tolist())

@@ -535,6 +535,8 @@ def test_virial_is_the_strain_derivative_for_a_translation_invariant_energy():
     F = fused_force(plan, nl, wf.expand(nl.n_rows, -1).contiguous())
     assert float(F.sum(dim=0).abs().max()) < 1e-10 * float(F.abs().max())
     W = virial(nl, F)[0].cpu()
+    F2, W2 = fused_force(plan, nl, wf.expand(nl.n_rows, -1).contiguous(), with_virial=True)   # one call: forces + virial
+    assert torch.equal(F2, F) and float((W2[0].cpu() - W).abs().max()) < 1e-12 * float(W.abs().max())
     W0 = virial(nl, F, origin=[10.0, -3.0, 2.0])[0].cpu()
     assert float((W - W0).abs().max()) < 1e-9 * float(W.abs().max())
     o = pos[0].mean(dim=0)
@@ -666,6 +668,42 @@ def test_million_atom_cell_subblocks_against_oracle(where):
     assert float(err_g.max()) < 1e-2 and float(err_dg.max()) < 2e-2 and float(err_f.max()) < 1e-3
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 1e-5)])
+def test_autograd_function_over_positions_gives_the_reference_forces(dtype, tol):
+    """north_star kernel 4: `symmetry_functions(cart, ...)` is a torch.autograd.Function whose backward is K4b.  With the
+    atomic network on top, -dE/d(cart) through it must equal the force of the explicit path (K6 -> K4c on the materialised
+    dG) and of the oracle chain; gradients w.r.t. the network weights flow through the same graph."""
+    from nnmd_b200.engine import energy_forces
+    from nnmd_b200.features import symmetry_functions
+    from nnmd_b200.nn import AtomicNN
+    from oracle import dense_oracle as O2
+    from oracle import nl_oracle as O3
+    d, sfd = load_case("sf_fcc108")
+    cart, cell, pbc = _inputs(d, dtype)
+    torch.manual_seed(4)
+    net = AtomicNN(len(sfd["features"]), [24, 12]).to(DEV, dtype)
+    x = cart.clone().requires_grad_(True)
+    g = symmetry_functions(x, cell, pbc, sfd)
+    assert g.requires_grad and g.shape == (1, 108, len(sfd["features"]))
+    E = net(g).sum()
+    (dEdx,) = torch.autograd.grad(E, x, retain_graph=True)
+    gw = torch.autograd.grad(E, list(net.parameters()))
+    res = energy_forces(cart, cell, pbc, sfd, net, mode="materialize", mlp_precision="exact")
+    scale = max(1.0, float(res.forces.abs().max()))
+    assert float((-dEdx - res.forces).abs().max()) < tol * scale
+    assert abs(float(E - res.energy.sum())) < tol * abs(float(E))
+    g3, dg3 = O3.descriptors(cart.double().cpu(), cell.double().cpu(), pbc.double().cpu(), sfd)
+    Ws = [m.weight.detach().double().cpu() for m in net.model]
+    bs = [m.bias.detach().double().cpu() for m in net.model]
+    _, _, f_o = O2.energy_force(g3, dg3, Ws, bs)
+    ftol = 1e-10 if dtype == torch.float64 else 1e-4
+    assert float((-dEdx.cpu().double() - f_o).abs().max()) < ftol * max(1.0, float(f_o.abs().max()))
+    assert all(torch.isfinite(v).all() and float(v.abs().max()) > 0 for v in gw)
+    # 2-D input, no batch axis
+    g1 = symmetry_functions(cart[0], cell, pbc, sfd)
+    assert g1.shape == (108, len(sfd["features"])) and torch.equal(g1, g[0].detach())
+
+
 def test_md_callers_calculator_and_verlet():
     """The callers either side of the path: the calculator adaptor returns predict's numbers in the caller's
     atom order (species matched by symbol), and the device-resident integrator reproduces a hand-rolled velocity Verlet."""
@@ -707,3 +745,80 @@ def test_md_callers_calculator_and_verlet():
         v = v + (f + fn) * (0.5 * 0.5 / 63.5)
         f = fn
     assert torch.allclose(vv.x, x, atol=1e-12) and torch.allclose(vv.v, v, atol=1e-12) and vv.steps == 3
+
+
+def test_sync_free_neighbour_workspace_matches_the_exact_build():
+    """NeighborWorkspace (capacity-bound K1, no host sync after the first build) gives the same list as the two-step build,
+    also for a later, different set of positions; a skin list is a superset that yields IDENTICAL descriptors; a structure
+    that outgrows the buffers raises the overflow flag instead of writing out of bounds, and validate() regrows."""
+    from nnmd_b200 import _lib
+    from nnmd_b200.features.calculate_sf import get_plan, raw_descriptors
+    from nnmd_b200.neighbor import NeighborWorkspace, build_from_wrapped, wrap_positions
+    from nnmd_b200.workloads import bench_table, fcc_cell
+    sfd = bench_table()
+    pos, cell, pbc = fcc_cell(6, dtype=torch.float32)
+    plan = get_plan(sfd, torch.float32, torch.device(DEV))
+    N = pos.shape[0]
+    ws = NeighborWorkspace(1, N, 6.0, torch.float32, DEV)
+    ws_skin = NeighborWorkspace(1, N, 6.0, torch.float32, DEV, skin=0.8)
+    gen = torch.Generator().manual_seed(3)
+    for it in range(3):
+        p = (pos + 0.02 * it * torch.randn(pos.shape, generator=gen)).to(DEV)
+        posw = wrap_positions(p[None], cell, pbc)
+        ref = build_from_wrapped(posw, 1, N, 6.0)
+        nl = ws.build(posw)
+        assert ws.validate() and ws.true_sizes() == (ref.total, ref.max_row, ref.n_edges)
+        assert torch.equal(nl.offsets, ref.offsets) and torch.equal(nl.idx[:ref.total], ref.idx) and torch.equal(nl.edge_offsets, ref.edge_offsets)
+        G0, dG0, _ = raw_descriptors(plan, ref)
+        G1, dG1, f1 = raw_descriptors(plan, nl, workspace=ws)
+        assert torch.equal(G0, G1) and torch.equal(dG0, dG1) and int(f1.item()) == 0
+        nls = ws_skin.build(posw)
+        G2, dG2, _ = raw_descriptors(plan, nls, workspace=ws_skin)
+        assert ws_skin.validate() and int(ws_skin.stats[0]) > ref.total
+        assert torch.equal(G0, G2) and torch.equal(dG0, dG2)       # same kept neighbours in the same order: bit-identical
+    assert int(ws.n_builds.item()) == 1 and int(ws_skin.n_builds.item()) == 1   # counted on the skin path only; 0.04 A < skin / 2
+    # overflow: shrink the index buffer below the demand
+    ws.idx_cap, ws.idx = 1000, ws.idx[:1000].clone()
+    nl = ws.build(posw)
+    G3, _, f3 = raw_descriptors(plan, nl, workspace=ws)
+    torch.cuda.synchronize()
+    assert int(ws.status.item()) & _lib.FLAG_OVERFLOW
+    assert not ws.validate() and ws.idx_cap >= ref.total and int(ws.status.item()) == 0
+    nl = ws.build(posw)
+    G4, dG4, _ = raw_descriptors(plan, nl, workspace=ws)
+    assert ws.validate() and torch.equal(G4, G0) and torch.equal(dG4, dG0)
+
+
+def test_graph_captured_md_loop_with_skin_follows_the_plain_loop():
+    """VelocityVerlet: 40 steps with a 0.6 A skin, the step replayed from ONE CUDA graph (no host sync per step), against
+    the same integration without skin and without graph.  The descriptor kernels re-test every listed neighbour, so the
+    trajectories agree to round-off; the skin run rebuilds its list only a few times; an induced buffer overflow is
+    recovered from the snapshot."""
+    from nnmd_b200.md import VelocityVerlet
+    from nnmd_b200.nn import AtomicNN
+    d, sfd = load_case("sf_cu111_json")
+    torch.manual_seed(2)
+    net = AtomicNN(len(sfd["features"]), [16, 8]).to(DEV, torch.float64)
+    x0 = torch.tensor(d["cart"][0], dtype=torch.float64, device=DEV)
+    gen = torch.Generator().manual_seed(1)
+    v0 = (0.02 * torch.randn(x0.shape, generator=gen, dtype=torch.float64)).to(DEV)
+    cell, pbc = torch.tensor(d["cell"], dtype=torch.float64), torch.tensor(d["pbc"], dtype=torch.float64)
+    kw = dict(mass=63.5, cell=cell, pbc=pbc, symm_funcs_data=sfd, net=net, dt=0.5)
+    plain = VelocityVerlet(x0, v0, skin=0.0, graph=False, **kw)
+    fast = VelocityVerlet(x0, v0, skin=0.6, graph=True, **kw)
+    plain.step(40)
+    fast.step(25)
+    assert fast._graph is not None
+    fast.step(15)
+    assert plain.steps == fast.steps == 40
+    assert float((plain.x - fast.x).abs().max()) < 1e-9 and float((plain.v - fast.v).abs().max()) < 1e-10
+    assert abs(float(plain.energy - fast.energy)) < 1e-10 * abs(float(plain.energy))
+    assert float((plain.x - x0).abs().max()) > 0.1                    # the atoms did move
+    assert 1 <= fast.list_builds() < 20
+    # induced overflow: the next block of steps detects it at its end, regrows, and repeats from the snapshot
+    fast.ws.idx_cap, fast.ws.idx = 64, fast.ws.idx[:64].clone()
+    fast.ws.pos_ref.fill_(float("nan"))
+    fast._graph, fast._eager_steps = None, 0
+    plain.step(5)
+    fast.step(5)
+    assert fast.ws.idx_cap > 64 and float((plain.x - fast.x).abs().max()) < 1e-9
