@@ -99,6 +99,8 @@ int nnmd_nlist_fill(int dtype, const void *posw, int64_t n_frames, int64_t n_ato
  * the caller reads `flag` / `stats` whenever it next synchronises (e.g. with the NaN flag at the end of a step) and
  * rebuilds with larger buffers.  This is what lets an MD step run with no host round trip and be replayed from a CUDA graph.
  *   go   dev int32 or NULL.  *go == 0 turns every kernel of the build into a no-op: the previous list is REUSED.
+ * stats here is int64[6]: {total pairs, longest row, owned edges} of the latest build, then the same three of the FIRST build
+ * that raised NNMD_FLAG_OVERFLOW since the flag was last cleared (what to regrow to).
  * nnmd_skin_check decides it on the device (Verlet skin): the list is built with cutoff rc + skin and stays valid until some
  * atom has moved more than skin / 2 from the positions of the last build (pos_ref, (n_total,4), updated when *go becomes 1;
  * fill it with NaN to force the first build).  acc: dev uint32 scratch, zero it once.  n_builds: dev int64 counter or NULL.

@@ -656,12 +656,18 @@ __global__ void clear_i32_kernel(int *p, int64_t n, const int32_t *go) {
 }
 // stats = {total pairs, longest row, owned edges}: totals come from the scans' last elements
 __global__ void stats_finish_kernel(int64_t *stats, const int64_t *offsets, const int64_t *edge_offsets, int64_t n_rows,
-                                    int64_t idx_cap, int64_t max_row_cap, int64_t edge_cap, uint32_t *flag, const int32_t *go) {
+                                    int64_t idx_cap, int64_t max_row_cap, int64_t edge_cap, uint32_t *flag, int need_out,
+                                    const int32_t *go) {
     NNMD_GO_GUARD(go);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     stats[0] = offsets[n_rows];
     if (edge_offsets) stats[2] = edge_offsets[n_rows];
-    if (flag && (stats[0] > idx_cap || stats[1] > max_row_cap || (edge_offsets && stats[2] > edge_cap))) atomicOr(flag, NNMD_FLAG_OVERFLOW);
+    if (flag && (stats[0] > idx_cap || stats[1] > max_row_cap || (edge_offsets && stats[2] > edge_cap))) {
+        // the demand of the FIRST build that did not fit is what the caller regrows to (stats[3..5]); the steps after it run
+        // on garbage and must not overwrite it
+        const unsigned old = atomicOr(flag, NNMD_FLAG_OVERFLOW);
+        if (!(old & NNMD_FLAG_OVERFLOW) && need_out) { stats[3] = stats[0]; stats[4] = stats[1]; stats[5] = stats[2]; }
+    }
 }
 
 template <typename T>
@@ -733,7 +739,7 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
         if (rcode) return rcode;
     }
     // stats[0] = total = offsets[n_rows], stats[2] = owned edges; raises NNMD_FLAG_OVERFLOW against the caller's capacities
-    stats_finish_kernel<<<1, 32, 0, st>>>(stats, offsets, edge_offsets, n_rows, idx_cap, max_row_cap, edge_cap, flag, go);
+    stats_finish_kernel<<<1, 32, 0, st>>>(stats, offsets, edge_offsets, n_rows, idx_cap, max_row_cap, edge_cap, flag, flag ? 1 : 0, go);
     NNMD_LAUNCH_CHECK("stats_finish_kernel");
     return NNMD_OK;
 }

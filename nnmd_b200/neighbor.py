@@ -32,7 +32,7 @@ class NeighborList:
     # capacity-bound lists (NeighborWorkspace): `total`, `max_row`, `n_edges` above are CAPACITIES, the true values sit in
     # `stats` on the device, and `status` is the sticky flag word every later kernel of the step reads and ORs into
     status: torch.Tensor | None = None         # int32 (1,) device: NNMD_FLAG_* bits
-    stats: torch.Tensor | None = None          # int64 (3,) device: total pairs, longest row, owned edges
+    stats: torch.Tensor | None = None          # int64 (6,) device: total pairs, longest row, owned edges (latest | first overflow)
 
     @property
     def n_rows(self) -> int:
@@ -142,7 +142,7 @@ class NeighborWorkspace:
             self.ws = torch.empty(max(int(self.lib.nnmd_nlist_workspace_bytes(self.n_frames, self.n_atoms)), 1), dtype=torch.uint8, device=dev)
         self.offsets = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
         self.edge_offsets = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
-        self.stats = torch.zeros(3, dtype=torch.int64, device=dev)
+        self.stats = torch.zeros(6, dtype=torch.int64, device=dev)   # latest build | first overflowing build
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.go = torch.ones(1, dtype=torch.int32, device=dev)
         self.acc = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -205,13 +205,13 @@ class NeighborWorkspace:
         bits = int(self.status.item())
         if not bits & _lib.FLAG_OVERFLOW:
             return True
-        total, max_row, n_edges = (int(v) for v in self.stats.tolist())
+        total, max_row, n_edges = (int(v) for v in self.stats[3:].tolist())  # demand of the first build that did not fit
         self._size_from(max(total, self.idx_cap), max(max_row, self.max_row_cap), max(n_edges, self.edge_cap))
-        self.status.bitwise_and_(~_lib.FLAG_OVERFLOW)
+        self.status.zero_()  # NaN bits raised by the steps that ran on the incomplete list mean nothing; the repeat re-raises real ones
         if self.pos_ref is not None:
             self.pos_ref.fill_(float("nan"))  # force the next skin check to rebuild
         return False
 
     def true_sizes(self):
         """(total pairs, longest row, owned edges) of the last build: one host sync."""
-        return tuple(int(v) for v in self.stats.tolist())
+        return tuple(int(v) for v in self.stats[:3].tolist())

@@ -757,6 +757,7 @@ def test_sync_free_neighbour_workspace_matches_the_exact_build():
     from nnmd_b200.workloads import bench_table, fcc_cell
     sfd = bench_table()
     pos, cell, pbc = fcc_cell(6, dtype=torch.float32)
+    pos = pos + 0.9   # keep every atom inside the cell: under wrap-only PBC an atom that crosses a face jumps by a cell length
     plan = get_plan(sfd, torch.float32, torch.device(DEV))
     N = pos.shape[0]
     ws = NeighborWorkspace(1, N, 6.0, torch.float32, DEV)
