@@ -53,6 +53,12 @@ const char *nnmd_last_error(void);
 /* number of SMs of the current device (grid sizing), or -1 */
 int nnmd_device_sm_count(void);
 
+/* Process-wide kernel-selection switches (explicit API calls, never the environment).
+ *   "edge_ws" 0|1   form of the edge-centric angular kernel: 0 (default) every warp stages, enumerates and accumulates;
+ *                   1 warp-specialised producer / consumer warps handing record batches over through mbarriers.
+ *                   Bit-identical results; which one is faster is a measurement (profiles/README.md). */
+int nnmd_set_option(const char *name, int value);
+
 /* Instrumentation for bench.py: number of kernel launches issued by this library so far, and optional
  * CUDA-event timing per kernel class on the launching stream (classes: 0 nlist, 1 radial, 2 angular,
  * 3 normalize, 4 contract, 5 mlp, 6 wrap, 7 edge gather).  nnmd_profile_read synchronises the device and resets. */

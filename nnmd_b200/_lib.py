@@ -25,6 +25,7 @@ _SIGNATURES = {
     "nnmd_abi_version": (ctypes.c_int, []),
     "nnmd_last_error": (ctypes.c_char_p, []),
     "nnmd_device_sm_count": (ctypes.c_int, []),
+    "nnmd_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "nnmd_launch_count": (ctypes.c_longlong, []),
     "nnmd_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "nnmd_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -156,6 +157,11 @@ def profile_read() -> dict:
     cnt = (ctypes.c_longlong * n)()
     check(load().nnmd_profile_read(ms, cnt))
     return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(PROF_CLASSES)}
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide kernel-selection switch of the library (see include/nnmd_b200.h: nnmd_set_option)."""
+    check(load().nnmd_set_option(name.encode(), int(value)))
 
 
 def launch_count() -> int:

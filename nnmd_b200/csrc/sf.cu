@@ -1008,6 +1008,11 @@ extern "C" void nnmd_sf_plan_destroy(nnmd_sf_plan *p) {
     delete p;
 }
 
+extern "C" int nnmd_set_option(const char *name, int value) {
+    if (name && strcmp(name, "edge_ws") == 0) { nnmd::g_edge_ws = value ? 1 : 0; return NNMD_OK; }
+    return set_err(NNMD_ERR_INVALID, "set_option: unknown option %s", name ? name : "(null)");
+}
+
 extern "C" double nnmd_sf_plan_rc_max(const nnmd_sf_plan *p) { return p ? p->rc_max : 0.0; }
 
 static int sf_args_ok(const nnmd_sf_plan *plan, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres,

@@ -108,6 +108,13 @@ __device__ __forceinline__ void make_record_edge(const NbView<float> &nb, int tj
     }
 }
 
+#ifndef NNMD_EDGE_PACK2
+#define NNMD_EDGE_PACK2 0
+#endif
+#ifndef NNMD_EDGE_UNROLL
+#define NNMD_EDGE_UNROLL 2
+#endif
+constexpr int NNMD_EDGE_UNROLL_N = NNMD_EDGE_UNROLL;
 #ifndef NNMD_EDGE_EBATCH
 #define NNMD_EDGE_EBATCH 64
 #endif
@@ -191,6 +198,11 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
         float2 phi[4], vg[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { phi[i] = make_float2(0.f, 0.f); vg[i] = phi[i]; }
+#if NNMD_EDGE_PACK2
+        // centre-k terms of the lane's functions (0,1) and (2,3), accumulated as packed pairs: two FFMA2 instead of four FFMA
+        float2 phik[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        const float2 zz01 = make_float2(zeta[0], zeta[1]), zz23 = make_float2(zeta[2], zeta[3]);
+#endif
         // the owner's own share of dG: sum over its edges of Phi * u (the gather then only visits the other edges)
         float gox[4], goy[4], goz[4];
 #pragma unroll
@@ -202,6 +214,9 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 ph[i] = phi[i].x + phi[i].y;
+#if NNMD_EDGE_PACK2
+                ph[i] += (i & 1) ? phik[i >> 1].y : phik[i >> 1].x;
+#endif
                 ph[i] += __shfl_xor_sync(0xffffffffu, ph[i], 16);
                 ga[i] = vg[i].y + __shfl_xor_sync(0xffffffffu, vg[i].y, 16);
             }
@@ -259,10 +274,13 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
                     cur_tj = __shfl_sync(0xffffffffu, t < 32 ? tj0 : tj1, t & 31);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { phi[i] = make_float2(0.f, 0.f); vg[i].y = 0.f; }
+#if NNMD_EDGE_PACK2
+                    phik[0] = phik[1] = make_float2(0.f, 0.f);
+#endif
                 }
                 const int t_end = rest ? __ffsll(static_cast<long long>(rest)) - 1 : cnt;
                 const float *r = recs + (t + half) * EREC_STRIDE + class_off;
-#pragma unroll 2
+#pragma unroll NNMD_EDGE_UNROLL_N
                 for (int tt = t + half; tt < t_end; tt += 2, r += 2 * EREC_STRIDE) {
                     const float4 l = *reinterpret_cast<const float4 *>(r);       // L0 L1 L2 .
                     const float4 c2 = *reinterpret_cast<const float4 *>(r + 8);  // A2 B2 V0a V0j
@@ -276,8 +294,16 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
 #pragma unroll
                         for (int i = 1; i < 4; ++i) {
                             q01[i] = __fmul2_rn(q01[i - 1], make_float2(rr.x, rr.y));
+#if !NNMD_EDGE_PACK2
                             q2[i] = q2[i - 1] * rr.z;
+#endif
                         }
+#if NNMD_EDGE_PACK2
+                        q2[1] = q2[0] * rr.z;
+                        const float rz2 = rr.z * rr.z;
+                        const float2 qk23 = __fmul2_rn(make_float2(q2[0], q2[1]), make_float2(rz2, rz2));
+                        q2[2] = qk23.x; q2[3] = qk23.y;
+#endif
                     } else {
 #pragma unroll
                         for (int i = 1; i < 4; ++i) {
@@ -291,10 +317,17 @@ __global__ void __launch_bounds__(128, NNMD_EDGE_MINB) angular_edge4_kernel(Edge
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float2 t01 = __ffma2_rn(make_float2(zeta[i], zeta[i]), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w));
-                            const float t2 = fmaf(zeta[i], c2.x, c2.y);
                             phi[i] = __ffma2_rn(q01[i], t01, phi[i]);
+#if !NNMD_EDGE_PACK2
+                            const float t2 = fmaf(zeta[i], c2.x, c2.y);
                             phi[i].x = fmaf(q2[i], t2, phi[i].x);
+#endif
                         }
+#if NNMD_EDGE_PACK2
+                        const float2 a2 = make_float2(c2.x, c2.x), b2 = make_float2(c2.y, c2.y);
+                        phik[0] = __ffma2_rn(make_float2(q2[0], q2[1]), __ffma2_rn(zz01, a2, b2), phik[0]);
+                        phik[1] = __ffma2_rn(make_float2(q2[2], q2[3]), __ffma2_rn(zz23, a2, b2), phik[1]);
+#endif
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) vg[i] = __ffma2_rn(q01[i], make_float2(c2.z, c2.w), vg[i]);
@@ -500,10 +533,33 @@ __global__ void __launch_bounds__(256, NNMD_GATHER_MINB) edge_gather_kernel(Edge
     if (MODE == MODE_DG && bad) atomicOr(a.flag, NNMD_FLAG_NAN_DG);
 }
 
+#include "sf_edge_ws.cuh"
+
+#ifndef NNMD_EDGE_WS
+#define NNMD_EDGE_WS 0  // default form of K3e: 0 = every warp does everything; 1 = warp-specialised (producer / consumer warps).
+#endif                  // Measured on the 1M-atom cell (profiles/README.md, round 2): 55.6 ms vs 60.5-64.7 ms -- the
+                        // specialised form halves the number of FMA-issuing warps the register file can hold, and loses.
+static int g_edge_ws = NNMD_EDGE_WS;  // nnmd_set_option("edge_ws", 0|1)
+
 template <int MODE>
 static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
     constexpr bool WITH_PHI = MODE != MODE_G;
-    {
+    bool use_ws = g_edge_ws != 0;
+    if (const char *env = tuning_env("NNMD_EDGE_WS")) use_ws = env[0] != '0';  // tuning builds only
+    const size_t ws_smem = ws_pair_bytes(a.cap) * WS_PAIRS;
+    if (ws_smem > 110 * 1024) use_ws = false;  // rows too long for two resident blocks per SM: the plain form degrades more gently
+    NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
+    if (use_ws) {
+        auto kern = a.ladder ? angular_edge4_ws_kernel<WITH_PHI, true> : angular_edge4_ws_kernel<WITH_PHI, false>;
+        NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ws_smem)));
+        int occ = 1;
+        NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 2 * WS_PAIRS * 32, ws_smem));
+        if (occ < 1) occ = 1;
+        int64_t blocks = std::min<int64_t>((a.n_rows + WS_PAIRS - 1) / WS_PAIRS, int64_t(sm_count()) * occ);
+        ProfScope prof(PROF_ANGULAR, st);
+        kern<<<unsigned(blocks), 2 * WS_PAIRS * 32, ws_smem, st>>>(a);
+        NNMD_LAUNCH_CHECK("angular_edge4_ws_kernel");
+    } else {
         const size_t per_warp = size_t(EBATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 256 * sizeof(int);
         int wpb = 4;
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
@@ -515,7 +571,6 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
         if (occ < 1) occ = 1;
         int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * occ);
-        NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
 #ifdef NNMD_TUNING
         if (const char *env = tuning_env("NNMD_DBG")) a.dbg = atoi(env);
 #endif
@@ -537,4 +592,3 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
     (void)g;
     return NNMD_OK;
 }
-

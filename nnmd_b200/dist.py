@@ -106,8 +106,9 @@ class SlabShard:
     def exchange_halo(self, device=None) -> torch.Tensor:
         """Positions this rank computes on: owned atoms first, then the halo atoms received from the peers.
 
-        world == 1: just the owned positions on `device`.  Otherwise one count all-gather plus one batched
-        send/recv round (NCCL on GPUs; gloo when the tensors live on the CPU).
+        world == 1: just the owned positions on `device`.  Otherwise one batched send/recv round (NCCL on GPUs; gloo when
+        the tensors live on the CPU) straight into a persistent local buffer: the peers' counts are learned once per send
+        plan (one all-gather), after which a step issues no host synchronisation and no concatenation.
         """
         device = torch.device(device) if device is not None else self.owned_pos.device
         own = self.owned_pos.to(device)
@@ -118,23 +119,27 @@ class SlabShard:
             all_counts = [torch.empty_like(counts) for _ in range(self.world)]
             td.all_gather(all_counts, counts)
             self.recv_counts = [int(all_counts[peer][self.rank]) for peer in range(self.world)]
-        recv_counts = self.recv_counts
-        ops, recv_bufs, keep = [], [], []
+            self._local = None
+        n_own = own.shape[0]
+        local = getattr(self, "_local", None)
+        if local is None or local.device != device or local.dtype != own.dtype or local.shape[0] != n_own + sum(self.recv_counts):
+            local = self._local = torch.empty((n_own + sum(self.recv_counts), 3), dtype=own.dtype, device=device)
+        local[:n_own].copy_(own)
+        ops, keep, off = [], [], n_own
         for peer in range(self.world):
             if peer == self.rank:
                 continue
             if self.send_idx[peer] is not None:
-                buf = own.index_select(0, self.send_idx[peer].to(device)).contiguous()
+                buf = own.index_select(0, self.send_idx[peer].to(device))
                 keep.append(buf)
                 ops.append(td.P2POp(td.isend, buf, peer))
-            if recv_counts[peer] > 0:
-                rb = torch.empty((recv_counts[peer], 3), dtype=own.dtype, device=device)
-                recv_bufs.append(rb)
-                ops.append(td.P2POp(td.irecv, rb, peer))
+            if self.recv_counts[peer] > 0:
+                ops.append(td.P2POp(td.irecv, local[off:off + self.recv_counts[peer]], peer))
+                off += self.recv_counts[peer]
         if ops:
             for req in td.batch_isend_irecv(ops):
                 req.wait()
-        return torch.cat([own] + recv_bufs, dim=0) if recv_bufs else own
+        return local
 
 
 def shard_frames(n_frames: int, rank: int | None = None, world: int | None = None) -> range:

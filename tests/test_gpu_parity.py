@@ -823,3 +823,37 @@ def test_graph_captured_md_loop_with_skin_follows_the_plain_loop():
     plain.step(5)
     fast.step(5)
     assert fast.ws.idx_cap > 64 and float((plain.x - fast.x).abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize("with_grad", [True, False])
+def test_warp_specialised_edge_kernel_is_bit_identical(with_grad):
+    """The producer/consumer form of K3e (nnmd_set_option("edge_ws", 1): batches of records handed from producer warps to
+    consumer warps through mbarrier-guarded shared-memory rings) does the same arithmetic in the same order as the default
+    form: G, dG and the fused forces must be bit-identical, on a multi-row-per-pair workload and on a tiny one where most
+    pairs of a block get no row at all (termination path)."""
+    from nnmd_b200 import _lib
+    from nnmd_b200.engine import fused_force
+    from nnmd_b200.features.calculate_sf import get_plan, raw_descriptors
+    from nnmd_b200.neighbor import build_neighbor_list
+    from nnmd_b200.workloads import bench_table, fcc_cell
+    sfd = bench_table()
+    plan = get_plan(sfd, torch.float32, torch.device(DEV))
+    try:
+        for ncell in (7, 1):
+            pos, cell, pbc = fcc_cell(ncell, dtype=torch.float32)
+            nl = build_neighbor_list(pos[None].to(DEV), cell.to(DEV), pbc.to(DEV), 6.0)
+            torch.manual_seed(ncell)
+            w = torch.randn(nl.n_rows, plan.nf, device=DEV)
+            out = []
+            for ws in (0, 1):
+                _lib.set_option("edge_ws", ws)
+                G, dG, flag = raw_descriptors(plan, nl, with_grad=with_grad)
+                F = fused_force(plan, nl, w)
+                torch.cuda.synchronize()
+                assert int(flag.item()) == 0
+                out.append((G, dG, F))
+            assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][2], out[1][2])
+            if with_grad:
+                assert torch.equal(out[0][1], out[1][1])
+    finally:
+        _lib.set_option("edge_ws", 0)
