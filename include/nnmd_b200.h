@@ -128,6 +128,20 @@ int nnmd_skin_check(int dtype, const void *posw, void *pos_ref, int64_t n_total,
  * ------------------------------------------------------------------------------------- */
 typedef struct nnmd_sf_plan nnmd_sf_plan;
 int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, const double *params, nnmd_sf_plan **plan);
+/* Multi-species plan (EXTENSION: the reference evaluates every species in isolation, nnmd/nn/dataset.py:59-67, and its
+ * training step raises for two species -- SURVEY Q9, 8f-3; there is no reference oracle, the tests use finite differences
+ * and a dense restatement).  Every atom carries a species index in posw.w (nnmd_set_species), all atoms of all species are
+ * neighbours of each other, and every function f weights its terms by species:
+ *     radial   G_i,f = sum_j  wr_f[s_j] phi_f(d_ij)
+ *     angular  G_i,f = 2^(1-zeta) sum_{j != k} pw_f[s_j][s_k] P(c_ijk) exp(..) fc fc fc          pw_f symmetric
+ *   weights host double[nf * n_species * n_species]: block f holds pw_f row-major; radial functions use its first row as
+ *   wr_f.  One-hot weights give the element-resolved functions of Behler's multi-species scheme (per-pair-type tables),
+ *   species-dependent scalars give weighted symmetry functions.  dG keeps the reference's meaning:
+ *   d(sum over ALL atoms i of G_i,f) / d r_a. */
+int nnmd_sf_plan_create_species(int dtype, int nf, const int32_t *kinds, const double *params, int n_species,
+                                const double *weights, nnmd_sf_plan **plan);
+/* posw[:, 3] = species[i % n_atoms] for n_frames frames of n_atoms atoms (species: dev int32[n_atoms], values < n_species) */
+int nnmd_set_species(int dtype, void *posw, const int32_t *species, int64_t n_frames, int64_t n_atoms, void *stream);
 void nnmd_sf_plan_destroy(nnmd_sf_plan *plan);
 double nnmd_sf_plan_rc_max(const nnmd_sf_plan *plan);
 

@@ -47,6 +47,10 @@ _SIGNATURES = {
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nnmd_sf_plan_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.POINTER(ctypes.c_void_p)]),
+    "nnmd_sf_plan_create_species": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                   ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "nnmd_set_species": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                        ctypes.c_void_p]),
     "nnmd_sf_plan_destroy": (None, [ctypes.c_void_p]),
     "nnmd_sf_plan_rc_max": (ctypes.c_double, [ctypes.c_void_p]),
     "nnmd_sf_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

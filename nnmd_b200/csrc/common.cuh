@@ -69,6 +69,18 @@ template <> __device__ __forceinline__ void load_pos<double>(const double *posw,
     x = a.x; y = a.y; z = b.x;
 }
 
+// position + the 4th component (species index of the atom as a real number, 0 when species are not used)
+template <typename T> __device__ __forceinline__ void load_pos4(const T *posw, int64_t i, T &x, T &y, T &z, T &w);
+template <> __device__ __forceinline__ void load_pos4<float>(const float *posw, int64_t i, float &x, float &y, float &z, float &w) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(posw) + i);
+    x = v.x; y = v.y; z = v.z; w = v.w;
+}
+template <> __device__ __forceinline__ void load_pos4<double>(const double *posw, int64_t i, double &x, double &y, double &z, double &w) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(posw) + 2 * i);
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(posw) + 2 * i + 1);
+    x = a.x; y = a.y; z = b.x; w = b.y;
+}
+
 // ---- math in the working precision ----------------------------------------------------------
 // "acc" = accurate library routine (used once per neighbour / per triangle),
 // "fast" = the SFU path used only inside the per-function inner loop of the fp32 kernels.

@@ -186,6 +186,8 @@ struct NbView {
 // Gathers the neighbours of a centre that lie inside rc into shared memory; returns their number.
 // FULL: also stage fc, fc', psi = exp(-eta d^2) fc, psi' for the given (rc, eta).
 // first_gt >= 0: also record each kept neighbour's edge slot (row position - first_gt; negative = owned by the neighbour).
+// first_gt == STAGE_SPECIES: record each kept neighbour's species index (posw.w) in the same array instead (multi-species plans).
+constexpr int STAGE_SPECIES = -2;
 template <typename T, bool FULL>
 __device__ __forceinline__ int stage_row(const T *__restrict__ posw, const int32_t *__restrict__ idx, int64_t o0,
                                          int64_t o1, T xa, T ya, T za, T rc, T inv_rc, T eta, NbView<T> nb, int cap,
@@ -195,11 +197,11 @@ __device__ __forceinline__ int stage_row(const T *__restrict__ posw, const int32
     for (int64_t base = o0; base < o1; base += 32) {
         const int64_t e = base + lane;
         bool keep = false;
-        T ux = 0, uy = 0, uz = 0, d = 0;
+        T ux = 0, uy = 0, uz = 0, d = 0, wj = 0;
         if (e < o1) {
             const int j = __ldg(idx + e);
             T xj, yj, zj;
-            load_pos<T>(posw, j, xj, yj, zj);
+            load_pos4<T>(posw, j, xj, yj, zj, wj);
             ux = xj - xa; uy = yj - ya; uz = zj - za;
             d = norm3<T>(ux, uy, uz);
             keep = (d < rc) && (d > T(0));
@@ -211,6 +213,7 @@ __device__ __forceinline__ int stage_row(const T *__restrict__ posw, const int32
                 st4<T>(nb.u4 + 4 * p, ux, uy, uz, d);
                 nb.invd[p] = M<T>::rcp(d);
                 if (first_gt >= 0) nb.epos[p] = int(e - o0) - first_gt;
+                else if (first_gt == STAGE_SPECIES) nb.epos[p] = int(wj);
                 if (FULL) {
                     T s, c;
                     M<T>::sincospi_(d * inv_rc, &s, &c);
@@ -250,12 +253,15 @@ struct RadArgs {
     const T *w;
     T *force;
     uint32_t *flag;
+    const T *wr;  // multi-species: weight of a neighbour of species s is wr[s]; NULL otherwise
 };
 
 // One warp per centre atom, lanes over radial functions, the staged row broadcast from shared memory.
 // UNI: every radial function has the same cutoff, so fc and fc' are staged once per neighbour and the
 // per-function work is one exponential and a handful of FMAs.
-template <typename T, int MODE, bool UNI>
+// MS (multi-species, extension without a reference counterpart: SURVEY Q9 / 8f-3): G_i = sum_j wr[s_j] phi(d_ij), and the
+// summed gradient d(sum_i G_i)/d r_a collects (wr[s_j] + wr[s_a]) phi'(d_aj) from the pair (a, j).
+template <typename T, int MODE, bool UNI, bool MS = false>
 __global__ void __launch_bounds__(256) radial_kernel(RadArgs<T> a) {
     if (a.flag != nullptr && (*a.flag & NNMD_FLAG_OVERFLOW)) return;  // incomplete neighbour list (capacity-bound build)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -268,14 +274,19 @@ __global__ void __launch_bounds__(256) radial_kernel(RadArgs<T> a) {
     for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
         const int64_t frame = row / a.n_centres;
         const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
-        T xa, ya, za;
-        load_pos<T>(a.posw, gi, xa, ya, za);
+        T xa, ya, za, sa;
+        load_pos4<T>(a.posw, gi, xa, ya, za, sa);
         const int nn = stage_row<T, UNI>(a.posw, a.idx, a.offsets[row], a.offsets[row + 1], xa, ya, za, a.rc_max,
-                                         inv_rc_max, T(0), nb, a.cap);
+                                         inv_rc_max, T(0), nb, a.cap, MS ? STAGE_SPECIES : -1);
+        if (MS) {  // psi is not used by the radial functions: it carries the neighbour's weight
+            for (int t = lane; t < nn; t += 32) nb.psi[t] = a.wr[nb.epos[t]];
+            __syncwarp();
+        }
         if (MODE != MODE_G) {  // fold the -2/d of the gradient into the staged vectors: u <- -2 u / d (d itself stays in .d)
+            const T wa = MS ? a.wr[int(sa)] : T(1);
             for (int t = lane; t < nn; t += 32) {
                 const Q4<T> u = ld4<T>(nb.u4 + 4 * t);
-                const T sc = T(-2) * nb.invd[t];
+                const T sc = (MS ? -(wa + nb.psi[t]) : T(-2)) * nb.invd[t];
                 st4<T>(nb.u4 + 4 * t, sc * u.a, sc * u.b, sc * u.c, u.d);
             }
             __syncwarp();
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(256) radial_kernel(RadArgs<T> a) {
                     }
                     const T dr = d - rs;
                     const T ex = M<T>::exp2_fast(nel2 * dr * dr);  // G1: eta = 0 -> 1
-                    val = M<T>::fma_(ex, fc, val);
+                    val = MS ? M<T>::fma_(ex * fc, nb.psi[t], val) : M<T>::fma_(ex, fc, val);
                     if (MODE != MODE_G) {
                         // own-atom gradient plus the identical term inside every neighbour's G_j: the staged
                         // vector already carries -2/d
@@ -356,6 +367,8 @@ struct AngArgs {
     const T *w;
     T *force;
     uint32_t *flag;
+    const T *pw;  // multi-species: symmetric pair weights pw[s_j * ns + s_k] of the two neighbours of a centre; NULL otherwise
+    int ns;
 };
 
 // Triangle record (REC_STRIDE reals in shared memory), one block of REC_CLASS per lambda class (+ then -):
@@ -380,7 +393,8 @@ __device__ __forceinline__ T cos_law(T p2, T q2, T r2, T p, T q, T ip, T iq, boo
 // fp64 uses the accurate library routines.
 template <typename T, int MODE>
 __device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk, int kind, int pm1, int ladder, T step,
-                                            T rc, T inv_rc, T eta, T *__restrict__ rec) {
+                                            T rc, T inv_rc, T eta, T *__restrict__ rec, const T *__restrict__ pw = nullptr,
+                                            int ns = 0, int s_a = 0) {
     const Q4<T> uj = ld4<T>(nb.u4 + 4 * tj), uk = ld4<T>(nb.u4 + 4 * tk);
     const T x = uj.d, y = uk.d, ix = nb.invd[tj], iy = nb.invd[tk];
     const T wx = uj.a - uk.a, wy = uj.b - uk.b, wz = uj.c - uk.c;
@@ -409,6 +423,14 @@ __device__ __forceinline__ void make_record(const NbView<T> &nb, int tj, int tk,
         E[0] = psx * psy * fz;   Ex[0] = dpsx * psy * fz;   Ey[0] = psx * dpsy * fz;
         E[1] = psx * psz * fcy;  Ex[1] = dpsx * psz * fcy;  Ey[1] = psx * psz * dfcy;
         E[2] = psy * psz * fcx;  Ex[2] = psy * psz * dfcx;  Ey[2] = dpsy * psz * fcx;
+    }
+    if (pw != nullptr) {
+        // multi-species: the term of a centre is weighted by the species pair of its two neighbours: centre a sees (j, k),
+        // centre j sees (a, k), centre k sees (a, j)   (the staged epos array carries the species index)
+        const int s_j = nb.epos[tj], s_k = nb.epos[tk];
+        const T W[3] = {pw[s_j * ns + s_k], pw[s_a * ns + s_k], pw[s_a * ns + s_j]};
+#pragma unroll
+        for (int X = 0; X < 3; ++X) { E[X] *= W[X]; Ex[X] *= W[X]; Ey[X] *= W[X]; }
     }
     T blk[2][REC_CLASS];
     blk[0][RR + 3] = blk[1][RR + 3] = T(0);
@@ -646,10 +668,11 @@ __global__ void __launch_bounds__(128, NNMD_ANG_MINB) angular_kernel(AngArgs<T> 
     for (int64_t row = int64_t(blockIdx.x) * wpb + warp; row < a.n_rows; row += int64_t(gridDim.x) * wpb) {
         const int64_t frame = row / a.n_centres;
         const int64_t gi = frame * a.n_atoms + (row - frame * a.n_centres);
-        T xa, ya, za;
-        load_pos<T>(a.posw, gi, xa, ya, za);
+        T xa, ya, za, sa;
+        load_pos4<T>(a.posw, gi, xa, ya, za, sa);
         const int nn = stage_row<T, true>(a.posw, a.idx, a.offsets[row], a.offsets[row + 1], xa, ya, za, a.rc, inv_rc,
-                                          a.eta, nb, a.cap);
+                                          a.eta, nb, a.cap, a.pw != nullptr ? STAGE_SPECIES : -1);
+        const int s_a = int(sa);
         AngAcc<T, FPL> acc;
         acc.clear();
 
@@ -660,7 +683,7 @@ __global__ void __launch_bounds__(128, NNMD_ANG_MINB) angular_kernel(AngArgs<T> 
             if (lane < cnt) {
                 const int pk = queue[(head + lane) & 63];
                 make_record<T, MODE>(nb, pk & 0xffff, pk >> 16, a.kind, a.pm1, a.ladder, a.step, a.rc, inv_rc, a.eta,
-                                     recs + lane * REC_STRIDE);
+                                     recs + lane * REC_STRIDE, a.pw, a.ns, s_a);
             }
             __syncwarp();
             if constexpr (sizeof(T) == 4) {
@@ -837,13 +860,13 @@ __global__ void virial_store_kernel(const double *__restrict__ wsum, int64_t n, 
 // =============================================================================================
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-template <typename T, int MODE, bool UNI>
+template <typename T, int MODE, bool UNI, bool MS = false>
 static int launch_radial_t(RadArgs<T> a, cudaStream_t st) {
     int wpb = 8;
     while (wpb > 1 && size_t(wpb) * NB_FIELDS * a.cap * sizeof(T) > 160 * 1024) wpb >>= 1;
     const size_t smem = size_t(wpb) * NB_FIELDS * a.cap * sizeof(T);
     if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "radial: neighbour row of %d entries exceeds shared memory", a.cap);
-    auto kern = radial_kernel<T, MODE, UNI>;
+    auto kern = radial_kernel<T, MODE, UNI, MS>;
     NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int64_t blocks = (a.n_rows + wpb - 1) / wpb;
     blocks = std::min<int64_t>(blocks, int64_t(sm_count()) * 8);
@@ -854,8 +877,9 @@ static int launch_radial_t(RadArgs<T> a, cudaStream_t st) {
 }
 
 template <typename T, int MODE>
-static int launch_radial(const nnmd_sf_plan *p, RadArgs<T> a, cudaStream_t st) {
-    return p->rad.uniform_rc ? launch_radial_t<T, MODE, true>(a, st) : launch_radial_t<T, MODE, false>(a, st);
+static int launch_radial(const RadialTab &rad, RadArgs<T> a, cudaStream_t st) {
+    if (a.wr != nullptr) return rad.uniform_rc ? launch_radial_t<T, MODE, true, true>(a, st) : launch_radial_t<T, MODE, false, true>(a, st);
+    return rad.uniform_rc ? launch_radial_t<T, MODE, true>(a, st) : launch_radial_t<T, MODE, false>(a, st);
 }
 
 template <typename T, int FPL, int MODE>
@@ -901,13 +925,20 @@ static int sf_run(const nnmd_sf_plan *p, const T *posw, int64_t n_frames, int64_
     if (n_rows == 0) return NNMD_OK;
     int cap = int((std::max<int64_t>(max_row, 1) + 3) & ~int64_t(3));
     if (cap >= 32768) return set_err(NNMD_ERR_CAPACITY, "neighbour row of %lld entries is not supported", (long long)max_row);
-    if (p->rad.n > 0) {
+    auto run_radial = [&](const RadialTab &rad) -> int {
         RadArgs<T> a;
         a.posw = posw; a.n_rows = n_rows; a.n_atoms = n_atoms; a.n_centres = n_centres; a.offsets = offsets; a.idx = idx;
-        a.cap = cap; a.n = p->rad.n; a.rc_max = T(p->rad.rc_max);
-        a.rc = (const T *)p->rad.d_rc; a.eta = (const T *)p->rad.d_eta; a.rs = (const T *)p->rad.d_rs; a.col = p->rad.d_col;
-        a.nf = p->nf; a.G = G; a.dG = dG; a.w = w; a.force = force; a.flag = flag;
-        int r = launch_radial<T, MODE>(p, a, st);
+        a.cap = cap; a.n = rad.n; a.rc_max = T(rad.rc_max);
+        a.rc = (const T *)rad.d_rc; a.eta = (const T *)rad.d_eta; a.rs = (const T *)rad.d_rs; a.col = rad.d_col;
+        a.nf = p->nf; a.G = G; a.dG = dG; a.w = w; a.force = force; a.flag = flag; a.wr = (const T *)rad.d_wr;
+        return launch_radial<T, MODE>(rad, a, st);
+    };
+    if (p->rad.n > 0) {
+        int r = run_radial(p->rad);
+        if (r) return r;
+    }
+    for (const RadialTab &rad : p->ms_rads) {  // multi-species plans: one launch per neighbour-weight vector
+        int r = run_radial(rad);
         if (r) return r;
     }
     // the first EDGE_WS_HEADER bytes of the scratch hold the row counter of the dynamically scheduled kernel: it belongs to
@@ -935,6 +966,7 @@ static int sf_run(const nnmd_sf_plan *p, const T *posw, int64_t n_frames, int64_
         AngArgs<T> a;
         a.posw = posw; a.n_rows = n_rows; a.n_atoms = n_atoms; a.n_centres = n_centres; a.offsets = offsets; a.idx = idx;
         a.cap = cap; a.nf = p->nf; a.G = G; a.dG = dG; a.w = w; a.force = force; a.flag = flag;
+        a.pw = (const T *)g.d_pw; a.ns = p->n_species;
         int r = launch_angular<T, MODE>(g, a, st);
         if (r) return r;
     }
@@ -948,11 +980,16 @@ using namespace nnmd;
 // =============================================================================================
 // C ABI
 // =============================================================================================
-extern "C" int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, const double *params, nnmd_sf_plan **out) {
+// weights == NULL: single-species plan (the reference's semantics).  Otherwise n_species > 0 and weights holds, per
+// function, an n_species x n_species block: radial functions read its first row as the neighbour weights wr[s_j];
+// angular functions read all of it as the symmetric pair weights pw[s_j][s_k].
+static int plan_create(int dtype, int nf, const int32_t *kinds, const double *params, int n_species, const double *weights,
+                       nnmd_sf_plan **out) {
     if (!out) return set_err(NNMD_ERR_INVALID, "plan: null output");
     *out = nullptr;
     if (dtype != NNMD_F32 && dtype != NNMD_F64) return set_err(NNMD_ERR_INVALID, "plan: bad dtype %d", dtype);
     if (nf <= 0 || !kinds || !params) return set_err(NNMD_ERR_INVALID, "plan: empty symmetry-function table");
+    if (weights && (n_species < 1 || n_species > 64)) return set_err(NNMD_ERR_INVALID, "plan: 1..64 species supported");
     for (int f = 0; f < nf; ++f) {
         const int k = kinds[f];
         if (k != NNMD_G1 && k != NNMD_G2 && k != NNMD_G4 && k != NNMD_G5)
@@ -962,37 +999,57 @@ extern "C" int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, cons
     nnmd_sf_plan *p = new (std::nothrow) nnmd_sf_plan();
     if (!p) return set_err(NNMD_ERR_INVALID, "plan: out of host memory");
     p->dtype = dtype; p->nf = nf; p->rc_max = 0;
-    std::vector<double> rrc, reta, rrs;
-    std::vector<int> rcol;
-    std::map<std::tuple<int, double, double>, std::vector<int>> groups;
-    std::vector<std::tuple<int, double, double>> order;  // first-appearance order keeps launches deterministic
+    p->n_species = weights ? n_species : 0;
+    const int S2 = weights ? n_species * n_species : 0;
+    using WKey = std::vector<double>;
+    auto wkey = [&](int f, int len) { return weights ? WKey(weights + size_t(f) * S2, weights + size_t(f) * S2 + len) : WKey(); };
+    struct RadBuild { std::vector<double> rc, eta, rs; std::vector<int> col; double rc_max = 0; };
+    std::map<WKey, RadBuild> rads;
+    std::vector<WKey> rad_order;
+    std::map<std::tuple<int, double, double, WKey>, std::vector<int>> groups;
+    std::vector<std::tuple<int, double, double, WKey>> order;  // first-appearance order keeps launches deterministic
     for (int f = 0; f < nf; ++f) {
         p->rc_max = std::max(p->rc_max, params[4 * f]);
         if (kinds[f] == NNMD_G1 || kinds[f] == NNMD_G2) {
-            rrc.push_back(params[4 * f]);
-            reta.push_back(kinds[f] == NNMD_G2 ? params[4 * f + 1] : 0.0);
-            rrs.push_back(kinds[f] == NNMD_G2 ? params[4 * f + 2] : 0.0);
-            rcol.push_back(f);
-            p->rad.rc_max = std::max(p->rad.rc_max, params[4 * f]);
+            const WKey k = wkey(f, weights ? n_species : 0);
+            if (!rads.count(k)) rad_order.push_back(k);
+            RadBuild &b = rads[k];
+            b.rc.push_back(params[4 * f]);
+            b.eta.push_back(kinds[f] == NNMD_G2 ? params[4 * f + 1] : 0.0);
+            b.rs.push_back(kinds[f] == NNMD_G2 ? params[4 * f + 2] : 0.0);
+            b.col.push_back(f);
+            b.rc_max = std::max(b.rc_max, params[4 * f]);
         } else {
-            auto key = std::make_tuple(int(kinds[f]), params[4 * f], params[4 * f + 1]);
+            auto key = std::make_tuple(int(kinds[f]), params[4 * f], params[4 * f + 1], wkey(f, S2));
             if (!groups.count(key)) order.push_back(key);
             groups[key].push_back(f);
         }
     }
-    p->rad.n = int(rcol.size());
-    p->rad.uniform_rc = 1;
-    for (double v : rrc) if (v != p->rad.rc_max) p->rad.uniform_rc = 0;
     int r = NNMD_OK;
-    if (p->rad.n > 0) {
-        if (!r) r = upload_real(dtype, rrc, &p->rad.d_rc);
-        if (!r) r = upload_real(dtype, reta, &p->rad.d_eta);
-        if (!r) r = upload_real(dtype, rrs, &p->rad.d_rs);
-        if (!r) r = upload_int(rcol, &p->rad.d_col);
+    for (const WKey &k : rad_order) {
+        if (r) break;
+        const RadBuild &b = rads[k];
+        RadialTab t;
+        t.n = int(b.col.size());
+        t.rc_max = b.rc_max;
+        t.uniform_rc = 1;
+        for (double v : b.rc) if (v != b.rc_max) t.uniform_rc = 0;
+        if (!r) r = upload_real(dtype, b.rc, &t.d_rc);
+        if (!r) r = upload_real(dtype, b.eta, &t.d_eta);
+        if (!r) r = upload_real(dtype, b.rs, &t.d_rs);
+        if (!r) r = upload_int(b.col, &t.d_col);
+        if (!r && weights) r = upload_real(dtype, k, &t.d_wr);
+        if (weights) p->ms_rads.push_back(t); else p->rad = t;
     }
     for (auto &key : order) {
         if (r) break;
+        const size_t first = p->groups.size();
         r = build_group(dtype, std::get<0>(key), std::get<1>(key), std::get<2>(key), groups[key], params, p->groups);
+        if (!r && weights)
+            for (size_t gi = first; gi < p->groups.size() && !r; ++gi) {
+                p->groups[gi].edge_path = 0;  // the edge-centric kernel relies on every atom weighting a triangle alike
+                r = upload_real(dtype, std::get<3>(key), &p->groups[gi].d_pw);
+            }
     }
     if (r) { nnmd_sf_plan_destroy(p); return r; }
     for (AngGroup &g : p->groups)
@@ -1001,10 +1058,47 @@ extern "C" int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, cons
     return NNMD_OK;
 }
 
+extern "C" int nnmd_sf_plan_create(int dtype, int nf, const int32_t *kinds, const double *params, nnmd_sf_plan **out) {
+    return plan_create(dtype, nf, kinds, params, 0, nullptr, out);
+}
+
+extern "C" int nnmd_sf_plan_create_species(int dtype, int nf, const int32_t *kinds, const double *params, int n_species,
+                                           const double *weights, nnmd_sf_plan **out) {
+    if (!weights) return set_err(NNMD_ERR_INVALID, "plan: null species weights");
+    for (int f = 0; f < nf && kinds; ++f)
+        if (kinds[f] == NNMD_G4 || kinds[f] == NNMD_G5)
+            for (int a = 0; a < n_species; ++a)
+                for (int b = 0; b < a; ++b)
+                    if (weights[(size_t(f) * n_species + a) * n_species + b] != weights[(size_t(f) * n_species + b) * n_species + a])
+                        return set_err(NNMD_ERR_INVALID, "plan: the pair weights of angular function %d are not symmetric", f);
+    return plan_create(dtype, nf, kinds, params, n_species, weights, out);
+}
+
+template <typename T>
+__global__ void set_species_kernel(T *__restrict__ posw, const int32_t *__restrict__ species, int64_t n_total, int64_t n_atoms) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < n_total) posw[4 * i + 3] = T(species[i % n_atoms]);
+}
+
+extern "C" int nnmd_set_species(int dtype, void *posw, const int32_t *species, int64_t n_frames, int64_t n_atoms, void *stream) {
+    if (dtype != NNMD_F32 && dtype != NNMD_F64) return set_err(NNMD_ERR_INVALID, "set_species: bad dtype %d", dtype);
+    if (n_frames < 0 || n_atoms < 0) return set_err(NNMD_ERR_INVALID, "set_species: bad sizes");
+    const int64_t n_total = n_frames * n_atoms;
+    if (n_total == 0) return NNMD_OK;
+    if (!posw || !species) return set_err(NNMD_ERR_INVALID, "set_species: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = unsigned((n_total + 255) / 256);
+    if (dtype == NNMD_F32) set_species_kernel<float><<<blocks, 256, 0, st>>>((float *)posw, species, n_total, n_atoms);
+    else set_species_kernel<double><<<blocks, 256, 0, st>>>((double *)posw, species, n_total, n_atoms);
+    NNMD_LAUNCH_CHECK("set_species_kernel");
+    return NNMD_OK;
+}
+
 extern "C" void nnmd_sf_plan_destroy(nnmd_sf_plan *p) {
     if (!p) return;
     cudaFree(p->rad.d_rc); cudaFree(p->rad.d_eta); cudaFree(p->rad.d_rs); cudaFree(p->rad.d_col);
-    for (AngGroup &g : p->groups) { cudaFree(g.d_zeta); cudaFree(g.d_lam); cudaFree(g.d_coef); cudaFree(g.d_col); }
+    for (nnmd::RadialTab &t : p->ms_rads) { cudaFree(t.d_rc); cudaFree(t.d_eta); cudaFree(t.d_rs); cudaFree(t.d_col); cudaFree(t.d_wr); }
+    for (AngGroup &g : p->groups) { cudaFree(g.d_zeta); cudaFree(g.d_lam); cudaFree(g.d_coef); cudaFree(g.d_col); cudaFree(g.d_pw); }
     delete p;
 }
 

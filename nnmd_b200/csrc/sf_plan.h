@@ -32,6 +32,8 @@ struct AngGroup {
     void *d_zeta = nullptr, *d_lam = nullptr, *d_coef = nullptr;
     int *d_col = nullptr;
     std::vector<int> cols;  // host copy (tests / debugging)
+    // multi-species plans: symmetric pair-weight table pw[s_j * n_species + s_k] of this group (working dtype), else NULL
+    void *d_pw = nullptr;
 };
 
 struct RadialTab {
@@ -40,6 +42,7 @@ struct RadialTab {
     double rc_max = 0;
     void *d_rc = nullptr, *d_eta = nullptr, *d_rs = nullptr;  // working dtype; G1 rows carry eta = 0, rs = 0
     int *d_col = nullptr;
+    void *d_wr = nullptr;  // multi-species plans: neighbour-species weight vector wr[s_j] of this group (working dtype), else NULL
 };
 
 }  // namespace nnmd
@@ -49,6 +52,8 @@ struct nnmd_sf_plan {
     int nf;
     double rc_max;
     nnmd::RadialTab rad;
+    std::vector<nnmd::RadialTab> ms_rads;  // multi-species plans: one radial launch per distinct neighbour-weight vector
+    int n_species = 0;                     // > 0: multi-species plan (posw.w carries the species index of every atom)
     std::vector<nnmd::AngGroup> groups;
     int edge_slots = 0;  // function-axis length of the edge scratch (sum of n_slots over edge-path groups)
 };

@@ -113,3 +113,28 @@ def energy_forces(cart: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, sym
         raise_on_flag(flag)
     e_atoms = e.view(B, nc)
     return EvalResult(e_atoms.sum(dim=1), e_atoms, f.view(B, nc, 3), g.view(B, nc, plan.nf), nl, flag)
+
+
+def energy_forces_species(cartesians: dict, cell: torch.Tensor, pbc: torch.Tensor, symm_funcs_data: dict, nets: dict,
+                          mlp_precision: str = "auto", check: bool = True):
+    """Multi-species evaluation with CROSS-species neighbours (extension; see features/multispecies.py):
+    {species: (B, N_s, 3)} and one atomic network per species -> (energy (B,), {species: per-atom energies (B, N_s)},
+    {species: forces (B, N_s, 3)}), atoms of each species in the caller's order.  The force is the reference's local
+    contraction with the network of the atom's own species."""
+    from .features.multispecies import raw_descriptors_species
+    species, counts, plan, nl, G, dG, flag = raw_descriptors_species(cartesians, cell, pbc, symm_funcs_data)
+    g = normalize(G, flag, out=G)
+    B, N, F = nl.n_frames, nl.n_atoms, plan.nf
+    g3, dG4 = g.view(B, N, F), dG.view(B, N, F, 3)
+    e_at, forces, off = {}, {}, 0
+    energy = torch.zeros(B, dtype=g.dtype, device=g.device)
+    for s, n in zip(species, counts):       # rows are type-sorted: one contiguous block of atoms per species
+        gs = g3[:, off:off + n].contiguous()
+        e, dE = nets[s].energy_and_grad(gs, need_grad=True, precision=mlp_precision)
+        forces[s] = force_contract(dE, dG4[:, off:off + n].contiguous()).view(B, n, 3)
+        e_at[s] = e.view(B, n)
+        energy = energy + e_at[s].sum(dim=1)
+        off += n
+    if check:
+        raise_on_flag(flag)
+    return energy, e_at, forces

@@ -11,6 +11,7 @@ from .symm_funcs import (
 from .calculate_sf import calculate_sf
 from .auto_params import calculate_params
 from .autograd import symmetry_functions
+from .multispecies import calculate_sf_species
 
 __all__ = [
     "calculate_sf",
@@ -23,4 +24,5 @@ __all__ = [
     "g5_function",
     "calculate_distances",
     "symmetry_functions",
+    "calculate_sf_species",
 ]
