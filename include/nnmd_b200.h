@@ -213,6 +213,15 @@ int nnmd_mlp_energy_grad(int dtype, int precision, int n_layers, const int32_t *
                          const void *const *biases, const void *x, int64_t n_rows, void *e, void *dEdx,
                          void *stream);
 
+/* K5 + K6 + K4c in ONE pass (fp32, tensor cores with 3xTF32, two hidden layers <= 96-64-64): reads the UN-normalised G and
+ * dG once, normalises per atom (calculate_sf.py:100-101; NNMD_FLAG_NAN_G on 0/0), runs the network forward and backward
+ * in registers and contracts dE/dg_hat with dG into the force (bpnn.py:353) -- g_hat, dE/dg_hat never travel through HBM.
+ *   ghat dev (n_rows, F) or NULL: normalised descriptors out (may alias G);  dEdx dev (n_rows, F) or NULL
+ *   returns NNMD_ERR_CAPACITY when the shape has no instantiation: use nnmd_sf_normalize + nnmd_mlp_energy_grad + nnmd_force_contract */
+int nnmd_energy_force_fused(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases,
+                            const void *G, const void *dG, int64_t n_rows, void *ghat, void *e, void *dEdx, void *force,
+                            uint32_t *flag, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * K7  training backward of the atomic MLP: gradients of a loss L(e, w = dE/dx) w.r.t. weights and biases, i.e. the
  *     double backward torch.autograd performs for bpnn.py:342-366 (energy term through e, force term through dE/dg).

@@ -22,6 +22,12 @@ struct TcArgs {
     const float *x;
     int64_t n_rows;
     float *e, *dEdx;
+    // fused form (K5 + K6 + K4c in one pass): x holds the UN-normalised descriptors G; the kernel normalises them itself
+    // (calculate_sf.py:100-101), optionally writes g_hat back, and contracts dE/dg_hat with dG into the force (bpnn.py:353)
+    float *ghat;         // (n_rows, K0) normalised descriptors out, or NULL (may alias x)
+    const float *dG;     // (n_rows, K0, 3)
+    float *force;        // (n_rows, 3)
+    uint32_t *flag;      // NNMD_FLAG_NAN_G on 0/0
 };
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
@@ -64,8 +70,9 @@ __device__ __forceinline__ void fill_frags(float4 *dst, const float *W, int ld_n
     }
 }
 
-template <int K0T, int H1T, int H2T>
+template <int K0T, int H1T, int H2T, bool FUSED = false>
 __global__ void __launch_bounds__(256, 1) mlp_tc_kernel(TcArgs a) {
+    if (FUSED && a.flag != nullptr && (*a.flag & NNMD_FLAG_OVERFLOW)) return;  // incomplete neighbour list: G / dG are not valid
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *f_fwd0 = reinterpret_cast<float4 *>(smem_raw);   // x  (K0) -> z1 (H1):  k = input feature, n = neuron of layer 0
     float4 *f_fwd1 = f_fwd0 + K0T * H1T * 32;                 // h1 (H1) -> z2 (H2)
@@ -85,9 +92,18 @@ __global__ void __launch_bounds__(256, 1) mlp_tc_kernel(TcArgs a) {
     const float b2 = __ldg(a.b2);
     const int lane = lane_id(), warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int64_t n_groups = (a.n_rows + 15) / 16;
+    bool bad = false;
     for (int64_t grp = int64_t(blockIdx.x) * 8 + warp; grp < n_groups; grp += int64_t(gridDim.x) * 8) {
         const int64_t r0 = grp * 16 + g, r1 = r0 + 8;
         const bool v0 = r0 < a.n_rows, v1 = r1 < a.n_rows;
+        if (FUSED) {
+            // the 16 rows of dG this warp contracts at the END of the pass (16 x K0 x 12 B, contiguous): ask L2 for them now
+            const char *base = reinterpret_cast<const char *>(a.dG + size_t(grp) * 16 * a.K0 * 3);
+            const int64_t rows_here = (a.n_rows - grp * 16) < 16 ? (a.n_rows - grp * 16) : 16;
+            const int64_t bytes = rows_here * a.K0 * 12;
+            for (int64_t o = int64_t(lane) * 128; o < bytes; o += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+        }
         // ---- x as A fragments
         float xa[K0T][4];
 #pragma unroll
@@ -97,6 +113,32 @@ __global__ void __launch_bounds__(256, 1) mlp_tc_kernel(TcArgs a) {
             xa[j][2] = (v0 && k + 1 < a.K0) ? __ldg(a.x + r0 * a.K0 + k + 1) : 0.f;
             xa[j][1] = (v1 && k < a.K0) ? __ldg(a.x + r1 * a.K0 + k) : 0.f;
             xa[j][3] = (v1 && k + 1 < a.K0) ? __ldg(a.x + r1 * a.K0 + k + 1) : 0.f;
+        }
+        if (FUSED) {
+            // K5: g_hat = G / ||G||_2 per atom; a row is spread over the four lanes of a quad
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < K0T; ++j) {
+                s0 = fmaf(xa[j][0], xa[j][0], fmaf(xa[j][2], xa[j][2], s0));
+                s1 = fmaf(xa[j][1], xa[j][1], fmaf(xa[j][3], xa[j][3], s1));
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            const float n0 = sqrtf(s0), n1 = sqrtf(s1);
+#pragma unroll
+            for (int j = 0; j < K0T; ++j) {
+                const int k = 8 * j + 2 * t;
+                // 0/0 -> NaN for an atom without neighbours, like calculate_sf.py:101 (padding columns stay 0)
+                xa[j][0] = (k < a.K0) ? xa[j][0] / n0 : 0.f;  xa[j][2] = (k + 1 < a.K0) ? xa[j][2] / n0 : 0.f;
+                xa[j][1] = (k < a.K0) ? xa[j][1] / n1 : 0.f;  xa[j][3] = (k + 1 < a.K0) ? xa[j][3] / n1 : 0.f;
+                bad |= (v0 && (xa[j][0] != xa[j][0] || xa[j][2] != xa[j][2])) || (v1 && (xa[j][1] != xa[j][1] || xa[j][3] != xa[j][3]));
+                if (a.ghat) {
+                    if (v0 && k < a.K0) a.ghat[r0 * a.K0 + k] = xa[j][0];
+                    if (v0 && k + 1 < a.K0) a.ghat[r0 * a.K0 + k + 1] = xa[j][2];
+                    if (v1 && k < a.K0) a.ghat[r1 * a.K0 + k] = xa[j][1];
+                    if (v1 && k + 1 < a.K0) a.ghat[r1 * a.K0 + k + 1] = xa[j][3];
+                }
+            }
         }
         // ---- layer 0
         float h1[H1T][4];
@@ -133,7 +175,7 @@ __global__ void __launch_bounds__(256, 1) mlp_tc_kernel(TcArgs a) {
             if (v0) a.e[r0] = e0 + b2;
             if (v1) a.e[r1] = e1 + b2;
         }
-        if (a.dEdx) {
+        if (FUSED || a.dEdx) {
             // ---- g1 = d2 W1, d1 = g1 * h1 (1 - h1)
             float d1[H1T][4];
 #pragma unroll
@@ -151,23 +193,76 @@ __global__ void __launch_bounds__(256, 1) mlp_tc_kernel(TcArgs a) {
 #pragma unroll
             for (int i = 0; i < K0T; ++i) gx[i][0] = gx[i][1] = gx[i][2] = gx[i][3] = 0.f;
             gemm3x<H1T, K0T>(gx, d1, f_bwd0, lane);
+            if (a.dEdx) {
 #pragma unroll
-            for (int i = 0; i < K0T; ++i) {
-                const int k = 8 * i + 2 * t;
-                if (v0 && k < a.K0) a.dEdx[r0 * a.K0 + k] = gx[i][0];
-                if (v0 && k + 1 < a.K0) a.dEdx[r0 * a.K0 + k + 1] = gx[i][1];
-                if (v1 && k < a.K0) a.dEdx[r1 * a.K0 + k] = gx[i][2];
-                if (v1 && k + 1 < a.K0) a.dEdx[r1 * a.K0 + k + 1] = gx[i][3];
+                for (int i = 0; i < K0T; ++i) {
+                    const int k = 8 * i + 2 * t;
+                    if (v0 && k < a.K0) a.dEdx[r0 * a.K0 + k] = gx[i][0];
+                    if (v0 && k + 1 < a.K0) a.dEdx[r0 * a.K0 + k + 1] = gx[i][1];
+                    if (v1 && k < a.K0) a.dEdx[r1 * a.K0 + k] = gx[i][2];
+                    if (v1 && k + 1 < a.K0) a.dEdx[r1 * a.K0 + k + 1] = gx[i][3];
+                }
+            }
+            if (FUSED) {
+                // K4c: F[a,:] = - sum_f dE/dg_hat[a,f] dG[a,f,:].  A lane holds two adjacent functions of rows r0 and r1:
+                // their six gradient components are 24 contiguous bytes of dG.
+                float f0[3] = {0.f, 0.f, 0.f}, f1[3] = {0.f, 0.f, 0.f};
+                const bool pairs_ok = (a.K0 & 1) == 0;  // rows of an even number of functions keep the 8 B alignment of a pair
+#pragma unroll
+                for (int i = 0; i < K0T; ++i) {
+                    const int k = 8 * i + 2 * t;
+                    if (pairs_ok && k + 1 < a.K0) {
+                        if (v0) {
+                            const float2 *p = reinterpret_cast<const float2 *>(a.dG + (r0 * a.K0 + k) * 3);
+                            const float2 q0 = __ldcs(p), q1 = __ldcs(p + 1), q2 = __ldcs(p + 2);   // (x y) (z | x) (y z)
+                            f0[0] = fmaf(gx[i][0], q0.x, fmaf(gx[i][1], q1.y, f0[0]));
+                            f0[1] = fmaf(gx[i][0], q0.y, fmaf(gx[i][1], q2.x, f0[1]));
+                            f0[2] = fmaf(gx[i][0], q1.x, fmaf(gx[i][1], q2.y, f0[2]));
+                        }
+                        if (v1) {
+                            const float2 *p = reinterpret_cast<const float2 *>(a.dG + (r1 * a.K0 + k) * 3);
+                            const float2 q0 = __ldcs(p), q1 = __ldcs(p + 1), q2 = __ldcs(p + 2);
+                            f1[0] = fmaf(gx[i][2], q0.x, fmaf(gx[i][3], q1.y, f1[0]));
+                            f1[1] = fmaf(gx[i][2], q0.y, fmaf(gx[i][3], q2.x, f1[1]));
+                            f1[2] = fmaf(gx[i][2], q1.x, fmaf(gx[i][3], q2.y, f1[2]));
+                        }
+                    } else {  // odd number of functions: scalar loads
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            if (k + q >= a.K0) continue;
+                            if (v0) {
+                                const float *p = a.dG + (r0 * a.K0 + k + q) * 3;
+                                const float w = gx[i][q];
+                                f0[0] = fmaf(w, __ldg(p), f0[0]); f0[1] = fmaf(w, __ldg(p + 1), f0[1]); f0[2] = fmaf(w, __ldg(p + 2), f0[2]);
+                            }
+                            if (v1) {
+                                const float *p = a.dG + (r1 * a.K0 + k + q) * 3;
+                                const float w = gx[i][2 + q];
+                                f1[0] = fmaf(w, __ldg(p), f1[0]); f1[1] = fmaf(w, __ldg(p + 1), f1[1]); f1[2] = fmaf(w, __ldg(p + 2), f1[2]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    f0[c] += __shfl_xor_sync(0xffffffffu, f0[c], 1); f0[c] += __shfl_xor_sync(0xffffffffu, f0[c], 2);
+                    f1[c] += __shfl_xor_sync(0xffffffffu, f1[c], 1); f1[c] += __shfl_xor_sync(0xffffffffu, f1[c], 2);
+                }
+                if (t == 0) {
+                    if (v0) { a.force[3 * r0] = -f0[0]; a.force[3 * r0 + 1] = -f0[1]; a.force[3 * r0 + 2] = -f0[2]; }
+                    if (v1) { a.force[3 * r1] = -f1[0]; a.force[3 * r1 + 1] = -f1[1]; a.force[3 * r1 + 2] = -f1[2]; }
+                }
             }
         }
     }
+    if (FUSED && bad && a.flag) atomicOr(a.flag, NNMD_FLAG_NAN_G);
 }
 
-template <int K0T, int H1T, int H2T>
+template <int K0T, int H1T, int H2T, bool FUSED = false>
 static int tc_launch(const TcArgs &a, cudaStream_t st) {
     const size_t smem = size_t(K0T * H1T + H1T * H2T + H2T * H1T + H1T * K0T) * 32 * sizeof(float4) + size_t(8 * H1T + 16 * H2T) * sizeof(float);
     if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "mlp(tf32): weights need %zu B of shared memory", smem);
-    auto kern = mlp_tc_kernel<K0T, H1T, H2T>;
+    auto kern = mlp_tc_kernel<K0T, H1T, H2T, FUSED>;
     NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int occ = 1;
     NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
@@ -189,6 +284,7 @@ int mlp_tf32_run(int n_layers, const int32_t *sizes, const void *const *weights,
     a.W2 = (const float *)weights[2]; a.b2 = (const float *)biases[2];
     a.K0 = sizes[0]; a.H1 = sizes[1]; a.H2 = sizes[2];
     a.x = (const float *)x; a.n_rows = n_rows; a.e = (float *)e; a.dEdx = (float *)dEdx;
+    a.ghat = nullptr; a.dG = nullptr; a.force = nullptr; a.flag = nullptr;
     const int k0t = (a.K0 + 7) / 8, h1t = (a.H1 + 7) / 8, h2t = (a.H2 + 7) / 8;
     if (k0t <= 2 && h1t <= 4 && h2t <= 4) return tc_launch<2, 4, 4>(a, st);     // e.g. LJ 3-25-25-1
     if (k0t <= 2 && h1t <= 8 && h2t <= 8) return tc_launch<2, 8, 8>(a, st);     // e.g. Li 14-64-64-1
@@ -197,4 +293,37 @@ int mlp_tf32_run(int n_layers, const int32_t *sizes, const void *const *weights,
     return set_err(NNMD_ERR_CAPACITY, "mlp(tf32): shape %d-%d-%d-1 has no tensor-core instantiation", a.K0, a.H1, a.H2);
 }
 
+// K5 + K6 + K4c in one pass over G / dG.  Returns a negative value when the shape has no tensor-core instantiation.
+int energy_force_fused_run(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases,
+                           const void *G, const void *dG, int64_t n_rows, void *ghat, void *e, void *dEdx, void *force,
+                           uint32_t *flag, cudaStream_t st) {
+    if (n_layers != 3) return -1;
+    TcArgs a;
+    a.W0 = (const float *)weights[0]; a.b0 = (const float *)biases[0];
+    a.W1 = (const float *)weights[1]; a.b1 = (const float *)biases[1];
+    a.W2 = (const float *)weights[2]; a.b2 = (const float *)biases[2];
+    a.K0 = sizes[0]; a.H1 = sizes[1]; a.H2 = sizes[2];
+    a.x = (const float *)G; a.n_rows = n_rows; a.e = (float *)e; a.dEdx = (float *)dEdx;
+    a.ghat = (float *)ghat; a.dG = (const float *)dG; a.force = (float *)force; a.flag = flag;
+    const int k0t = (a.K0 + 7) / 8, h1t = (a.H1 + 7) / 8, h2t = (a.H2 + 7) / 8;
+    if (k0t <= 2 && h1t <= 8 && h2t <= 8) return tc_launch<2, 8, 8, true>(a, st);
+    if (k0t <= 7 && h1t <= 8 && h2t <= 8) return tc_launch<7, 8, 8, true>(a, st);
+    if (k0t <= 12 && h1t <= 8 && h2t <= 8) return tc_launch<12, 8, 8, true>(a, st);
+    return -1;
+}
+
 }  // namespace nnmd
+
+extern "C" int nnmd_energy_force_fused(int n_layers, const int32_t *sizes, const void *const *weights, const void *const *biases,
+                                       const void *G, const void *dG, int64_t n_rows, void *ghat, void *e, void *dEdx, void *force,
+                                       uint32_t *flag, void *stream) {
+    using namespace nnmd;
+    if (n_layers != 3 || !sizes) return set_err(NNMD_ERR_CAPACITY, "fused energy+force: two hidden layers only");
+    if (sizes[3] != 1) return set_err(NNMD_ERR_INVALID, "fused energy+force: the atomic network has a single output");
+    if (n_rows < 0) return set_err(NNMD_ERR_INVALID, "fused energy+force: negative row count");
+    if (n_rows == 0) return NNMD_OK;
+    if (!weights || !biases || !G || !dG || !e || !force || !flag) return set_err(NNMD_ERR_INVALID, "fused energy+force: null pointer");
+    const int r = energy_force_fused_run(n_layers, sizes, weights, biases, G, dG, n_rows, ghat, e, dEdx, force, flag, (cudaStream_t)stream);
+    if (r < 0) return set_err(NNMD_ERR_CAPACITY, "fused energy+force: shape %d-%d-%d-1 has no tensor-core instantiation", sizes[0], sizes[1], sizes[2]);
+    return r;
+}

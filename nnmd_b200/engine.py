@@ -103,12 +103,17 @@ def energy_forces(cart: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, sym
         G, dG, flag = raw_descriptors(plan, nl, with_grad=False, workspace=workspace)
     else:
         raise ValueError(f"unknown mode {mode!r}")
-    g = normalize(G, flag, out=G)
-    e, dE = net.energy_and_grad(g, need_grad=True, precision=mlp_precision)
-    if mode == "materialize":
-        f = force_contract(dE, dG)
+    if mode == "materialize" and mlp_precision in ("auto", "tf32") and net.fused_shape(G.dtype):
+        # K5 + K6 + K4c in ONE pass over G / dG: g_hat and dE/dg_hat never travel through HBM
+        e, f = net.energy_force_fused(G, dG, flag, out_g=G)
+        g = G
     else:
-        f = fused_force(plan, nl, dE, workspace=workspace)
+        g = normalize(G, flag, out=G)
+        e, dE = net.energy_and_grad(g, need_grad=True, precision=mlp_precision)
+        if mode == "materialize":
+            f = force_contract(dE, dG)
+        else:
+            f = fused_force(plan, nl, dE, workspace=workspace)
     if check:
         raise_on_flag(flag)
     e_atoms = e.view(B, nc)

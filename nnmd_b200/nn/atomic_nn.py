@@ -59,6 +59,32 @@ class AtomicNN(nn.Module):
         s = self.layer_sizes()
         return len(s) == 4 and s[3] == 1 and s[0] <= 96 and s[1] <= 64 and s[2] <= 64
 
+    def fused_shape(self, dtype: torch.dtype) -> bool:
+        """True when csrc/mlp_tc.cu has a fused K5 + K6 + K4c instantiation for this network and precision."""
+        s = self.layer_sizes()
+        return dtype == torch.float32 and self.activation is torch.sigmoid and self.tensor_core_shape() and s[1] > 32
+
+    def energy_force_fused(self, G: torch.Tensor, dG: torch.Tensor, flag: torch.Tensor, out_g: torch.Tensor | None = None):
+        """K5 + K6 + K4c in one pass (csrc/mlp_tc.cu): un-normalised G (n_rows, F) and dG (n_rows, F, 3) in, per-atom energies
+        (n_rows,) and reference-semantic forces (n_rows, 3) out; the normalised descriptors go to `out_g` when given (may be
+        G itself), the NaN bit to `flag`.  fp32, tensor cores (3xTF32)."""
+        _lib.require_cuda()
+        lib = _lib.load()
+        sizes = self.layer_sizes()
+        ws = [m.weight.detach().to(device=G.device, dtype=torch.float32).contiguous() for m in self.model]
+        bs = [m.bias.detach().to(device=G.device, dtype=torch.float32).contiguous() for m in self.model]
+        L = len(ws)
+        n_rows = G.shape[0]
+        e = torch.empty(n_rows, dtype=torch.float32, device=G.device)
+        f = torch.empty((n_rows, 3), dtype=torch.float32, device=G.device)
+        c_sizes = (ctypes.c_int32 * (L + 1))(*sizes)
+        c_w = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+        c_b = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs])
+        with torch.cuda.device(G.device):
+            _lib.check(lib.nnmd_energy_force_fused(L, c_sizes, c_w, c_b, _lib.ptr(G), _lib.ptr(dG), n_rows, _lib.ptr(out_g), _lib.ptr(e),
+                                                   None, _lib.ptr(f), _lib.ptr(flag), _lib.stream_ptr()))
+        return e, f
+
     def energy_and_grad(self, x: torch.Tensor, need_grad: bool = True, precision: str = "auto"):
         """K6: per-atom energies e (..., 1) and dE/dx (..., F) for x (..., F) on the GPU; no autograd graph.
 

@@ -857,3 +857,41 @@ def test_warp_specialised_edge_kernel_is_bit_identical(with_grad):
                 assert torch.equal(out[0][1], out[1][1])
     finally:
         _lib.set_option("edge_ws", 0)
+
+
+@pytest.mark.parametrize("F,hidden,rows", [(96, [64, 64], 1003), (14, [64, 64], 77), (50, [40, 64], 333), (33, [64, 48], 16)])
+def test_fused_normalise_network_contract_kernel(F, hidden, rows):
+    """K5 + K6 + K4c in one pass (nnmd_energy_force_fused) against the three separate kernels and the fp64 truth: normalised
+    descriptors, per-atom energies (1e-5) and forces (1e-4 absolute, and 1e-5 of the largest force); the NaN bit for a row
+    of zeros (an atom without neighbours)."""
+    from nnmd_b200 import _lib
+    from nnmd_b200.engine import force_contract
+    from nnmd_b200.features.calculate_sf import normalize
+    from nnmd_b200.nn import AtomicNN
+    from oracle import dense_oracle as O2
+    torch.manual_seed(F + rows)
+    net = AtomicNN(F, hidden).to(DEV)
+    assert net.fused_shape(torch.float32)
+    G = torch.rand(rows, F, device=DEV) * 3.0
+    dG = torch.randn(rows, F, 3, device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ghat = torch.empty_like(G)
+    e, f = net.energy_force_fused(G, dG, flag, out_g=ghat)
+    assert int(flag.item()) == 0
+    g_ref = normalize(G.clone(), flag)
+    e_ref, dE_ref = net.energy_and_grad(g_ref, precision="exact")
+    f_ref = force_contract(dE_ref, dG)
+    assert relerr(ghat.cpu(), g_ref.cpu()) < 1e-6
+    Ws = [m.weight.detach().double().cpu() for m in net.model]
+    bs = [m.bias.detach().double().cpu() for m in net.model]
+    g64 = G.double().cpu() / G.double().cpu().norm(dim=1, keepdim=True)
+    e_o, _, f_o = O2.energy_force(g64, dG.double().cpu(), Ws, bs)
+    assert relerr(e.cpu(), e_o.reshape(-1)) < 1e-5 and relerr(e.cpu(), e_ref.reshape(-1).cpu()) < 1e-5
+    ferr = float((f.cpu().double() - f_o).abs().max())
+    assert ferr < 1e-4 and ferr < 1e-5 * float(f_o.abs().max()) + 1e-6, ferr
+    assert float((f - f_ref).abs().max()) < 1e-4
+    # in place (ghat aliases G) and the NaN guard
+    G2 = G.clone()
+    G2[5] = 0.0
+    net.energy_force_fused(G2, dG, flag, out_g=G2)
+    assert int(flag.item()) == _lib.FLAG_NAN_G and bool(torch.isnan(G2[5]).all()) and relerr(G2[6:].cpu(), g_ref[6:].cpu()) < 1e-6
