@@ -111,10 +111,14 @@ int nnmd_nlist_fill(int dtype, const void *posw, int64_t n_frames, int64_t n_ato
  * atom has moved more than skin / 2 from the positions of the last build (pos_ref, (n_total,4), updated when *go becomes 1;
  * fill it with NaN to force the first build).  acc: dev uint32 scratch, zero it once.  n_builds: dev int64 counter or NULL.
  * The K2..K4 kernels re-test every listed neighbour against the functions' own cutoff, so a skin list gives the SAME
- * descriptors as an exact one (replaces the O(N^2) Python loop of nnmd/md/verlet.py:97-218, which has no list at all). */
+ * descriptors as an exact one (replaces the O(N^2) Python loop of nnmd/md/verlet.py:97-218, which has no list at all).
+ *   row_scratch  dev, nnmd_nlist_row_scratch_bytes(n_rows, max_row_cap) bytes, or NULL.  With it the candidates are visited
+ *                ONCE: sorted rows go to padded scratch rows, then counts are scanned and the rows compacted into idx (the
+ *                separate count pass of the two-step build disappears). */
+int64_t nnmd_nlist_row_scratch_bytes(int64_t n_rows, int64_t max_row_cap);
 int nnmd_nlist_build(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc, void *ws,
                      int64_t *offsets, int64_t *edge_offsets, int32_t *idx, int64_t idx_cap, int64_t max_row_cap,
-                     int64_t edge_cap, int64_t *stats, uint32_t *flag, const int32_t *go, void *stream);
+                     int64_t edge_cap, void *row_scratch, int64_t *stats, uint32_t *flag, const int32_t *go, void *stream);
 int nnmd_skin_check(int dtype, const void *posw, void *pos_ref, int64_t n_total, double skin, uint32_t *acc, int32_t *go,
                     int64_t *n_builds, void *stream);
 

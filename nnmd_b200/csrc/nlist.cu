@@ -368,6 +368,54 @@ __device__ __forceinline__ void rank_sort_row(const int *__restrict__ buf, int n
     }
 }
 
+// Bitonic sort of a staged row of up to 32 * NR unique keys held NR per lane (key i lives in lane i & 31, register i >> 5):
+// exchanges across lanes are shuffles, exchanges across registers stay in the lane.  ~430 warp instructions for 128 keys
+// against ~700 for the rank sort above (measured on the 1M-atom cell: profiles/README.md, round 2).
+template <int NR>
+__device__ __forceinline__ void bitonic_sort_row(const int *__restrict__ buf, int n, int32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int v[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) v[r] = lane + 32 * r < n ? buf[lane + 32 * r] : 0x7fffffff;
+#pragma unroll
+    for (int k = 2; k <= 32 * NR; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {  // partner register r ^ (j / 32), same lane
+                const int dr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    if ((r & dr) == 0) {
+                        const bool asc = (((lane + 32 * r) & k) == 0);
+                        const int lo = min(v[r], v[r | dr]), hi = max(v[r], v[r | dr]);
+                        v[r] = asc ? lo : hi;
+                        v[r | dr] = asc ? hi : lo;
+                    }
+                }
+            } else {        // partner lane ^ j, same register
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const int p = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool asc = (((lane + 32 * r) & k) == 0);
+                    const bool keep_min = asc == ((lane & j) == 0);
+                    v[r] = keep_min ? min(v[r], p) : max(v[r], p);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+        if (lane + 32 * r < n) out[lane + 32 * r] = v[r];
+}
+
+// sorted copy of a staged row: bitonic network for rows that fit 128 keys, rank sort beyond
+__device__ __forceinline__ void sort_row(const int *__restrict__ buf, int n, int32_t *__restrict__ out) {
+    if (n <= 32) bitonic_sort_row<1>(buf, n, out);
+    else if (n <= 64) bitonic_sort_row<2>(buf, n, out);
+    else if (n <= 128) bitonic_sort_row<4>(buf, n, out);
+    else rank_sort_row(buf, n, out);
+}
+
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ posw, const T *__restrict__ spos,
                                                          int64_t n_rows, int64_t n_atoms, int64_t n_centres,
@@ -435,7 +483,7 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
             const int n = min(n_found, max_row);
             const int64_t o = offsets[row];
             // rank sort: indices inside a row are unique (no periodic images), so ranks are a permutation
-            if (o + n <= idx_cap) rank_sort_row(buf, n, idx + o);  // beyond the capacity: the overflow flag is raised elsewhere
+            if (o + n <= idx_cap) sort_row(buf, n, idx + o);  // beyond the capacity: the overflow flag is raised elsewhere
             __syncwarp();
         }
     }
@@ -458,7 +506,9 @@ template <> __device__ __forceinline__ void load_pos_smem<double>(const double *
     x = a.x; y = a.y; z = b.x;
 }
 
-template <typename T, bool FILL>
+// PASS 0: count (counts, ecounts, stats).  PASS 1: fill the CSR rows at offsets[row] (sorted).  PASS 2: both at once for
+// the capacity-bound build: the sorted row goes to a padded scratch row (idx + row * max_row), the count pass disappears.
+template <typename T, int PASS>
 __global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__restrict__ spos, int64_t n_frames, int64_t n_atoms,
                                                                      int64_t n_centres, int64_t cap, const GridHdr *__restrict__ h,
                                                                      const int *__restrict__ cell_start, const int *__restrict__ order,
@@ -467,6 +517,7 @@ __global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__
                                                                      int32_t *__restrict__ idx, unsigned long long *__restrict__ stats,
                                                                      int64_t idx_cap, const int32_t *go) {
     NNMD_GO_GUARD(go);
+    constexpr bool FILL = PASS != 0, COUNT = PASS != 1;
     extern __shared__ __align__(16) unsigned char cell_smem[];
     T *cpos = reinterpret_cast<T *>(cell_smem);                                  // CELL_MCAND x 4
     int *cidx = reinterpret_cast<int *>(cpos + 4 * CELL_MCAND);                  // CELL_MCAND global atom indices
@@ -531,9 +582,8 @@ __global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__
                             const int p = n_found + __popc(m & ((1u << lane) - 1u));
                             if (p < max_row) buf[p] = gj;
                         }
-                    } else {
-                        n_gt += __popc(__ballot_sync(0xffffffffu, ok && int64_t(gj) > gi));
                     }
+                    if (COUNT) n_gt += __popc(__ballot_sync(0xffffffffu, ok && int64_t(gj) > gi));
                     n_found += __popc(m);
                 }
             } else {
@@ -555,24 +605,24 @@ __global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__
                                 const int p = n_found + __popc(m & ((1u << lane) - 1u));
                                 if (p < max_row) buf[p] = gj;
                             }
-                        } else {
-                            n_gt += __popc(__ballot_sync(0xffffffffu, ok && int64_t(gj) > gi));
                         }
+                        if (COUNT) n_gt += __popc(__ballot_sync(0xffffffffu, ok && int64_t(gj) > gi));
                         n_found += __popc(m);
                     }
                 }
             }
-            if (!FILL) {
+            if (COUNT) {
                 if (lane == 0) {
                     counts[row] = n_found;
                     ecounts[row] = n_gt;
                     atomicMax(&stats[1], (unsigned long long)n_found);
                 }
-            } else {
+            }
+            if (FILL) {
                 __syncwarp();
                 const int n = min(n_found, max_row);
-                const int64_t o = offsets[row];
-                if (o + n <= idx_cap) rank_sort_row(buf, n, idx + o);  // unique indices -> ranks are a permutation
+                const int64_t o = PASS == 2 ? row * int64_t(max_row) : offsets[row];
+                if (o + n <= idx_cap) sort_row(buf, n, idx + o);  // unique indices: ascending row, fixed summation order downstream
                 __syncwarp();
             }
         }
@@ -580,14 +630,14 @@ __global__ void __launch_bounds__(CELL_WARPS * 32) nlist_cell_kernel(const T *__
     }
 }
 
-template <typename T, bool FILL>
+template <typename T, int PASS>
 static int launch_cell_kernel(const T *spos, int64_t n_frames, int64_t n_atoms, int64_t n_centres, int64_t cap, const GridHdr *h,
                               const int *cell_start, const int *order, T rc, int *counts, int *ecounts, const int64_t *offsets,
                               int max_row, int32_t *idx, unsigned long long *stats, cudaStream_t st,
                               int64_t idx_cap = INT64_MAX, const int32_t *go = nullptr) {
-    const size_t smem = size_t(CELL_MCAND) * (4 * sizeof(T) + sizeof(int)) + (FILL ? size_t(CELL_WARPS) * max_row * sizeof(int) : 0);
+    const size_t smem = size_t(CELL_MCAND) * (4 * sizeof(T) + sizeof(int)) + (PASS != 0 ? size_t(CELL_WARPS) * max_row * sizeof(int) : 0);
     if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "neighbour row of %d entries exceeds shared memory", max_row);
-    auto kern = nlist_cell_kernel<T, FILL>;
+    auto kern = nlist_cell_kernel<T, PASS>;
     NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int occ = 1;
     NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CELL_WARPS * 32, smem));
@@ -720,7 +770,7 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
     bin_fill_kernel<T><<<ablocks, 256, 0, st>>>(posw, n_total, n_atoms, L.cap, cell_of, cell_start, cursor, order, spos, go);
     NNMD_LAUNCH_CHECK("bin_fill_kernel");
     if (use_cell_kernel()) {
-        rcode = launch_cell_kernel<T, false>(spos, n_frames, n_atoms, n_centres, L.cap, h, cell_start, order, T(rc), counts,
+        rcode = launch_cell_kernel<T, 0>(spos, n_frames, n_atoms, n_centres, L.cap, h, cell_start, order, T(rc), counts,
                                              ecounts, nullptr, 0, nullptr, (unsigned long long *)stats, st, INT64_MAX, go);
         if (rcode) return rcode;
     } else {
@@ -744,6 +794,83 @@ static int nlist_count_impl(const T *posw, int64_t n_frames, int64_t n_atoms, in
     return NNMD_OK;
 }
 
+// padded scratch rows (row * stride) -> CSR rows at offsets[row]; one warp per row, coalesced
+__global__ void compact_rows_kernel(const int32_t *__restrict__ rows, int64_t n_rows, int stride, const int64_t *__restrict__ offsets,
+                                    int32_t *__restrict__ idx, int64_t idx_cap, const int32_t *go) {
+    NNMD_GO_GUARD(go);
+    const int lane = lane_id(), wpb = blockDim.x >> 5;
+    for (int64_t row = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); row < n_rows; row += int64_t(gridDim.x) * wpb) {
+        const int64_t o0 = offsets[row], o1 = offsets[row + 1];
+        if (o1 > idx_cap || o1 - o0 > stride) continue;  // overflow: flagged by stats_finish_kernel
+        const int32_t *src = rows + row * int64_t(stride);
+        for (int64_t t = lane; t < o1 - o0; t += 32) idx[o0 + t] = src[t];
+    }
+}
+
+// capacity-bound build in ONE pass over the candidates (cell-tiled kernel only): sorted rows into padded scratch, counts,
+// scans, compaction.  Saves the separate count pass of the two-step build (1.3 of 4.0 ms on the 1M-atom cell).
+template <typename T>
+static int nlist_single_pass_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc, char *ws,
+                                  int64_t *offsets, int64_t *edge_offsets, int32_t *idx, int64_t idx_cap, int64_t max_row_cap,
+                                  int64_t edge_cap, int32_t *row_scratch, int64_t *stats, uint32_t *flag, const int32_t *go,
+                                  cudaStream_t st) {
+    const WsLayout L = ws_layout(n_frames, n_atoms, n_centres);
+    const int64_t n_total = n_frames * n_atoms, n_rows = n_frames * n_centres;
+    GridHdr *h = (GridHdr *)ws;
+    int *cell_start = (int *)(ws + L.off_cell_start);
+    int *cursor = (int *)(ws + L.off_cursor);
+    int *cell_of = (int *)(ws + L.off_cell_of);
+    int *order = (int *)(ws + L.off_order);
+    T *spos = (T *)(ws + L.off_spos);
+    int *counts = (int *)(ws + L.off_counts);
+    int *ecounts = (int *)(ws + L.off_ecounts);
+    long long *scratch = (long long *)(ws + L.off_scan);
+    const int sms = sm_count();
+    clear_i64_kernel<<<1, 32, 0, st>>>(stats, 3, go);
+    NNMD_LAUNCH_CHECK("clear_i64_kernel");
+    ProfScope prof(PROF_NLIST, st);
+    hdr_init_kernel<<<1, 32, 0, st>>>(h, go);
+    NNMD_LAUNCH_CHECK("hdr_init_kernel");
+    {
+        int64_t blocks = (n_total + 255) / 256;
+        if (blocks > int64_t(sms) * 8) blocks = int64_t(sms) * 8;
+        bbox_kernel<T><<<unsigned(blocks), 256, 0, st>>>(posw, n_total, h, go);
+        NNMD_LAUNCH_CHECK("bbox_kernel");
+    }
+    grid_setup_kernel<<<1, 32, 0, st>>>(h, rc, (long long)L.cap, go);
+    NNMD_LAUNCH_CHECK("grid_setup_kernel");
+    const unsigned cblocks = unsigned(std::min<int64_t>((L.ncells_total + 1 + 255) / 256, int64_t(sms) * 8));
+    clear_i32_kernel<<<cblocks, 256, 0, st>>>(cursor, L.ncells_total + 1, go);
+    NNMD_LAUNCH_CHECK("clear_i32_kernel");
+    const unsigned ablocks = unsigned((n_total + 255) / 256);
+    bin_count_kernel<T><<<ablocks, 256, 0, st>>>(posw, n_total, n_atoms, L.cap, h, cell_of, cursor, go);
+    NNMD_LAUNCH_CHECK("bin_count_kernel");
+    int rcode = exclusive_scan<int>(cursor, L.ncells_total, cell_start, scratch, st, go);
+    if (rcode) return rcode;
+    clear_i32_kernel<<<cblocks, 256, 0, st>>>(cursor, L.ncells_total + 1, go);
+    NNMD_LAUNCH_CHECK("clear_i32_kernel");
+    bin_fill_kernel<T><<<ablocks, 256, 0, st>>>(posw, n_total, n_atoms, L.cap, cell_of, cell_start, cursor, order, spos, go);
+    NNMD_LAUNCH_CHECK("bin_fill_kernel");
+    rcode = launch_cell_kernel<T, 2>(spos, n_frames, n_atoms, n_centres, L.cap, h, cell_start, order, T(rc), counts, ecounts, nullptr,
+                                     int(max_row_cap), row_scratch, (unsigned long long *)stats, st, n_rows * max_row_cap, go);
+    if (rcode) return rcode;
+    rcode = exclusive_scan<int64_t>(counts, n_rows, offsets, scratch, st, go);
+    if (rcode) return rcode;
+    if (edge_offsets) {
+        rcode = exclusive_scan<int64_t>(ecounts, n_rows, edge_offsets, scratch, st, go);
+        if (rcode) return rcode;
+    }
+    stats_finish_kernel<<<1, 32, 0, st>>>(stats, offsets, edge_offsets, n_rows, idx_cap, max_row_cap, edge_cap, flag, flag ? 1 : 0, go);
+    NNMD_LAUNCH_CHECK("stats_finish_kernel");
+    {
+        const int wpb = 8;
+        const int64_t blocks = std::min<int64_t>((n_rows + wpb - 1) / wpb, int64_t(sms) * 16);
+        compact_rows_kernel<<<unsigned(blocks), wpb * 32, 0, st>>>(row_scratch, n_rows, int(max_row_cap), offsets, idx, idx_cap, go);
+        NNMD_LAUNCH_CHECK("compact_rows_kernel");
+    }
+    return NNMD_OK;
+}
+
 template <typename T>
 static int nlist_fill_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
                            const char *ws, const int64_t *offsets, int64_t max_row, int32_t *idx, cudaStream_t st,
@@ -758,7 +885,7 @@ static int nlist_fill_impl(const T *posw, int64_t n_frames, int64_t n_atoms, int
     const T *spos = (const T *)(ws + L.off_spos);
     if (use_cell_kernel()) {
         ProfScope prof(PROF_NLIST, st);
-        return launch_cell_kernel<T, true>(spos, n_frames, n_atoms, n_centres, L.cap, h, cell_start, order, T(rc), nullptr, nullptr,
+        return launch_cell_kernel<T, 1>(spos, n_frames, n_atoms, n_centres, L.cap, h, cell_start, order, T(rc), nullptr, nullptr,
                                            offsets, int(max_row), idx, nullptr, st, idx_cap, go);
     }
     int wpb = 8;
@@ -843,13 +970,21 @@ extern "C" int nnmd_nlist_fill(int dtype, const void *posw, int64_t n_frames, in
 
 extern "C" int nnmd_nlist_build(int dtype, const void *posw, int64_t n_frames, int64_t n_atoms, int64_t n_centres, double rc,
                                 void *ws, int64_t *offsets, int64_t *edge_offsets, int32_t *idx, int64_t idx_cap,
-                                int64_t max_row_cap, int64_t edge_cap, int64_t *stats, uint32_t *flag, const int32_t *go,
-                                void *stream) {
+                                int64_t max_row_cap, int64_t edge_cap, void *row_scratch, int64_t *stats, uint32_t *flag,
+                                const int32_t *go, void *stream) {
     int r = nlist_args_ok(dtype, posw, n_frames, n_atoms, n_centres, rc, ws);
     if (r) return r;
     if (!offsets || !stats || !flag || (idx_cap > 0 && !idx)) return set_err(NNMD_ERR_INVALID, "nlist_build: null pointer");
     if (idx_cap < 0 || max_row_cap < 1 || edge_cap < 0) return set_err(NNMD_ERR_INVALID, "nlist_build: bad capacities");
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t cell_smem = size_t(CELL_MCAND) * ((dtype == NNMD_F32 ? 16 : 32) + sizeof(int)) + size_t(CELL_WARPS) * max_row_cap * sizeof(int);
+    if (row_scratch && use_cell_kernel() && n_frames * n_centres > 0 && n_frames * n_atoms > 0 && cell_smem <= 220 * 1024) {
+        if (dtype == NNMD_F32)
+            return nlist_single_pass_impl<float>((const float *)posw, n_frames, n_atoms, n_centres, rc, (char *)ws, offsets, edge_offsets, idx,
+                                                 idx_cap, max_row_cap, edge_cap, (int32_t *)row_scratch, stats, flag, go, st);
+        return nlist_single_pass_impl<double>((const double *)posw, n_frames, n_atoms, n_centres, rc, (char *)ws, offsets, edge_offsets, idx,
+                                              idx_cap, max_row_cap, edge_cap, (int32_t *)row_scratch, stats, flag, go, st);
+    }
     if (dtype == NNMD_F32) {
         r = nlist_count_impl<float>((const float *)posw, n_frames, n_atoms, n_centres, rc, (char *)ws, offsets, edge_offsets, stats, st,
                                     idx_cap, max_row_cap, edge_cap, flag, go);
@@ -860,6 +995,11 @@ extern "C" int nnmd_nlist_build(int dtype, const void *posw, int64_t n_frames, i
                                  idx_cap, max_row_cap, edge_cap, flag, go);
     if (r) return r;
     return nlist_fill_impl<double>((const double *)posw, n_frames, n_atoms, n_centres, rc, (const char *)ws, offsets, max_row_cap, idx, st, idx_cap, go);
+}
+
+extern "C" int64_t nnmd_nlist_row_scratch_bytes(int64_t n_rows, int64_t max_row_cap) {
+    if (n_rows < 0 || max_row_cap < 0) return -1;
+    return n_rows * max_row_cap * int64_t(sizeof(int32_t));
 }
 
 extern "C" int nnmd_skin_check(int dtype, const void *posw, void *pos_ref, int64_t n_total, double skin, uint32_t *acc,

@@ -161,13 +161,18 @@ class NeighborWorkspace:
         self.max_row_cap = (max(max_row + max(4, (max_row + 9) // 10), 8) + 3) & ~3
         self.edge_cap = max(int(n_edges * m) + 512, 1)
         self.idx = torch.empty(self.idx_cap, dtype=torch.int32, device=self.device)
+        n_rows = self.n_frames * self.n_centres
+        nbytes = int(self.lib.nnmd_nlist_row_scratch_bytes(n_rows, self.max_row_cap))
+        # padded scratch rows of the single-pass build (skipped when it would be unreasonably large: many short frames)
+        self.row_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device) if 0 < nbytes <= (8 << 30) else None
         self._scratch = {}
 
     def _enqueue(self, posw: torch.Tensor, go) -> None:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.nnmd_nlist_build(self.code, _lib.ptr(posw), self.n_frames, self.n_atoms, self.n_centres,
                                                  self.rc + self.skin, _lib.ptr(self.ws), _lib.ptr(self.offsets), _lib.ptr(self.edge_offsets),
-                                                 _lib.ptr(self.idx), self.idx_cap, self.max_row_cap, self.edge_cap, _lib.ptr(self.stats),
+                                                 _lib.ptr(self.idx), self.idx_cap, self.max_row_cap, self.edge_cap,
+                                                 _lib.ptr(self.row_scratch), _lib.ptr(self.stats),
                                                  _lib.ptr(self.status), _lib.ptr(go), _lib.stream_ptr()))
 
     def build(self, posw: torch.Tensor) -> NeighborList:
