@@ -2,7 +2,8 @@
 """Summarise ncu outputs into the text files kept under profiles/.
 
     python tools/ncu_summary.py launches <launches.csv>          per-kernel totals and shares of a --metrics gpu__time_duration.sum run
-    python tools/ncu_summary.py kernel <report.ncu-rep>           key counters + hot SASS regions of a --set full capture
+    python tools/ncu_summary.py kernel <report.ncu-rep> [name]    key counters + hot SASS regions of a --set full capture
+                                                                  (first kernel of the report, or the first whose name matches)
 """
 import collections
 import csv
@@ -46,8 +47,9 @@ def launches(path):
         print(f"{k[:100]:100s} n={v[0]:4d} total={v[1]:10.3f} ms  avg={v[1] / v[0]:9.4f} ms  share={100 * v[1] / tot:5.1f}%")
 
 
-def kernel(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def kernel(path, name=None):
+    sel = ["-k", "regex:" + name] if name else []
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     print(f"# {path}")
@@ -64,7 +66,7 @@ def kernel(path):
                 continue
             if v > 0.2:
                 print(f"stall {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):40s} {v:8.3f} warps per issue")
-    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     hdr = rows[1]
     iE, iS = hdr.index("Instructions Executed"), hdr.index("# Samples")
@@ -90,4 +92,4 @@ def kernel(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](*sys.argv[2:])
