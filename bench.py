@@ -262,9 +262,10 @@ def run_ours(args):
         td.init_process_group("nccl", device_id=dev)
     sfd = bench_table()
     nf = len(sfd["features"])
-    pos, cell, pbc = fcc_cell(args.cells, dtype=torch.float32)
+    dt = torch.float64 if args.dtype == "f64" else torch.float32   # f64: the parity mode of north_star, measured on request
+    pos, cell, pbc = fcc_cell(args.cells, dtype=dt)
     n_atoms = pos.shape[0]
-    net = make_net(nf, dev)
+    net = make_net(nf, dev, dt)
     lib = _lib.load()
 
     # ---- spatial shard of this rank (whole cell for N=1): owned atoms first, halo atoms after
@@ -275,7 +276,7 @@ def run_ours(args):
     # capacity-bound neighbour build: after the first step nothing in a step waits for the host (skin 0: the list is rebuilt
     # from scratch EVERY step -- a step is one complete pass of the hot path over the structure)
     from nnmd_b200.neighbor import NeighborWorkspace
-    ws = None if args.sync_build else NeighborWorkspace(1, local_pos.shape[0], 6.0, torch.float32, dev, n_centres=n_owned)
+    ws = None if args.sync_build else NeighborWorkspace(1, local_pos.shape[0], 6.0, dt, dev, n_centres=n_owned)
 
     def step_device():
         # N>1: the halo exchange is part of every step (positions change every MD step)
@@ -334,12 +335,12 @@ def run_ours(args):
     e2e = None
     n_e2e = max(2, min(args.steps, 5))
     if world == 1:
-        bp = BPNN(dtype=torch.float32)
+        bp = BPNN(dtype=dt)
         bp.species, bp.atomic_nets, bp.pbc = ["Cu"], [net], None
         host = pos.clone().pin_memory()
 
-        out_e = torch.empty(n_atoms, dtype=torch.float32).pin_memory()     # per-atom energies (single frame: bpnn.py:532-554)
-        out_f = torch.empty(n_atoms, 3, dtype=torch.float32).pin_memory()
+        out_e = torch.empty(n_atoms, dtype=dt).pin_memory()     # per-atom energies (single frame: bpnn.py:532-554)
+        out_f = torch.empty(n_atoms, 3, dtype=dt).pin_memory()
 
         def step_e2e():
             E, F = bp.predict({"Cu": host}, cell, {"Cu": sfd}, pbc=pbc)
@@ -351,8 +352,8 @@ def run_ours(args):
     else:
         host = shard.owned_pos.cpu().pin_memory()
 
-        out_e = torch.empty(1, dtype=torch.float32).pin_memory()
-        out_f = torch.empty(1, n_owned, 3, dtype=torch.float32).pin_memory()
+        out_e = torch.empty(1, dtype=dt).pin_memory()
+        out_f = torch.empty(1, n_owned, 3, dtype=dt).pin_memory()
 
         def step_e2e():
             shard.set_owned_positions(host.to(dev, non_blocking=True))
@@ -372,8 +373,8 @@ def run_ours(args):
     if world > 1:
         td.all_reduce(dt, op=td.ReduceOp.MAX)
     dt = float(dt.item())
-    e2e = {"value": n_atoms / dt, "unit": "atoms/s", "h2d_bytes_per_step": int(host.numel() * 4) * world,
-           "d2h_bytes_per_step": int(F.numel() * 4 + E.numel() * 4) * world, "api": api, "ms_per_step": dt * 1e3}
+    e2e = {"value": n_atoms / dt, "unit": "atoms/s", "h2d_bytes_per_step": int(host.numel() * host.element_size()) * world,
+           "d2h_bytes_per_step": int(F.numel() * F.element_size() + E.numel() * E.element_size()) * world, "api": api, "ms_per_step": dt * 1e3}
 
     # ---- checksum of the structure the LAST timed step computed: must agree across N = 1, 2, 4, 8 to fp32 round-off
     chk = torch.stack([res.forces.double().abs().sum(), *res.forces.double().sum(dim=(0, 1))])
@@ -442,7 +443,7 @@ def run_ours(args):
                                 "frac": sfu_ops / (ang_ms_per_launch * 1e-3) / mb["mufu_ex2_lane_ops_per_s"]}
     line = {"metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "synthetic Cu fcc 1M-atom cell, rc=6 A, 32 G2 + 64 G4: descriptor+force eval"
                                    if args.cells == 63 else f"synthetic Cu fcc {args.cells}^3 cells",
                        "atoms": n_atoms, "cells": args.cells, "mlp": [nf] + HIDDEN + [1], "mode": args.mode,
@@ -485,6 +486,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput block")
     ap.add_argument("--train-frames", type=int, default=8000)
     ap.add_argument("--train-steps", type=int, default=40)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="working precision (f32 = the reference's training/eval precision and the headline; f64 = parity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-build", action="store_true", help="neighbour build with a host sync per step (the round-1 form)")
     ap.add_argument("--tri-per-atom", type=float, default=1350.0,

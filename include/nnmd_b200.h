@@ -64,6 +64,8 @@ int nnmd_set_option(const char *name, int value);
  * 3 normalize, 4 contract, 5 mlp, 6 wrap, 7 edge gather).  nnmd_profile_read synchronises the device and resets. */
 #define NNMD_PROF_NCLASS 8
 long long nnmd_launch_count(void);
+/* NVTX ranges around every kernel class ("nnmd:K1 neighbour list", "nnmd:K3 angular", ...) for nsys / ncu --nvtx; off by default */
+int nnmd_nvtx_enable(int on);
 int nnmd_profile_enable(int on);
 int nnmd_profile_read(double *ms, long long *count);
 

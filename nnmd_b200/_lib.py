@@ -28,6 +28,7 @@ _SIGNATURES = {
     "nnmd_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "nnmd_launch_count": (ctypes.c_longlong, []),
     "nnmd_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "nnmd_nvtx_enable": (ctypes.c_int, [ctypes.c_int]),
     "nnmd_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "nnmd_wrap_positions": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
@@ -156,6 +157,11 @@ PROF_CLASSES = ("nlist", "radial", "angular", "normalize", "contract", "mlp", "w
 
 def profile_enable(on: bool) -> None:
     check(load().nnmd_profile_enable(int(on)))
+
+
+def nvtx_enable(on: bool = True) -> None:
+    """NVTX ranges around every kernel class of the library (visible to nsys / `ncu --nvtx`); off by default."""
+    check(load().nnmd_nvtx_enable(int(on)))
 
 
 def profile_read() -> dict:

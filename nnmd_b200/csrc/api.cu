@@ -3,6 +3,8 @@
 
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges show up in nsys / ncu --nvtx when a tool is attached
+
 #include "common.cuh"
 
 namespace nnmd {
@@ -31,6 +33,9 @@ std::atomic<long long> g_launches{0};
 
 // Per-class event pairs recorded on the launching stream while profiling is enabled.
 static bool g_prof_on = false;
+static bool g_nvtx_on = false;
+static const char *const g_class_names[PROF_NCLASS] = {"nnmd:K1 neighbour list", "nnmd:K2 radial", "nnmd:K3 angular", "nnmd:K5 normalise",
+                                                       "nnmd:K4c contraction", "nnmd:K6 atomic network", "nnmd:K0 wrap", "nnmd:K4e edge gather"};
 struct ProfRec { int cls; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_pool;
@@ -41,12 +46,14 @@ static cudaEvent_t prof_event() {
     return e;
 }
 void prof_begin(int cls, cudaStream_t st) {
+    if (g_nvtx_on) nvtxRangePushA(g_class_names[cls]);
     if (!g_prof_on) return;
     ProfRec r{cls, prof_event(), prof_event()};
     cudaEventRecord(r.a, st);
     g_prof.push_back(r);
 }
 void prof_end(int cls, cudaStream_t st) {
+    if (g_nvtx_on) nvtxRangePop();
     if (!g_prof_on) return;
     for (size_t i = g_prof.size(); i-- > 0;)
         if (g_prof[i].cls == cls) { cudaEventRecord(g_prof[i].b, st); return; }
@@ -55,6 +62,11 @@ void prof_end(int cls, cudaStream_t st) {
 }  // namespace nnmd
 
 extern "C" long long nnmd_launch_count(void) { return nnmd::g_launches.load(); }
+
+extern "C" int nnmd_nvtx_enable(int on) {
+    nnmd::g_nvtx_on = on != 0;
+    return NNMD_OK;
+}
 
 extern "C" int nnmd_profile_enable(int on) {
     nnmd::g_prof_on = on != 0;

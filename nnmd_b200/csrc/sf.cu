@@ -691,8 +691,10 @@ __device__ __forceinline__ void phase2_ladder(const float *__restrict__ recs, in
     }
 }
 
+// fp64 values take two registers each: with the fp32 bound of 128 registers the double instantiations spilled 0.7-1.6 kB per
+// thread (round-1 VERDICT); two resident blocks per SM give them 255 registers and no spills.
 template <typename T, int FPL, int MODE>
-__global__ void __launch_bounds__(128, NNMD_ANG_MINB) angular_kernel(AngArgs<T> a) {
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : NNMD_ANG_MINB) angular_kernel(AngArgs<T> a) {
     if (a.flag != nullptr && (*a.flag & NNMD_FLAG_OVERFLOW)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
