@@ -472,23 +472,51 @@ class BPNN(torch.nn.Module):
 
         cartesians: {species: (B,N,3) or (N,3)}; returns (E per frame squeezed, F squeezed) like the reference:
         species are concatenated along dim 0 exactly as bpnn.py:546-552 does.
+
+        Repeated calls with the same system size (MD, scans) reuse a per-species `NeighborWorkspace`: the neighbour build
+        then runs in one pass without a host synchronisation, and for fp32 nets with a tensor-core instantiation the
+        normalisation, the network and the force contraction are ONE kernel.  The call synchronises once, at its end, to
+        raise the reference's ValueError on NaN descriptors (calculate_sf.py:106-109).  `release_workspaces()` frees the
+        cached buffers (the edge scratch of a million-atom structure is ~19 GB).
         """
+        from ..engine import energy_forces
+        from ..features.calculate_sf import get_plan, raise_on_flag
+        from ..neighbor import NeighborWorkspace
         for net in self.atomic_nets:
             net.eval()
+        torch.manual_seed(42)  # side effect of the reference's calculate_sf call inside predict (calculate_sf.py:115)
         pbc_t = self._default_pbc(cell) if pbc is None else torch.as_tensor(pbc)
+        cache = self.__dict__.setdefault("_predict_ws", {})
         e_nn = f_nn = None
         for i, spec in enumerate(self.species):
             cart = cartesians[spec].to(device=self.device)
             if cart.dim() == 2:
                 cart = cart.unsqueeze(0)
             cartesians[spec] = cart
-            g, dg = calculate_sf(cart, cell, pbc_t.to(cart.dtype), symm_func_params[spec], disable_tqdm=True)
-            e_spec, dE = self.atomic_nets[i].energy_and_grad(g, need_grad=True)
-            f_spec = force_contract(dE, dg)
+            B, N, _ = cart.shape
+            plan = get_plan(symm_func_params[spec], cart.dtype, cart.device)
+            key = (spec, B, N, cart.dtype, plan.rc_max)
+            for attempt in range(3):
+                ws = cache.get(key)
+                if ws is None:
+                    if len(cache) >= 4:  # a handful of shapes at most: drop the oldest (its buffers go back to the allocator)
+                        cache.pop(next(iter(cache)))
+                    ws = cache[key] = NeighborWorkspace(B, N, plan.rc_max, cart.dtype, cart.device)
+                ws.status.zero_()  # the status word is sticky across steps: a predict call starts clean
+                res = energy_forces(cart, cell, pbc_t.to(cart.dtype), symm_func_params[spec], self.atomic_nets[i],
+                                    mode="materialize", check=False, workspace=ws)
+                if ws.validate():  # one host sync per species; False: the structure outgrew the cached buffers (regrown)
+                    break
+            raise_on_flag(res.flag)
+            e_spec, f_spec = res.e_atoms.unsqueeze(-1), res.forces
             e_spec, f_spec = e_spec.squeeze(0), f_spec.squeeze(0)  # the reference squeezes g/dg before the net
             e_nn = e_spec if e_nn is None else torch.cat((e_nn, e_spec), dim=0)
             f_nn = f_spec if f_nn is None else torch.cat((f_nn, f_spec), dim=0)
         return e_nn.sum(1).squeeze(), f_nn.squeeze()
+
+    def release_workspaces(self) -> None:
+        """Free the neighbour-list workspaces `predict` keeps between calls."""
+        self.__dict__.pop("_predict_ws", None)
 
     def save_model(self, path: str):
         """One state_dict per species at <path>/atomic_nn_<spec>.pt (reference: bpnn.py:556-565)."""
