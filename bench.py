@@ -278,12 +278,24 @@ def run_ours(args):
     from nnmd_b200.neighbor import NeighborWorkspace
     ws = None if args.sync_build else NeighborWorkspace(1, local_pos.shape[0], 6.0, dt, dev, n_centres=n_owned)
 
+    graphed = None
+    if world > 1 and not args.no_graph and ws is not None:
+        # sharded steps are a few ms: replay the whole local evaluation from ONE CUDA graph (the halo exchange writes into the
+        # persistent buffer the graph reads; NCCL stays outside the graph)
+        from nnmd_b200.engine import GraphedEnergyForces
+        graphed = GraphedEnergyForces(local_pos, cell, pbc, sfd, net, n_centres=n_owned, mode=args.mode, mlp_precision=args.mlp)
+        ws = graphed.ws
+
     def step_device():
         # N>1: the halo exchange is part of every step (positions change every MD step)
         lp = shard.exchange_halo(dev) if world > 1 else local_pos
-        # cell and pbc stay on the host: K0 takes them as kernel arguments (a device copy would cost a read-back per step)
-        res = energy_forces(lp[None], cell, pbc, sfd, net, mode=args.mode, n_centres=n_owned,
-                            mlp_precision=args.mlp, check=False, workspace=ws)
+        if graphed is not None:
+            assert lp.data_ptr() == local_pos.data_ptr()
+            res = graphed()
+        else:
+            # cell and pbc stay on the host: K0 takes them as kernel arguments (a device copy would cost a read-back per step)
+            res = energy_forces(lp[None], cell, pbc, sfd, net, mode=args.mode, n_centres=n_owned,
+                                mlp_precision=args.mlp, check=False, workspace=ws)
         if world > 1:
             td.all_reduce(res.energy)  # total energy of the structure
         return res
@@ -320,6 +332,17 @@ def run_ours(args):
     launches = _lib.launch_count() - launches0
     assert int(res.flag.item()) == 0, "NaN / overflow flag raised during the timed steps"
     prof = _lib.profile_read()
+    prof_steps = args.steps
+    if graphed is not None:
+        # a graph replay carries no per-kernel events and no host-side launch calls: the stage breakdown (and the launch
+        # count) comes from two extra, UNTIMED steps launched kernel by kernel on the same buffers
+        launches0 = _lib.launch_count()
+        for _ in range(2):
+            energy_forces(local_pos[None], cell, pbc, sfd, net, mode=args.mode, n_centres=n_owned, mlp_precision=args.mlp,
+                          check=False, workspace=ws)
+        launches = (_lib.launch_count() - launches0) * args.steps // 2
+        prof = _lib.profile_read()
+        prof_steps = 2
     lib.nnmd_profile_enable(0)
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -401,6 +424,16 @@ def run_ours(args):
                 entry["cpu_baseline"] = bench_train.reference_train_baseline(cfg_name, *dataset)
             train[cfg_name] = entry
             del dataset
+    # per-rank stage times (device events): the step of a sharded run is set by the slowest rank
+    stage_names = sorted(prof)
+    stage_vec = torch.tensor([prof[k][0] / prof_steps for k in stage_names] + [float(n_owned), float(local_pos.shape[0])],
+                             dtype=torch.float64, device=dev)
+    if world > 1:
+        all_stage = [torch.empty_like(stage_vec) for _ in range(world)]
+        td.all_gather(all_stage, stage_vec)
+    else:
+        all_stage = [stage_vec]
+    per_rank = [{**{k: float(v[i]) for i, k in enumerate(stage_names)}, "owned_atoms": int(v[-2]), "local_atoms": int(v[-1])} for v in all_stage]
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (angular K3e): algorithmic bytes per centre atom
@@ -423,7 +456,7 @@ def run_ours(args):
                 "traffic_source": "profiles/r1_k3e_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                 "ms_per_launch": ang_ms_per_launch, "algorithmic_bytes_per_atom": bytes_per_atom,
                 "note": "K3e is bound by the FP32 FMA pipe and the SFU (ex2), not by HBM: see fp32_pipe/sfu_pipe, DESIGN.md, profiles/",
-                "stage_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+                "stage_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()}}
     # compute-side view of the same kernel against the MEASURED pipe peaks (tools/microbench.cu -> profiles/microbench_r1.json):
     # one (edge, third atom, function) costs 11 FMA-pipe lane-ops and 1.5 ex2; records per atom
     # = closed ordered (j,k) pairs / 2 = triangles-per-atom (3 edges x 1/3 ownership)
@@ -449,9 +482,12 @@ def run_ours(args):
                        "atoms": n_atoms, "cells": args.cells, "mlp": [nf] + HIDDEN + [1], "mode": args.mode,
                        "mlp_precision": args.mlp, "pbc": "reference wrap-only (SURVEY Q1)", "mean_neighbours": mean_nbrs,
                        "l2": "256 MiB buffer written between timed steps; per-step working set (neighbour list + dG) is >1 GB",
-                       "parallelism": "single GPU" if world == 1 else f"x-slabs x{world} (equal-work boundaries), halo rc, NCCL send/recv"},
+                       "parallelism": "single GPU" if world == 1 else f"x-slabs x{world} (equal-work boundaries), halo rc, NCCL send/recv",
+                       "launch": "one CUDA-graph replay per step + NCCL" if graphed is not None else "kernel by kernel"},
             "clocks": clocks.summary(), "gpu_launches": launches, "roofline": roofline}
     line["checksum"] = checksum
+    if world > 1:
+        line["per_rank_stage_ms"] = per_rank
     if train is not None:
         line["train"] = train
     if e2e is not None:
@@ -488,6 +524,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=40)
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="working precision (f32 = the reference's training/eval precision and the headline; f64 = parity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="N>1: launch the kernels of a step one by one instead of replaying a CUDA graph")
     ap.add_argument("--sync-build", action="store_true", help="neighbour build with a host sync per step (the round-1 form)")
     ap.add_argument("--tri-per-atom", type=float, default=1350.0,
                     help="closed triangles per atom of the workload (bulk fcc, rc=6: 1350) for the pipe-utilisation estimate")

@@ -120,6 +120,53 @@ def energy_forces(cart: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, sym
     return EvalResult(e_atoms.sum(dim=1), e_atoms, f.view(B, nc, 3), g.view(B, nc, plan.nf), nl, flag)
 
 
+class GraphedEnergyForces:
+    """`energy_forces` on a FIXED position buffer, captured once in a CUDA graph and replayed: for callers that evaluate the
+    same system over and over with new coordinates written into the same tensor (the sharded bench step, MD drivers).
+    The neighbour list lives in a NeighborWorkspace (capacity-bound, no host sync), every intermediate is static, and a
+    replay is one graph launch instead of ~45 kernel launches -- what matters once a step is down to a few milliseconds.
+    `__call__` returns the EvalResult whose tensors the replay overwrites; poll `ok()` when convenient (one host sync): it
+    raises the reference's ValueError on NaN descriptors and returns False after a buffer overflow (re-captured: call again)."""
+
+    def __init__(self, pos_buffer: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, symm_funcs_data: dict, net,
+                 n_centres: int | None = None, mode: str = "materialize", mlp_precision: str = "auto", skin: float = 0.0):
+        if pos_buffer.dim() != 2 or not pos_buffer.is_cuda:
+            raise ValueError("GraphedEnergyForces needs a CUDA position buffer of shape (n_atoms, 3)")
+        self.pos, self.args = pos_buffer, (cell.detach().to("cpu", pos_buffer.dtype), pbc.detach().to("cpu", pos_buffer.dtype), symm_funcs_data, net)
+        self.kw = dict(mode=mode, mlp_precision=mlp_precision, n_centres=n_centres, check=False)
+        plan = get_plan(symm_funcs_data, pos_buffer.dtype, pos_buffer.device)
+        self.ws = NeighborWorkspace(1, pos_buffer.shape[0], plan.rc_max, pos_buffer.dtype, pos_buffer.device, n_centres=n_centres, skin=skin)
+        self.graph = None
+        self._capture()
+
+    def _eval(self):
+        return energy_forces(self.pos[None], *self.args, workspace=self.ws, **self.kw)
+
+    def _capture(self):
+        for _ in range(2):  # the first call sizes the capacities (one sync), the second runs the steady-state sequence
+            self.result = self._eval()
+        torch.cuda.synchronize()
+        if not self.ws.validate():
+            self.result = self._eval()
+            torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.result = self._eval()
+        self.graph = g
+
+    def __call__(self) -> EvalResult:
+        self.graph.replay()
+        return self.result
+
+    def ok(self) -> bool:
+        if not self.ws.validate():      # buffers regrown: the captured addresses are stale
+            self.graph = None
+            self._capture()
+            return False
+        raise_on_flag(self.result.flag)
+        return True
+
+
 def energy_forces_species(cartesians: dict, cell: torch.Tensor, pbc: torch.Tensor, symm_funcs_data: dict, nets: dict,
                           mlp_precision: str = "auto", check: bool = True):
     """Multi-species evaluation with CROSS-species neighbours (extension; see features/multispecies.py):
