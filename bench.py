@@ -446,14 +446,14 @@ def run_ours(args):
     achieved = bytes_per_atom * n_owned / (ang_ms_per_launch * 1e-3) / 1e9 if ang_ms_per_launch > 0 else 0.0
     traffic = None
     try:  # DRAM bytes of ONE launch of this kernel from the committed ncu --set full capture (scaled if the cell differs)
-        with open(os.path.join(ROOT, "profiles", "r1_k3e_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2_k3e_traffic.json")) as fh:
             tr = json.load(fh)
         traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (n_owned / tr["atoms"])
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "angular_edge4_kernel<true,true> (K3e)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "traffic_source": "profiles/r1_k3e_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                "traffic_source": "profiles/r2_k3e_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                 "ms_per_launch": ang_ms_per_launch, "algorithmic_bytes_per_atom": bytes_per_atom,
                 "note": "K3e is bound by the FP32 FMA pipe and the SFU (ex2), not by HBM: see fp32_pipe/sfu_pipe, DESIGN.md, profiles/",
                 "stage_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()}}
