@@ -895,3 +895,42 @@ def test_fused_normalise_network_contract_kernel(F, hidden, rows):
     G2[5] = 0.0
     net.energy_force_fused(G2, dG, flag, out_g=G2)
     assert int(flag.item()) == _lib.FLAG_NAN_G and bool(torch.isnan(G2[5]).all()) and relerr(G2[6:].cpu(), g_ref[6:].cpu()) < 1e-6
+
+
+def test_graphed_evaluator_and_predict_workspace_reuse():
+    """`GraphedEnergyForces` (one CUDA-graph replay per evaluation on a fixed position buffer) and `BPNN.predict` (cached
+    NeighborWorkspace per system size) against the plain call: new coordinates through the same buffers, and a structure
+    that outgrows the cached capacities (compressed lattice: 2x the neighbours) is recovered transparently."""
+    from nnmd_b200.engine import GraphedEnergyForces, energy_forces
+    from nnmd_b200.nn import BPNN
+    from nnmd_b200.workloads import bench_net, bench_table, fcc_cell
+    sfd = bench_table()
+    pos, cell, pbc = fcc_cell(5, dtype=torch.float32)
+    pos = pos + 0.7
+    net = bench_net(96, DEV)
+    buf = pos.to(DEV).clone()
+    ev = GraphedEnergyForces(buf, cell, pbc, sfd, net)
+    gen = torch.Generator().manual_seed(9)
+    for it in range(3):
+        new = pos + 0.03 * torch.randn(pos.shape, generator=gen)
+        buf.copy_(new.to(DEV))
+        res = ev()
+        ref = energy_forces(new[None].to(DEV), cell, pbc, sfd, net)
+        assert ev.ok()
+        assert torch.equal(res.forces, ref.forces) and torch.equal(res.energy, ref.energy)
+    # predict: same numbers call after call, workspace reused; then a denser structure of the same size
+    bp = BPNN(dtype=torch.float32)
+    bp.species, bp.atomic_nets, bp.pbc = ["Cu"], [net], None
+    E1, F1 = bp.predict({"Cu": pos.clone()}, cell, {"Cu": sfd}, pbc=pbc)
+    E2, F2 = bp.predict({"Cu": pos.clone()}, cell, {"Cu": sfd}, pbc=pbc)
+    assert len(bp._predict_ws) == 1 and torch.equal(F1, F2) and torch.equal(E1, E2)
+    ref = energy_forces(pos[None].to(DEV), cell, pbc, sfd, net)
+    assert torch.equal(F1, ref.forces[0]) and torch.allclose(E1, ref.e_atoms[0])
+    dense = pos * 0.8                      # same atom count, 1.95x the density: rows and pair total outgrow the capacities
+    E3, F3 = bp.predict({"Cu": dense.clone()}, cell, {"Cu": sfd}, pbc=pbc)
+    ref3 = energy_forces(dense[None].to(DEV), cell, pbc, sfd, net)
+    assert torch.equal(F3, ref3.forces[0])
+    ws = next(iter(bp._predict_ws.values()))
+    assert ws.true_sizes()[0] == ref3.nlist.total and ws.idx_cap >= ref3.nlist.total
+    bp.release_workspaces()
+    assert not hasattr(bp, "_predict_ws")
