@@ -54,9 +54,10 @@ const char *nnmd_last_error(void);
 int nnmd_device_sm_count(void);
 
 /* Process-wide kernel-selection switches (explicit API calls, never the environment).
- *   "edge_ws" 0|1   form of the edge-centric angular kernel: 0 (default) every warp stages, enumerates and accumulates;
- *                   1 warp-specialised producer / consumer warps handing record batches over through mbarriers.
- *                   Bit-identical results; which one is faster is a measurement (profiles/README.md). */
+ *   "edge_form" 0|1  form of the edge-centric angular kernel: 1 (default) moment form -- per record and function three
+ *                    ladder multiplications and six accumulations (the derivative of the radial product is taken out of the
+ *                    sum over third atoms); 0 the derivative-record form of round 1 (eleven operations), kept for A/B
+ *                    measurements.  Same results to fp32 round-off (profiles/README.md). */
 int nnmd_set_option(const char *name, int value);
 
 /* Instrumentation for bench.py: number of kernel launches issued by this library so far, and optional

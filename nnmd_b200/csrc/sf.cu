@@ -1157,7 +1157,7 @@ extern "C" void nnmd_sf_plan_destroy(nnmd_sf_plan *p) {
 }
 
 extern "C" int nnmd_set_option(const char *name, int value) {
-    if (name && strcmp(name, "edge_ws") == 0) { nnmd::g_edge_ws = value ? 1 : 0; return NNMD_OK; }
+    if (name && strcmp(name, "edge_form") == 0) { nnmd::g_edge_form = value ? 1 : 0; return NNMD_OK; }
     return set_err(NNMD_ERR_INVALID, "set_option: unknown option %s", name ? name : "(null)");
 }
 

@@ -533,39 +533,28 @@ __global__ void __launch_bounds__(256, NNMD_GATHER_MINB) edge_gather_kernel(Edge
     if (MODE == MODE_DG && bad) atomicOr(a.flag, NNMD_FLAG_NAN_DG);
 }
 
-#include "sf_edge_ws.cuh"
+#include "sf_edge_m.cuh"
 
-#ifndef NNMD_EDGE_WS
-#define NNMD_EDGE_WS 0  // default form of K3e: 0 = every warp does everything; 1 = warp-specialised (producer / consumer warps).
-#endif                  // Measured on the 1M-atom cell (profiles/README.md, round 2): 55.6 ms vs 60.5-64.7 ms -- the
-                        // specialised form halves the number of FMA-issuing warps the register file can hold, and loses.
-static int g_edge_ws = NNMD_EDGE_WS;  // nnmd_set_option("edge_ws", 0|1)
+// Form of K3e: 1 (default) = moment form (sf_edge_m.cuh, 9 FMA-pipe lane-ops per record and function), 0 = the round-1
+// derivative-record form above (11), kept for A/B measurements.  nnmd_set_option("edge_form", 0|1).
+static int g_edge_form = 1;
 
 template <int MODE>
 static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
     constexpr bool WITH_PHI = MODE != MODE_G;
-    bool use_ws = g_edge_ws != 0;
-    if (const char *env = tuning_env("NNMD_EDGE_WS")) use_ws = env[0] != '0';  // tuning builds only
-    const size_t ws_smem = ws_pair_bytes(a.cap) * WS_PAIRS;
-    if (ws_smem > 110 * 1024) use_ws = false;  // rows too long for two resident blocks per SM: the plain form degrades more gently
+    int form = g_edge_form;
+    if (const char *env = tuning_env("NNMD_EDGE_FORM")) form = atoi(env);  // tuning builds only
     NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
-    if (use_ws) {
-        auto kern = a.ladder ? angular_edge4_ws_kernel<WITH_PHI, true> : angular_edge4_ws_kernel<WITH_PHI, false>;
-        NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ws_smem)));
-        int occ = 1;
-        NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 2 * WS_PAIRS * 32, ws_smem));
-        if (occ < 1) occ = 1;
-        int64_t blocks = std::min<int64_t>((a.n_rows + WS_PAIRS - 1) / WS_PAIRS, int64_t(sm_count()) * occ);
-        ProfScope prof(PROF_ANGULAR, st);
-        kern<<<unsigned(blocks), 2 * WS_PAIRS * 32, ws_smem, st>>>(a);
-        NNMD_LAUNCH_CHECK("angular_edge4_ws_kernel");
-    } else {
-        const size_t per_warp = size_t(EBATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 256 * sizeof(int);
+    {
+        const int stride = form ? EM_STRIDE : EREC_STRIDE;
+        const size_t per_warp = size_t(EBATCH) * stride * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 256 * sizeof(int);
         int wpb = 4;
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
         if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "angular: neighbour row of %d entries exceeds shared memory", a.cap);
-        auto kern = a.ladder ? angular_edge4_kernel<WITH_PHI, true> : angular_edge4_kernel<WITH_PHI, false>;
+        void (*kern)(EdgeArgs);
+        if (form) kern = a.ladder ? angular_edgem_kernel<WITH_PHI, true> : angular_edgem_kernel<WITH_PHI, false>;
+        else kern = a.ladder ? angular_edge4_kernel<WITH_PHI, true> : angular_edge4_kernel<WITH_PHI, false>;
         NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int occ = 1;
         NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
@@ -576,7 +565,7 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
 #endif
         ProfScope prof(PROF_ANGULAR, st);
         kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
-        NNMD_LAUNCH_CHECK("angular_edge4_kernel");
+        NNMD_LAUNCH_CHECK("angular_edge_kernel");
     }
     {
         int wpb = 8;

@@ -825,18 +825,21 @@ def test_graph_captured_md_loop_with_skin_follows_the_plain_loop():
     assert fast.ws.idx_cap > 64 and float((plain.x - fast.x).abs().max()) < 1e-9
 
 
+@pytest.mark.parametrize("kind", [4, 5])
 @pytest.mark.parametrize("with_grad", [True, False])
-def test_warp_specialised_edge_kernel_is_bit_identical(with_grad):
-    """The producer/consumer form of K3e (nnmd_set_option("edge_ws", 1): batches of records handed from producer warps to
-    consumer warps through mbarrier-guarded shared-memory rings) does the same arithmetic in the same order as the default
-    form: G, dG and the fused forces must be bit-identical, on a multi-row-per-pair workload and on a tiny one where most
-    pairs of a block get no row at all (termination path)."""
+def test_edge_kernel_forms_agree(with_grad, kind):
+    """The moment form of K3e (default, nnmd_set_option("edge_form", 1): B = b dE/dx and V = b E come out of ONE moment per
+    centre, scaled by the edge's own radial factor when the edge retires) against the derivative-record form of round 1
+    (edge_form 0): same sums in a different association, so G, dG and the fused forces agree to fp32 round-off
+    (column-normwise 2e-6; the parity tests hold each form to the oracle separately through the default).  Multi-row
+    workload and a tiny one where most warps get no row at all (termination path); G4 and G5."""
     from nnmd_b200 import _lib
     from nnmd_b200.engine import fused_force
     from nnmd_b200.features.calculate_sf import get_plan, raw_descriptors
     from nnmd_b200.neighbor import build_neighbor_list
     from nnmd_b200.workloads import bench_table, fcc_cell
     sfd = bench_table()
+    sfd = dict(sfd, features=[f if f == 2 else kind for f in sfd["features"]])
     plan = get_plan(sfd, torch.float32, torch.device(DEV))
     try:
         for ncell in (7, 1):
@@ -845,18 +848,20 @@ def test_warp_specialised_edge_kernel_is_bit_identical(with_grad):
             torch.manual_seed(ncell)
             w = torch.randn(nl.n_rows, plan.nf, device=DEV)
             out = []
-            for ws in (0, 1):
-                _lib.set_option("edge_ws", ws)
+            for form in (0, 1):
+                _lib.set_option("edge_form", form)
                 G, dG, flag = raw_descriptors(plan, nl, with_grad=with_grad)
                 F = fused_force(plan, nl, w)
                 torch.cuda.synchronize()
                 assert int(flag.item()) == 0
                 out.append((G, dG, F))
-            assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][2], out[1][2])
+            assert col_relerr(out[1][0], out[0][0], 1) < 2e-6
+            fmax = float(out[0][2].abs().max())
+            assert float((out[1][2] - out[0][2]).abs().max()) < 5e-6 * fmax
             if with_grad:
-                assert torch.equal(out[0][1], out[1][1])
+                assert col_relerr(out[1][1], out[0][1], 1) < 2e-6
     finally:
-        _lib.set_option("edge_ws", 0)
+        _lib.set_option("edge_form", 1)
 
 
 @pytest.mark.parametrize("F,hidden,rows", [(96, [64, 64], 1003), (14, [64, 64], 77), (50, [40, 64], 333), (33, [64, 48], 16)])
