@@ -546,14 +546,15 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
     if (const char *env = tuning_env("NNMD_EDGE_FORM")) form = atoi(env);  // tuning builds only
     NNMD_CUDA_CHECK(cudaMemsetAsync(a.row_counter, 0, sizeof(unsigned long long), st));
     {
-        const int stride = form ? EM_STRIDE : EREC_STRIDE;
-        const size_t per_warp = size_t(EBATCH) * stride * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 256 * sizeof(int);
+        const size_t per_warp = form ? edgem_per_warp_bytes(a.cap)
+                                     : size_t(EBATCH) * EREC_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 256 * sizeof(int);
         int wpb = 4;
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
         if (smem > 220 * 1024) return set_err(NNMD_ERR_CAPACITY, "angular: neighbour row of %d entries exceeds shared memory", a.cap);
         void (*kern)(EdgeArgs);
-        if (form) kern = a.ladder ? angular_edgem_kernel<WITH_PHI, true> : angular_edgem_kernel<WITH_PHI, false>;
+        if (form && a.cap <= 256) kern = a.ladder ? angular_edgem_kernel<WITH_PHI, true, uint16_t> : angular_edgem_kernel<WITH_PHI, false, uint16_t>;
+        else if (form) kern = a.ladder ? angular_edgem_kernel<WITH_PHI, true, uint32_t> : angular_edgem_kernel<WITH_PHI, false, uint32_t>;
         else kern = a.ladder ? angular_edge4_kernel<WITH_PHI, true> : angular_edge4_kernel<WITH_PHI, false>;
         NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int occ = 1;

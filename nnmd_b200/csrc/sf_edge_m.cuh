@@ -22,7 +22,29 @@
 #pragma once
 
 constexpr int EM_CLASS = 12;
-constexpr int EM_STRIDE = 28;  // 24 used; 28 mod 32 = 28: the 16 B stores of 32 lanes spread over all banks
+#ifndef NNMD_EDGEM_STRIDE
+#define NNMD_EDGEM_STRIDE 28
+#endif
+constexpr int EM_STRIDE = NNMD_EDGEM_STRIDE;  // 24 used; 28 mod 32 = 28: the 16 B stores of 32 lanes spread over all banks
+#ifndef NNMD_EDGEM_EBATCH
+#define NNMD_EDGEM_EBATCH 64
+#endif
+constexpr int EMBATCH = NNMD_EDGEM_EBATCH;  // (edge, third atom) records built per flush: up to two per lane
+// queue entry (tj, tk): 8 + 8 bits while rows have at most 256 entries, else 15 + 15 bits
+template <typename QT> struct QPack;
+template <> struct QPack<uint16_t> {
+    static __device__ __forceinline__ uint16_t pack(int tj, int tk) { return uint16_t(tj | (tk << 8)); }
+    static __device__ __forceinline__ int tj(uint16_t v) { return v & 0xff; }
+    static __device__ __forceinline__ int tk(uint16_t v) { return v >> 8; }
+};
+template <> struct QPack<uint32_t> {
+    static __device__ __forceinline__ uint32_t pack(int tj, int tk) { return uint32_t(tj | (tk << 15)); }
+    static __device__ __forceinline__ int tj(uint32_t v) { return v & 0x7fff; }
+    static __device__ __forceinline__ int tk(uint32_t v) { return (v >> 15) & 0x7fff; }
+};
+static inline size_t edgem_per_warp_bytes(int cap) {
+    return size_t(EMBATCH) * EM_STRIDE * sizeof(float) + size_t(NB_FIELDS) * cap * sizeof(float) + 256 * (cap <= 256 ? sizeof(uint16_t) : sizeof(uint32_t));
+}
 
 template <bool WITH_PHI, bool LADDER>
 __device__ __forceinline__ void make_record_m(const NbView<float> &nb, int tj, int tk, int kind, float step, float inv_rc,
@@ -89,18 +111,19 @@ __device__ __forceinline__ void make_record_m(const NbView<float> &nb, int tj, i
 #endif
 constexpr int NNMD_EDGEM_UNROLL_N = NNMD_EDGEM_UNROLL;
 
-template <bool WITH_PHI, bool LADDER>
+template <bool WITH_PHI, bool LADDER, typename QT>
 __global__ void __launch_bounds__(128, NNMD_EDGEM_MINB) angular_edgem_kernel(EdgeArgs a) {
     if (a.flag != nullptr && (*a.flag & NNMD_FLAG_OVERFLOW)) return;  // incomplete neighbour list (capacity-bound build)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using MF = M<float>;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    const size_t per_warp = size_t(EBATCH) * EM_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 256 * sizeof(int);
+    constexpr int EBATCH = EMBATCH;
+    const size_t per_warp = size_t(EBATCH) * EM_STRIDE * sizeof(float) + size_t(NB_FIELDS) * a.cap * sizeof(float) + 256 * sizeof(QT);
     unsigned char *wbase = smem_raw + per_warp * warp;
     float *recs = reinterpret_cast<float *>(wbase);
     NbView<float> nb;
     nb.bind(recs + EBATCH * EM_STRIDE, a.cap);
-    int *queue = reinterpret_cast<int *>(recs + EBATCH * EM_STRIDE + size_t(NB_FIELDS) * a.cap);  // ring of 256 packed (tj, tk)
+    QT *queue = reinterpret_cast<QT *>(recs + EBATCH * EM_STRIDE + size_t(NB_FIELDS) * a.cap);  // ring of 256 packed (tj, tk)
 
     const float inv_rc = MF::rcp(a.rc), rc2 = a.rc * a.rc;
     const int half = lane >> 4, l16 = lane & 15;
@@ -208,16 +231,16 @@ __global__ void __launch_bounds__(128, NNMD_EDGEM_MINB) angular_edgem_kernel(Edg
         auto flush = [&](int cnt) {
             __syncwarp();
             const bool has0 = lane < cnt, has1 = EBATCH > 32 && lane + 32 < cnt;
-            const int pk0 = has0 ? queue[(head + lane) & 255] : 0, pk1 = has1 ? queue[(head + lane + 32) & 255] : 0;
-            const int tj0 = has0 ? (pk0 & 0x7fff) : -2, tj1 = has1 ? (pk1 & 0x7fff) : -2;
+            const QT pk0 = has0 ? queue[(head + lane) & 255] : QT(0), pk1 = has1 ? queue[(head + lane + 32) & 255] : QT(0);
+            const int tj0 = has0 ? QPack<QT>::tj(pk0) : -2, tj1 = has1 ? QPack<QT>::tj(pk1) : -2;
             int prev0 = __shfl_up_sync(0xffffffffu, tj0, 1), prev1 = __shfl_up_sync(0xffffffffu, tj1, 1);
             const int tj0_last = __shfl_sync(0xffffffffu, tj0, 31);
             if (lane == 0) { prev0 = last_tj; prev1 = tj0_last; }
             // the queue is edge-major: a change of tj opens the next edge
             const bool first0 = has0 && tj0 != prev0, first1 = has1 && tj1 != prev1;
-            if (has0) make_record_m<WITH_PHI, LADDER>(nb, tj0, (pk0 >> 15) & 0x7fff, kind, step, inv_rc, eta, recs + lane * EM_STRIDE);
+            if (has0) make_record_m<WITH_PHI, LADDER>(nb, tj0, QPack<QT>::tk(pk0), kind, step, inv_rc, eta, recs + lane * EM_STRIDE);
             if (EBATCH > 32 && has1)
-                make_record_m<WITH_PHI, LADDER>(nb, tj1, (pk1 >> 15) & 0x7fff, kind, step, inv_rc, eta, recs + (lane + 32) * EM_STRIDE);
+                make_record_m<WITH_PHI, LADDER>(nb, tj1, QPack<QT>::tk(pk1), kind, step, inv_rc, eta, recs + (lane + 32) * EM_STRIDE);
             last_tj = cnt > 32 ? __shfl_sync(0xffffffffu, tj1, cnt - 33) : __shfl_sync(0xffffffffu, tj0, cnt - 1);
             const unsigned long long firsts = (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, first1)) << 32) |
                                               __ballot_sync(0xffffffffu, first0);
@@ -305,7 +328,7 @@ __global__ void __launch_bounds__(128, NNMD_EDGEM_MINB) angular_edgem_kernel(Edg
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const unsigned m = __ballot_sync(0xffffffffu, ok[c]);
-                    if (ok[c]) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 255] = tj | ((kb + 32 * c + lane) << 15);
+                    if (ok[c]) queue[(head + qn + __popc(m & ((1u << lane) - 1u))) & 255] = QPack<QT>::pack(tj, kb + 32 * c + lane);
                     const int n_ok = __popc(m);
                     pushed_edge += n_ok;
                     qn += n_ok;
