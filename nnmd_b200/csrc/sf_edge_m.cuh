@@ -23,9 +23,10 @@
 
 constexpr int EM_CLASS = 12;
 #ifndef NNMD_EDGEM_STRIDE
-#define NNMD_EDGEM_STRIDE 28
+#define NNMD_EDGEM_STRIDE 24
 #endif
-constexpr int EM_STRIDE = NNMD_EDGEM_STRIDE;  // 24 used; 28 mod 32 = 28: the 16 B stores of 32 lanes spread over all banks
+constexpr int EM_STRIDE = NNMD_EDGEM_STRIDE;  // 24 used.  28 would make the 16 B record stores conflict-free (24: two-way), but the
+                                              // 1 kB per warp it costs is what lets a fifth block fit on the SM (measured: 47.5 vs 49.4 ms)
 #ifndef NNMD_EDGEM_EBATCH
 #define NNMD_EDGEM_EBATCH 64
 #endif
@@ -46,9 +47,11 @@ static inline size_t edgem_per_warp_bytes(int cap) {
     return size_t(EMBATCH) * EM_STRIDE * sizeof(float) + size_t(NB_FIELDS) * cap * sizeof(float) + 256 * (cap <= 256 ? sizeof(uint16_t) : sizeof(uint32_t));
 }
 
+// `store` = false: the lane has no record in this slot; it still runs the arithmetic (on clamped indices) so that the two
+// records of a lane are built in ONE instruction stream with twice the instruction-level parallelism.
 template <bool WITH_PHI, bool LADDER>
 __device__ __forceinline__ void make_record_m(const NbView<float> &nb, int tj, int tk, int kind, float step, float inv_rc,
-                                              float eta, float *__restrict__ rec) {
+                                              float eta, float *__restrict__ rec, bool store) {
     using MF = M<float>;
     const Q4<float> uj = ld4<float>(nb.u4 + 4 * tj), uk = ld4<float>(nb.u4 + 4 * tk);
     const float x = uj.d, y = uk.d, ix = nb.invd[tj], iy = nb.invd[tk];
@@ -93,6 +96,7 @@ __device__ __forceinline__ void make_record_m(const NbView<float> &nb, int tj, i
         else R[0][X] = R[1][X] = 0.f;
     }
     if (!WITH_PHI) A[0] = A[1] = A[2] = 0.f;
+    if (!store) return;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         float *r = rec + s * EM_CLASS;
@@ -104,7 +108,7 @@ __device__ __forceinline__ void make_record_m(const NbView<float> &nb, int tj, i
 }
 
 #ifndef NNMD_EDGEM_MINB
-#define NNMD_EDGEM_MINB 4
+#define NNMD_EDGEM_MINB 5
 #endif
 #ifndef NNMD_EDGEM_UNROLL
 #define NNMD_EDGEM_UNROLL 2
@@ -233,14 +237,24 @@ __global__ void __launch_bounds__(128, NNMD_EDGEM_MINB) angular_edgem_kernel(Edg
             const bool has0 = lane < cnt, has1 = EBATCH > 32 && lane + 32 < cnt;
             const QT pk0 = has0 ? queue[(head + lane) & 255] : QT(0), pk1 = has1 ? queue[(head + lane + 32) & 255] : QT(0);
             const int tj0 = has0 ? QPack<QT>::tj(pk0) : -2, tj1 = has1 ? QPack<QT>::tj(pk1) : -2;
+#ifndef NNMD_EDGEM_MERGE
+#define NNMD_EDGEM_MERGE 1
+#endif
             int prev0 = __shfl_up_sync(0xffffffffu, tj0, 1), prev1 = __shfl_up_sync(0xffffffffu, tj1, 1);
             const int tj0_last = __shfl_sync(0xffffffffu, tj0, 31);
             if (lane == 0) { prev0 = last_tj; prev1 = tj0_last; }
             // the queue is edge-major: a change of tj opens the next edge
             const bool first0 = has0 && tj0 != prev0, first1 = has1 && tj1 != prev1;
-            if (has0) make_record_m<WITH_PHI, LADDER>(nb, tj0, QPack<QT>::tk(pk0), kind, step, inv_rc, eta, recs + lane * EM_STRIDE);
+#if NNMD_EDGEM_MERGE
+            // pk = 0 names the staged neighbours (0, 0): finite garbage that is never stored
+            make_record_m<WITH_PHI, LADDER>(nb, QPack<QT>::tj(pk0), QPack<QT>::tk(pk0), kind, step, inv_rc, eta, recs + lane * EM_STRIDE, has0);
+            if (EBATCH > 32)
+                make_record_m<WITH_PHI, LADDER>(nb, QPack<QT>::tj(pk1), QPack<QT>::tk(pk1), kind, step, inv_rc, eta, recs + (lane + 32) * EM_STRIDE, has1);
+#else
+            if (has0) make_record_m<WITH_PHI, LADDER>(nb, tj0, QPack<QT>::tk(pk0), kind, step, inv_rc, eta, recs + lane * EM_STRIDE, true);
             if (EBATCH > 32 && has1)
-                make_record_m<WITH_PHI, LADDER>(nb, tj1, QPack<QT>::tk(pk1), kind, step, inv_rc, eta, recs + (lane + 32) * EM_STRIDE);
+                make_record_m<WITH_PHI, LADDER>(nb, tj1, QPack<QT>::tk(pk1), kind, step, inv_rc, eta, recs + (lane + 32) * EM_STRIDE, true);
+#endif
             last_tj = cnt > 32 ? __shfl_sync(0xffffffffu, tj1, cnt - 33) : __shfl_sync(0xffffffffu, tj0, cnt - 1);
             const unsigned long long firsts = (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, first1)) << 32) |
                                               __ballot_sync(0xffffffffu, first0);
