@@ -297,7 +297,7 @@ def run_ours(args):
             res = energy_forces(lp[None], cell, pbc, sfd, net, mode=args.mode, n_centres=n_owned,
                                 mlp_precision=args.mlp, check=False, workspace=ws)
         if world > 1:
-            td.all_reduce(res.energy)  # total energy of the structure
+            dist.allreduce_sum(res.energy)  # total energy of the structure (peer-window kernel; NCCL where unavailable)
         return res
 
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)

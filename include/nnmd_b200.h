@@ -267,6 +267,35 @@ int nnmd_loss_mse(int dtype, int n_species, const int32_t *n_atoms, const void *
 int nnmd_gather_rows(int n_arrays, const void *const *src, void *const *dst, const int64_t *row_bytes,
                      const int64_t *sel, int64_t n_sel, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Peer windows: the two collectives of the path as ordinary kernels over NVLink peer memory (csrc/peer.cu).
+ * One process per GPU; every rank creates a window of the same size, the ranks exchange the CUDA-IPC handles
+ * (nnmd_peer_handle_bytes() bytes each; nnmd_b200/dist.py does it through torch.distributed), and connect.
+ * The kernels synchronise through step numbers stored in the windows, so they can be captured into the CUDA graph of
+ * the step they belong to; every rank must issue the same sequence of calls.  A peer that never arrives raises the
+ * window's status word after ~2 s instead of hanging the device.
+ *   nnmd_peer_allreduce_weighted_f32  replaces the NCCL all-reduce of the flat MLP gradient buffer of the data-parallel
+ *       form of the reference's optimizer step (nnmd/nn/bpnn.py:366-368): buf[0..n-1) = this rank's batch-mean gradient,
+ *       buf[n-1] = its frame count b_r;  afterwards buf[i] = sum_r b_r buf_r[i] / sum_r b_r, buf[n-1] = sum_r b_r,
+ *       bit-identical on all ranks.
+ *   nnmd_peer_halo_exchange  one halo round of the x-slab decomposition (nnmd_b200/dist.py:SlabShard): rows of `width`
+ *       4-byte words; own[send_idx[k]] goes to row dst_slot[k] of the halo of rank dst_peer[k];
+ *       local = [ own (n_own rows) | halo (n_halo rows) ].
+ */
+typedef struct nnmd_peer nnmd_peer;
+int nnmd_peer_handle_bytes(void);
+int nnmd_peer_create(int rank, int world, int64_t cap_bytes, nnmd_peer **out);
+int nnmd_peer_export(nnmd_peer *p, void *handle_out);
+int nnmd_peer_connect(nnmd_peer *p, const void *handles);
+void nnmd_peer_destroy(nnmd_peer *p);
+int64_t nnmd_peer_capacity(const nnmd_peer *p);
+int nnmd_peer_status(nnmd_peer *p, int *status);
+int nnmd_peer_allreduce_weighted_f32(nnmd_peer *p, float *buf, int64_t n, void *stream);
+/* plain sum of buf[0..n) over the ranks, in place (the total energy of a spatially sharded structure) */
+int nnmd_peer_allreduce_sum_f32(nnmd_peer *p, float *buf, int64_t n, void *stream);
+int nnmd_peer_halo_exchange(nnmd_peer *p, const void *own, int64_t n_own, const int64_t *send_idx, const int32_t *dst_peer,
+                            const int64_t *dst_slot, int64_t n_send, int64_t n_halo, int width, void *local, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libnnmd_b200.so")
-SOURCES = ["api.cu", "nlist.cu", "sf.cu", "mlp.cu", "mlp_tc.cu", "mlp_train.cu", "mlp_fast.cu", "loss.cu"]
+SOURCES = ["api.cu", "nlist.cu", "sf.cu", "mlp.cu", "mlp_tc.cu", "mlp_train.cu", "mlp_fast.cu", "loss.cu", "peer.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

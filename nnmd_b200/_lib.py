@@ -92,6 +92,18 @@ _SIGNATURES = {
     "nnmd_loss_mse": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nnmd_peer_handle_bytes": (ctypes.c_int, []),
+    "nnmd_peer_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]),
+    "nnmd_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "nnmd_peer_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "nnmd_peer_destroy": (None, [ctypes.c_void_p]),
+    "nnmd_peer_capacity": (ctypes.c_int64, [ctypes.c_void_p]),
+    "nnmd_peer_status": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
+    "nnmd_peer_allreduce_weighted_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "nnmd_peer_allreduce_sum_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "nnmd_peer_halo_exchange": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

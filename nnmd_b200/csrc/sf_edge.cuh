@@ -557,12 +557,16 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         else if (form) kern = a.ladder ? angular_edgem_kernel<WITH_PHI, true, uint32_t> : angular_edgem_kernel<WITH_PHI, false, uint32_t>;
         else kern = a.ladder ? angular_edge4_kernel<WITH_PHI, true> : angular_edge4_kernel<WITH_PHI, false>;
         NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+#ifdef NNMD_TUNING
+        if (const char *env = tuning_env("NNMD_CARVEOUT")) NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env)));
+#endif
         int occ = 1;
         NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
         if (occ < 1) occ = 1;
         int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * occ);
 #ifdef NNMD_TUNING
         if (const char *env = tuning_env("NNMD_DBG")) a.dbg = atoi(env);
+        if (tuning_env("NNMD_VERBOSE")) fprintf(stderr, "[nnmd] K3e form %d cap %d smem %zu B/block, %d blocks/SM\n", form, a.cap, smem, occ);
 #endif
         ProfScope prof(PROF_ANGULAR, st);
         kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);

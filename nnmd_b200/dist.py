@@ -25,6 +25,120 @@ def _world():
     return 0, 1
 
 
+class PeerWindow:
+    """A symmetric device window mapped into every rank of the job (CUDA IPC over NVLink; csrc/peer.cu): the collectives of
+    the path run on it as ordinary kernels, so they are captured into the CUDA graph of the step they belong to.
+
+    Collective constructor: every rank must create its windows in the same order.  `PeerWindow.create` returns None (after
+    saying so once) where peer windows cannot be had -- CPU tensors / gloo tests, one rank, ranks on different hosts, or an
+    IPC mapping the platform refuses -- and the callers fall back to torch.distributed (NCCL)."""
+
+    _warned = False
+
+    def __init__(self, handle, lib, cap_bytes: int):
+        self.handle, self._lib, self.cap_bytes = handle, lib, cap_bytes
+
+    @classmethod
+    def create(cls, cap_bytes: int, device) -> "PeerWindow | None":
+        import ctypes
+        import os
+        from . import _lib
+        rank, world = _world()
+        device = torch.device(device)
+        if world == 1 or device.type != "cuda" or os.environ.get("NNMD_NO_PEER", "0") == "1":
+            return None
+        lib = _lib.load()
+        handle, blob, err = ctypes.c_void_p(), b"", None
+        try:
+            with torch.cuda.device(device):
+                _lib.check(lib.nnmd_peer_create(rank, world, int(cap_bytes), ctypes.byref(handle)))
+                buf = ctypes.create_string_buffer(lib.nnmd_peer_handle_bytes())
+                _lib.check(lib.nnmd_peer_export(handle, buf))
+                blob = buf.raw
+        except _lib.NnmdError as exc:
+            err = str(exc)
+        # one all-gather carries the handles AND the verdicts: either every rank connects or none does
+        gathered = [None] * world
+        td.all_gather_object(gathered, (blob, err, os.uname().nodename))
+        ok = all(g[1] is None for g in gathered) and len({g[2] for g in gathered}) == 1
+        if ok:
+            try:
+                with torch.cuda.device(device):
+                    _lib.check(lib.nnmd_peer_connect(handle, b"".join(g[0] for g in gathered)))
+            except _lib.NnmdError as exc:
+                err = str(exc)
+        verdicts = [None] * world
+        td.all_gather_object(verdicts, err)
+        if not ok or any(v is not None for v in verdicts):
+            if handle:
+                lib.nnmd_peer_destroy(handle)
+            if rank == 0 and not cls._warned:
+                cls._warned = True
+                why = next((v for v in verdicts if v), None) or next((g[1] for g in gathered if g[1]), "ranks on different hosts")
+                print(f"nnmd_b200: peer windows unavailable ({why}); using NCCL for the exchanges", flush=True)
+            return None
+        return cls(handle, lib, int(lib.nnmd_peer_capacity(handle)))
+
+    def status(self) -> int:
+        """0, or 1 when a peer failed to arrive in some call since creation (that call's result is garbage).  Synchronises."""
+        import ctypes
+        from . import _lib
+        v = ctypes.c_int(0)
+        _lib.check(self._lib.nnmd_peer_status(self.handle, ctypes.byref(v)))
+        return int(v.value)
+
+    def check(self) -> None:
+        if self.status():
+            from . import _lib
+            raise _lib.NnmdError("a peer did not arrive at a peer-window exchange within the spin limit")
+
+    def allreduce_weighted(self, buf: torch.Tensor) -> None:
+        from . import _lib
+        with torch.cuda.device(buf.device):
+            _lib.check(self._lib.nnmd_peer_allreduce_weighted_f32(self.handle, _lib.ptr(buf), buf.numel(), _lib.stream_ptr()))
+
+    def allreduce_sum(self, buf: torch.Tensor) -> None:
+        from . import _lib
+        with torch.cuda.device(buf.device):
+            _lib.check(self._lib.nnmd_peer_allreduce_sum_f32(self.handle, _lib.ptr(buf), buf.numel(), _lib.stream_ptr()))
+
+    def halo_exchange(self, own: torch.Tensor, send_idx, dst_peer, dst_slot, n_halo: int, local: torch.Tensor) -> None:
+        from . import _lib
+        width = own.shape[1] * own.element_size() // 4
+        with torch.cuda.device(own.device):
+            _lib.check(self._lib.nnmd_peer_halo_exchange(self.handle, _lib.ptr(own), own.shape[0], _lib.ptr(send_idx), _lib.ptr(dst_peer),
+                                                         _lib.ptr(dst_slot), 0 if send_idx is None else send_idx.numel(), int(n_halo),
+                                                         width, _lib.ptr(local), _lib.stream_ptr()))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._lib.nnmd_peer_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+_SMALL_WINDOW: dict = {}
+
+
+def allreduce_sum(t: torch.Tensor) -> torch.Tensor:
+    """In-place sum of a small float32 CUDA tensor over the ranks (e.g. the total energy of a sharded structure): one kernel
+    over a peer window where available (first call is collective: it creates the window), NCCL / gloo otherwise."""
+    rank, world = _world()
+    if world == 1:
+        return t
+    if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= 4096:
+        key = t.device.index
+        if key not in _SMALL_WINDOW:
+            _SMALL_WINDOW[key] = PeerWindow.create(4 * (4096 + 64), t.device)
+        if _SMALL_WINDOW[key] is not None:
+            _SMALL_WINDOW[key].allreduce_sum(t)
+            return t
+    td.all_reduce(t)
+    return t
+
+
 @dataclass
 class SlabShard:
     """Ownership and halo plan of one rank for an x-slab decomposition."""
@@ -120,10 +234,31 @@ class SlabShard:
             td.all_gather(all_counts, counts)
             self.recv_counts = [int(all_counts[peer][self.rank]) for peer in range(self.world)]
             self._local = None
+            self._window = None
+            if device.type == "cuda" and own.dtype in (torch.float32, torch.float64):
+                # peer-memory route: every sender writes its rows straight into the receiver's halo (same order as the
+                # send/recv route: blocks by ascending sender rank), three small kernels per step and no NCCL call
+                cm = torch.stack(all_counts).cpu()                     # cm[q][p] = rows q sends to p
+                row_bytes = own.shape[1] * own.element_size()
+                self._window = PeerWindow.create(max(int(cm.sum(0).max()) * row_bytes, 256), device)
+                if self._window is not None:
+                    idx, peers, slots = [], [], []
+                    for peer in range(self.world):
+                        if peer == self.rank or self.send_idx[peer] is None:
+                            continue
+                        k = int(self.send_idx[peer].numel())
+                        base = int(cm[:self.rank, peer].sum())          # my block starts after the lower-ranked senders'
+                        idx.append(self.send_idx[peer].to(device=device, dtype=torch.int64))
+                        peers.append(torch.full((k,), peer, dtype=torch.int32, device=device))
+                        slots.append(torch.arange(base, base + k, dtype=torch.int64, device=device))
+                    self._push = (torch.cat(idx), torch.cat(peers), torch.cat(slots)) if idx else (None, None, None)
         n_own = own.shape[0]
         local = getattr(self, "_local", None)
         if local is None or local.device != device or local.dtype != own.dtype or local.shape[0] != n_own + sum(self.recv_counts):
             local = self._local = torch.empty((n_own + sum(self.recv_counts), 3), dtype=own.dtype, device=device)
+        if getattr(self, "_window", None) is not None:
+            self._window.halo_exchange(own.contiguous(), *self._push, sum(self.recv_counts), local)
+            return local
         local[:n_own].copy_(own)
         ops, keep, off = [], [], n_own
         for peer in range(self.world):
@@ -165,6 +300,7 @@ class FlatGradients:
         self.buf = torch.zeros(n + 1, dtype=ref.dtype, device=ref.device)
         self.flat = self.buf[:n]
         self.count = self.buf[n:]  # (1,) frames behind the gradient: local before, global after `allreduce`
+        self.window, self._window_tried = None, False  # PeerWindow of the buffer's size, made at the first multi-rank all-reduce
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -195,10 +331,21 @@ class FlatGradients:
             td.all_reduce(self.flat, op=td.ReduceOp.SUM)
             self.flat /= world
             return
-        self.flat *= float(n_frames)
         self.count.fill_(float(n_frames))
+        if self.window is None and not self._window_tried:
+            self._window_tried = True
+            if self.buf.dtype == torch.float32:
+                self.window = PeerWindow.create(4 * (self.buf.numel() + 64), self.buf.device)
+        if self.window is not None:  # one kernel over NVLink peer memory, capturable into the step's CUDA graph
+            self.window.allreduce_weighted(self.buf)
+            return
+        self.flat *= float(n_frames)
         td.all_reduce(self.buf, op=td.ReduceOp.SUM)
         self.flat /= self.count
+
+    def graph_capturable(self) -> bool:
+        """True when `allreduce` is plain kernels on the current stream (one rank, or a connected peer window)."""
+        return _world()[1] == 1 or self.window is not None
 
 
 def allreduce_gradients(params, average: bool = True) -> None:

@@ -260,18 +260,23 @@ class BPNN(torch.nn.Module):
         return plan
 
     def _step_plan(self, plan):
-        """Run one loaded plan.  One rank: the whole step is one CUDA graph.  Several ranks: forward + backward (graph 1) |
-        gradient all-reduce | optimizer (graph 2) -- capturing the NCCL all-reduce into the graph hung on this stack
-        (torch 2.11 / NCCL 2.28, 2 GPUs), so it stays between the graphs."""
+        """Run one loaded plan.  One rank: the whole step is one CUDA graph.  Several ranks with a peer window
+        (dist.PeerWindow: the gradient all-reduce is a kernel over NVLink peer memory): still ONE graph -- forward, backward,
+        all-reduce, optimizer, loss accounting.  Several ranks on NCCL: forward + backward (graph 1) | all-reduce |
+        optimizer (graph 2); capturing the NCCL all-reduce hung on this stack (torch 2.11 / NCCL 2.28, 2 GPUs)."""
+        multi = self._flat_grads.world_size() > 1
         if self._graphs_ok and plan.graphs is None and self._opt_ready:
-            multi = self._flat_grads.world_size() > 1
             try:  # the optimizer state exists (one eager step was done): capture the step
                 torch.cuda.synchronize()
-                if not multi:  # one rank: forward + backward and optimizer in ONE graph
+                if not multi or self._flat_grads.graph_capturable():
                     whole = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(whole):
                         plan.run()
+                        if multi:
+                            self._flat_grads.allreduce(plan.n_frames)
                         self.optim.step()
+                        if multi:  # this rank's share of the global-batch loss: out * b_r / sum_r b_r
+                            self._acc_multi.addcdiv_(plan.out, self._flat_grads.count, value=float(plan.n_frames))
                     plan.graphs = (whole,)
                 else:
                     fwd_bwd, opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -286,7 +291,8 @@ class BPNN(torch.nn.Module):
                 self._graphs_ok = False
         if plan.graphs is not None and len(plan.graphs) == 1:
             plan.graphs[0].replay()
-        elif plan.graphs is not None:
+            return
+        if plan.graphs is not None:
             plan.graphs[0].replay()
             self._flat_grads.allreduce(plan.n_frames)  # frames are sharded across ranks: weighted by the batch sizes
             plan.graphs[1].replay()
@@ -295,7 +301,7 @@ class BPNN(torch.nn.Module):
             self._flat_grads.allreduce(plan.n_frames)
             self.optim.step()
             self._opt_ready = True
-        if self._flat_grads.world_size() > 1:  # this rank's share of the global-batch loss: out * b_r / sum_r b_r
+        if multi:
             self._acc_multi.addcdiv_(plan.out, self._flat_grads.count, value=float(plan.n_frames))
 
     def _train_step(self, g, dG, energy, forces, out):
@@ -322,7 +328,9 @@ class BPNN(torch.nn.Module):
             self._flat_grads = FlatGradients([p for net in self.atomic_nets for p in net.parameters()])
             self._plans, self._opt_ready, self._acc_carry = {}, False, None
         n_steps = self._epoch_steps(len(loader))
-        self._acc_multi = torch.zeros(3, device=self.device)
+        if getattr(self, "_acc_multi", None) is None:  # persistent: the captured step adds into it
+            self._acc_multi = torch.zeros(3, device=self.device)
+        self._acc_multi.zero_()
         if train and isinstance(loader, FrameBatches) and loader.base.energies.is_cuda \
                 and self._fused_ok({s: v[0] for s, v in loader.base.sf_data.items()}, {s: v[1] for s, v in loader.base.sf_data.items()}):
             # batches are gathered straight into the static buffers of the step (no per-batch tensors, no copies)
