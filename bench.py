@@ -8,7 +8,7 @@ A step is one pass of the hot path over the whole cell: K0 wrap -> K1 cell-list 
 and angular symmetry functions with analytic summed gradients -> K5 normalise -> K6 atomic MLP (e, dE/dg) ->
 K4c force contraction.  N=1 workload: configs[3] of BASELINE.json, 63^3 fcc cells = 1,000,188 Cu atoms, rc = 6 A,
 32 G2 + 64 G4 (the literal table is nnmd_b200.workloads.bench_table), fp32, reference (wrap-only) PBC semantics.
-N>1: the same cell sharded spatially in x-slabs with a halo of rc (nnmd_b200.dist), strong scaling.
+N>1: the same cell sharded spatially into boxes (2x2x2 on 8 GPUs) with a halo of rc (nnmd_b200.dist), strong scaling.
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -269,7 +269,7 @@ def run_ours(args):
     lib = _lib.load()
 
     # ---- spatial shard of this rank (whole cell for N=1): owned atoms first, halo atoms after
-    shard = dist.SlabShard.from_global(pos, cell, pbc, rc=6.0, rank=rank, world=world).to(dev)
+    shard = dist.SlabShard.from_global(pos, cell, pbc, rc=6.0, rank=rank, world=world, grid=args.grid).to(dev)
     local_pos = shard.exchange_halo(dev)           # (n_local, 3) on the GPU: owned + halo (NCCL send/recv for N>1)
     n_owned = shard.n_owned
 
@@ -482,7 +482,10 @@ def run_ours(args):
                        "atoms": n_atoms, "cells": args.cells, "mlp": [nf] + HIDDEN + [1], "mode": args.mode,
                        "mlp_precision": args.mlp, "pbc": "reference wrap-only (SURVEY Q1)", "mean_neighbours": mean_nbrs,
                        "l2": "256 MiB buffer written between timed steps; per-step working set (neighbour list + dG) is >1 GB",
-                       "parallelism": "single GPU" if world == 1 else f"x-slabs x{world} (equal-work boundaries), halo rc, NCCL send/recv",
+                       "parallelism": "single GPU" if world == 1 else
+                       f"{'x'.join(str(v) for v in shard.grid)} boxes (equal-work boundaries), halo rc, "
+                       + ("halo exchange and energy sum as kernels over NVLink peer memory (CUDA IPC windows)"
+                          if getattr(shard, "_window", None) is not None else "NCCL send/recv"),
                        "launch": "one CUDA-graph replay per step + NCCL" if graphed is not None else "kernel by kernel"},
             "clocks": clocks.summary(), "gpu_launches": launches, "roofline": roofline}
     line["checksum"] = checksum
@@ -524,6 +527,8 @@ def main():
     ap.add_argument("--train-steps", type=int, default=40)
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="working precision (f32 = the reference's training/eval precision and the headline; f64 = parity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid", default="auto", type=lambda v: v if v == "auto" else tuple(int(x) for x in v.split("x")),
+                    help="N>1: decomposition, 'auto' (least boundary area, 2x2x2 on 8 GPUs) or e.g. 8x1x1 for x-slabs")
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the kernels of a step one by one instead of replaying a CUDA graph")
     ap.add_argument("--sync-build", action="store_true", help="neighbour build with a host sync per step (the round-1 form)")
     ap.add_argument("--tri-per-atom", type=float, default=1350.0,

@@ -266,6 +266,11 @@ int nnmd_loss_mse(int dtype, int n_species, const int32_t *n_atoms, const void *
  * ------------------------------------------------------------------------------------- */
 int nnmd_gather_rows(int n_arrays, const void *const *src, void *const *dst, const int64_t *row_bytes,
                      const int64_t *sel, int64_t n_sel, void *stream);
+/* The same gather driven from the device: rows perm[*cursor .. *cursor + n_sel), then *cursor += n_sel.  `perm` is an
+ * epoch's frame order, `cursor` a device int64; a captured training step that starts with this call needs no per-batch
+ * arguments (replaces the DataLoader iteration of nnmd/nn/bpnn.py:321-329 without a host round trip per batch). */
+int nnmd_gather_rows_cursor(int n_arrays, const void *const *src, void *const *dst, const int64_t *row_bytes,
+                            const int64_t *perm, int64_t *cursor, int64_t n_sel, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Peer windows: the two collectives of the path as ordinary kernels over NVLink peer memory (csrc/peer.cu).

@@ -88,6 +88,8 @@ _SIGNATURES = {
                                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "nnmd_gather_rows": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_int64, ctypes.c_void_p]),
+    "nnmd_gather_rows_cursor": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "nnmd_loss_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
     "nnmd_loss_mse": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double,

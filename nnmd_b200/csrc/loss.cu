@@ -155,10 +155,11 @@ struct GatherArgs {
     unsigned char *dst[GATHER_MAX_ARRAYS];
     long long row_bytes[GATHER_MAX_ARRAYS];
     const long long *sel;
+    const long long *cursor;  // optional (device): the rows are sel[*cursor + k], the position inside an epoch's permutation
 };
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs a) {
-    const long long row = a.sel[blockIdx.x];
+    const long long row = a.sel[(a.cursor ? *a.cursor : 0) + blockIdx.x];
     for (int k = 0; k < a.n_arrays; ++k) {
         const long long nb = a.row_bytes[k];
         const unsigned char *s = a.src[k] + row * nb;
@@ -175,10 +176,34 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs a) {
     }
 }
 
+__global__ void advance_cursor_kernel(long long *cursor, long long by) { *cursor += by; }
+
 }  // namespace nnmd
+
+static int gather_rows_impl(int n_arrays, const void *const *src, void *const *dst, const int64_t *row_bytes,
+                            const int64_t *sel, int64_t *cursor, int64_t n_sel, void *stream);
 
 extern "C" int nnmd_gather_rows(int n_arrays, const void *const *src, void *const *dst, const int64_t *row_bytes,
                                 const int64_t *sel, int64_t n_sel, void *stream) {
+    return gather_rows_impl(n_arrays, src, dst, row_bytes, sel, nullptr, n_sel, stream);
+}
+
+// The batch loader of a whole epoch without the host: `perm` holds the epoch's frame order on the device, `cursor` (device
+// int64) the position of the next batch; the call gathers rows perm[*cursor .. *cursor + n_sel) and advances the cursor, so a
+// captured training step (gather included) is replayed once per batch with no per-batch arguments.
+// (reference: the DataLoader iteration of nnmd/nn/bpnn.py:321-329)
+extern "C" int nnmd_gather_rows_cursor(int n_arrays, const void *const *src, void *const *dst, const int64_t *row_bytes,
+                                       const int64_t *perm, int64_t *cursor, int64_t n_sel, void *stream) {
+    if (!cursor) return set_err(NNMD_ERR_INVALID, "gather: null cursor");
+    int r = gather_rows_impl(n_arrays, src, dst, row_bytes, perm, cursor, n_sel, stream);
+    if (r != NNMD_OK || n_sel == 0) return r;
+    advance_cursor_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long *)cursor, (long long)n_sel);
+    NNMD_LAUNCH_CHECK("advance_cursor_kernel");
+    return NNMD_OK;
+}
+
+static int gather_rows_impl(int n_arrays, const void *const *src, void *const *dst, const int64_t *row_bytes,
+                            const int64_t *sel, int64_t *cursor, int64_t n_sel, void *stream) {
     if (n_arrays < 1 || n_arrays > GATHER_MAX_ARRAYS) return set_err(NNMD_ERR_INVALID, "gather: 1..%d arrays supported", GATHER_MAX_ARRAYS);
     if (n_sel < 0 || n_sel > 0x7fffffffLL) return set_err(NNMD_ERR_INVALID, "gather: bad row count");
     if (n_sel == 0) return NNMD_OK;
@@ -191,6 +216,7 @@ extern "C" int nnmd_gather_rows(int n_arrays, const void *const *src, void *cons
         a.src[k] = (const unsigned char *)src[k]; a.dst[k] = (unsigned char *)dst[k]; a.row_bytes[k] = row_bytes[k];
     }
     a.sel = (const long long *)sel;
+    a.cursor = (const long long *)cursor;
     cudaStream_t st = (cudaStream_t)stream;
     gather_rows_kernel<<<unsigned(n_sel), 256, 0, st>>>(a);
     NNMD_LAUNCH_CHECK("gather_rows_kernel");

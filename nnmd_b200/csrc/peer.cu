@@ -69,7 +69,7 @@ __device__ __forceinline__ void signal_and_wait(char *const *peer_base, int64_t 
     __syncthreads();  // the block's stores precede the fence of the signalling threads
     const int t = threadIdx.x;
     if (t < world) {
-        __threadfence_system();
+        // release at system scope, cumulative over the block's stores through the barrier above (no separate fence needed)
         st_release_sys(arrival(peer_base[t], cap_bytes, kind, block) + rank, step);
         const uint32_t *mine = arrival(peer_base[rank], cap_bytes, kind, block) + t;
         const long long t0 = clock64();

@@ -141,7 +141,7 @@ def allreduce_sum(t: torch.Tensor) -> torch.Tensor:
 
 @dataclass
 class SlabShard:
-    """Ownership and halo plan of one rank for an x-slab decomposition."""
+    """Ownership and halo plan of one rank for a decomposition into x-slabs or, with `grid`, into px x py x pz boxes."""
 
     rank: int
     world: int
@@ -152,6 +152,8 @@ class SlabShard:
     send_idx: list = field(default_factory=list)  # per peer: indices into `owned_*` to send (None: nothing)
     edges: torch.Tensor | None = None           # (world+1,) slab boundaries on the wrapped x axis
     recv_counts: list | None = None             # atoms each peer sends here; learned once per send plan (no per-step sync)
+    grid: tuple = (1, 1, 1)                     # boxes per axis (x-slabs: (world, 1, 1))
+    edges3: list | None = None                  # per axis: (grid[ax]+1,) boundaries
 
     @property
     def n_owned(self) -> int:
@@ -180,31 +182,65 @@ class SlabShard:
             inner = [float(xs[int(p)]) for p in pos]
         return torch.tensor([-float("inf")] + inner + [float("inf")], dtype=torch.float64)
 
+    @staticmethod
+    def grid_for(world: int, lengths=(1.0, 1.0, 1.0)) -> tuple:
+        """(px, py, pz) with px*py*pz = world that minimises the total area of the internal boundaries of a box with the
+        given side lengths: the duplicated owner<->halo edge work and the halo volume both scale with that area
+        (8 ranks on a cube: 2x2x2 has 3 L^2 of boundary, 8 x-slabs have 7 L^2)."""
+        lx, ly, lz = (float(v) for v in lengths)
+        best, best_area = (world, 1, 1), None
+        for px in range(1, world + 1):
+            if world % px:
+                continue
+            for py in range(1, world // px + 1):
+                if (world // px) % py:
+                    continue
+                pz = world // (px * py)
+                area = (px - 1) * ly * lz + (py - 1) * lx * lz + (pz - 1) * lx * ly
+                if best_area is None or area < best_area - 1e-12:
+                    best, best_area = (px, py, pz), area
+        return best
+
     @classmethod
     def from_global(cls, pos: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor, rc: float, rank: int, world: int,
-                    balance: str = "work"):
+                    balance: str = "work", grid=None):
         """Domain decomposition of a structure every rank can see (synthetic benchmarks, file-based inputs).
         balance: "work" (default, see `slab_edges`) or "count" (equal atom counts).
+        grid: None = `world` x-slabs; (px, py, pz) = boxes, rank = (ix*py + iy)*pz + iz, the boundaries of every axis placed
+        by `slab_edges` on that axis' wrapped coordinate; "auto" = `grid_for(world, extent of the structure)`.
 
-        Ownership is decided on the WRAPPED x coordinate (the coordinate the kernels measure distances in);
+        Ownership is decided on the WRAPPED coordinates (the ones the kernels measure distances in);
         the positions that travel are the original ones, so every rank's K0 reproduces the single-GPU wrap bit for bit.
         """
         pos = pos.detach().cpu()
-        xw = map_positions_pbc(pos, cell.detach().cpu().to(pos.dtype), pbc.detach().cpu().to(pos.dtype))[:, 0].double()
+        pw = map_positions_pbc(pos, cell.detach().cpu().to(pos.dtype), pbc.detach().cpu().to(pos.dtype)).double()
         if balance not in ("work", "count"):
             raise ValueError("balance must be 'work' or 'count'")
-        edges = cls.slab_edges(xw, world, rc if balance == "work" else None)
-        lo, hi = edges[rank], edges[rank + 1]
-        mine = torch.nonzero((xw >= lo) & (xw < hi)).flatten()
+        if grid is None:
+            grid = (world, 1, 1)
+        elif isinstance(grid, str):
+            if grid != "auto":
+                raise ValueError("grid must be None, 'auto' or (px, py, pz)")
+            ext = (pw.max(0).values - pw.min(0).values) if pw.shape[0] else torch.ones(3, dtype=torch.float64)
+            grid = cls.grid_for(world, [float(v) for v in ext])
+        grid = tuple(int(v) for v in grid)
+        if len(grid) != 3 or grid[0] * grid[1] * grid[2] != world:
+            raise ValueError(f"grid {grid} does not have {world} boxes")
+        edges = [cls.slab_edges(pw[:, ax], grid[ax], rc if balance == "work" else None) for ax in range(3)]
+        coords = lambda r: (r // (grid[1] * grid[2]), (r // grid[2]) % grid[1], r % grid[2])
+        inside = lambda r, margin: torch.stack([(pw[:, ax] >= edges[ax][c] - margin) & (pw[:, ax] < edges[ax][c + 1] + margin)
+                                               for ax, c in enumerate(coords(r))]).all(0)
+        mine = torch.nonzero(inside(rank, 0.0)).flatten()
         send = []
         for peer in range(world):
             if peer == rank:
                 send.append(None)
                 continue
-            plo, phi = edges[peer] - rc, edges[peer + 1] + rc
-            sel = torch.nonzero((xw[mine] >= plo) & (xw[mine] < phi)).flatten()
+            sel = torch.nonzero(inside(peer, rc)[mine]).flatten()
             send.append(sel if sel.numel() else None)
-        return cls(rank, world, float(rc), pos.shape[0], mine, pos[mine].contiguous(), send, edges)
+        shard = cls(rank, world, float(rc), pos.shape[0], mine, pos[mine].contiguous(), send, edges[0])
+        shard.grid, shard.edges3 = grid, edges
+        return shard
 
     def to(self, device) -> "SlabShard":
         """Move the owned positions and the send plan to `device` (done once; the per-step exchange then stays on it)."""

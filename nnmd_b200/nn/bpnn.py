@@ -259,18 +259,31 @@ class BPNN(torch.nn.Module):
             self._plans[key] = plan
         return plan
 
-    def _step_plan(self, plan):
-        """Run one loaded plan.  One rank: the whole step is one CUDA graph.  Several ranks with a peer window
-        (dist.PeerWindow: the gradient all-reduce is a kernel over NVLink peer memory): still ONE graph -- forward, backward,
-        all-reduce, optimizer, loss accounting.  Several ranks on NCCL: forward + backward (graph 1) | all-reduce |
-        optimizer (graph 2); capturing the NCCL all-reduce hung on this stack (torch 2.11 / NCCL 2.28, 2 GPUs)."""
+    def _step_plan(self, plan, feed=None):
+        """Run one plan.  feed=None: its buffers were loaded by the caller.  feed=(dataset, perm, cursor): the batch is
+        perm[cursor : cursor + n_frames] of the dataset, gathered on the device and the cursor advanced there -- the gather
+        is part of the captured step, so a batch costs the host one graph replay and nothing else.
+
+        One rank: the whole step is one CUDA graph.  Several ranks with a peer window (dist.PeerWindow: the gradient
+        all-reduce is a kernel over NVLink peer memory): still ONE graph -- gather, forward, backward, all-reduce, optimizer,
+        loss accounting.  Several ranks on NCCL: gather + forward + backward (graph 1) | all-reduce | optimizer (graph 2);
+        capturing the NCCL all-reduce hung on this stack (torch 2.11 / NCCL 2.28, 2 GPUs)."""
         multi = self._flat_grads.world_size() > 1
+        key = None if feed is None else (plan.source_key(feed[0]), int(feed[1].data_ptr()), int(feed[2].data_ptr()))
+        if plan.graphs is not None and plan.graph_key != key:
+            plan.graphs = None  # captured for another feed (dataset, permutation buffer): capture again
+
+        def load():
+            if feed is not None:
+                plan.load_indexed(feed[0], feed[1], cursor=feed[2])
+
         if self._graphs_ok and plan.graphs is None and self._opt_ready:
             try:  # the optimizer state exists (one eager step was done): capture the step
                 torch.cuda.synchronize()
                 if not multi or self._flat_grads.graph_capturable():
                     whole = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(whole):
+                        load()
                         plan.run()
                         if multi:
                             self._flat_grads.allreduce(plan.n_frames)
@@ -281,10 +294,12 @@ class BPNN(torch.nn.Module):
                 else:
                     fwd_bwd, opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                     with torch.cuda.graph(fwd_bwd):
+                        load()
                         plan.run()
                     with torch.cuda.graph(opt, pool=fwd_bwd.pool()):
                         self.optim.step()
                     plan.graphs = (fwd_bwd, opt)
+                plan.graph_key = key
                 # a capture does not execute: fall through to the replay below
             except Exception as exc:  # capture not possible here: stay eager, loudly
                 print(f"nnmd_b200: CUDA-graph capture of the training step failed ({exc!r}); continuing without graphs")
@@ -297,6 +312,7 @@ class BPNN(torch.nn.Module):
             self._flat_grads.allreduce(plan.n_frames)  # frames are sharded across ranks: weighted by the batch sizes
             plan.graphs[1].replay()
         else:
+            load()
             plan.run()
             self._flat_grads.allreduce(plan.n_frames)
             self.optim.step()
@@ -338,15 +354,22 @@ class BPNN(torch.nn.Module):
             self._acc_carry = None  # loss sums of plans evicted during the epoch
             for plan in self._plans.values():
                 plan.acc.zero_()
-            batches = loader.index_batches(self.device)
+            # the epoch's frame order goes to the device once; every step then reads its batch through a device cursor
+            order = loader._epoch_order()
+            if getattr(self, "_perm", None) is None or self._perm.numel() < order.numel():
+                self._perm = torch.empty(max(order.numel(), 1), dtype=torch.int64, device=self.device)
+                self._cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._perm[:order.numel()].copy_(order, non_blocking=False)
+            self._cursor.zero_()
+            feed = (loader.base, self._perm, self._cursor)
+            left = order.numel()
             for _ in tqdm(range(n_steps), desc=desc, total=n_steps):
-                sel = next(batches, None)
-                if sel is None:
+                if left <= 0:
                     self._train_step_empty()
                     continue
-                plan = self._plan_for(shapes, int(sel.numel()))
-                plan.load_indexed(loader.base, sel)
-                self._step_plan(plan)
+                nb = min(loader.batch_size, left)
+                left -= nb
+                self._step_plan(self._plan_for(shapes, nb), feed)
             if world > 1:
                 import torch.distributed as td
                 td.all_reduce(self._acc_multi)

@@ -144,6 +144,7 @@ class TrainStepPlan:
         self.acc = torch.zeros(3, **f32)   # running sum over the steps of an epoch
         self.ws = torch.zeros(int(self.lib.nnmd_loss_workspace_bytes(B)), dtype=torch.uint8, device=self.device)
         self.graphs = None
+        self.graph_key = None  # what the captured step reads its batch from (BPNN._step_plan)
         # parameter / gradient pointer tables (the optimizer updates parameters in place: the pointers are stable)
         self._keep = []
         self.tables = []
@@ -169,8 +170,10 @@ class TrainStepPlan:
         self.E.copy_(energy.reshape(-1))
         self.F.copy_(forces)
 
-    def load_indexed(self, base, sel):
-        """Gather the frames `sel` (device int64) of a TrainAtomicDataset straight into the static buffers (one launch)."""
+    def load_indexed(self, base, sel, cursor=None):
+        """Gather the frames `sel` (device int64) of a TrainAtomicDataset straight into the static buffers (one launch).
+        cursor (device int64[1]): `sel` is the whole epoch's order and the batch is sel[cursor : cursor + n_frames]; the call
+        advances the cursor on the device, so it can sit inside the captured step."""
         src, dst = [], []
         for s in self.species:
             gs, dgs = base.sf_data[s]
@@ -185,8 +188,16 @@ class TrainStepPlan:
         rows = (ctypes.c_int64 * n)(*[(a.numel() // max(a.shape[0], 1)) * a.element_size() for a in src])
         sel = sel.contiguous()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.nnmd_gather_rows(n, _param_arrays(src), _param_arrays(dst), rows, _lib.ptr(sel), sel.numel(),
-                                                 _lib.stream_ptr()))
+            if cursor is not None:
+                _lib.check(self.lib.nnmd_gather_rows_cursor(n, _param_arrays(src), _param_arrays(dst), rows, _lib.ptr(sel),
+                                                            _lib.ptr(cursor), self.n_frames, _lib.stream_ptr()))
+            else:
+                _lib.check(self.lib.nnmd_gather_rows(n, _param_arrays(src), _param_arrays(dst), rows, _lib.ptr(sel), sel.numel(),
+                                                     _lib.stream_ptr()))
+
+    def source_key(self, base):
+        """Identity of the cached tensors a captured gather reads (a graph is only valid for the dataset it was captured on)."""
+        return tuple(int(t.data_ptr()) for s in self.species for t in base.sf_data[s]) + (int(base.energies.data_ptr()), int(base.forces.data_ptr()))
 
     # ---- the step
     def run(self):

@@ -109,3 +109,38 @@ def test_slab_shard_halo_and_allreduce(tmp_path):
     # slabs are cut on the wrapped coordinate
     xw = map_positions_pbc(pos, cell, pbc)[:, 0]
     assert xw[list(owned[0])].max() <= xw[list(owned[1])].min()
+
+
+def test_box_decomposition_partitions_and_covers_every_neighbour():
+    """grid="auto": 8 ranks on a cube become 2x2x2 boxes (3 L^2 of internal boundary instead of the 7 L^2 of x-slabs); the
+    boxes partition the atoms, and the rows the peers send to a rank contain every neighbour (reference pair set) of its owned
+    atoms.  The halo volume is what the duplicated owner<->halo edge work scales with: it must shrink against x-slabs."""
+    from nnmd_b200.dist import SlabShard
+    from nnmd_b200.workloads import fcc_cell
+    from oracle import nl_oracle as O3
+    assert SlabShard.grid_for(8) == (2, 2, 2) and SlabShard.grid_for(2, (1.0, 1.0, 3.0)) == (1, 1, 2)
+    assert SlabShard.grid_for(8, (100.0, 1.0, 1.0)) == (8, 1, 1)
+    pos, cell, pbc = fcc_cell(8, dtype=torch.float64)
+    pos = pos - 2.0
+    n = pos.shape[0]
+    pairs = O3.pairs(pos, cell, pbc, 6.0)
+    world = 8
+    boxes = [SlabShard.from_global(pos, cell, pbc, rc=6.0, rank=r, world=world, grid="auto") for r in range(world)]
+    slabs = [SlabShard.from_global(pos, cell, pbc, rc=6.0, rank=r, world=world) for r in range(world)]
+    assert boxes[0].grid == (2, 2, 2) and slabs[0].grid == (8, 1, 1)
+    owned = torch.cat([b.owned_idx for b in boxes])
+    assert owned.numel() == n and owned.unique().numel() == n
+    counts = [b.n_owned for b in boxes]
+    assert max(counts) - min(counts) <= n // 20  # the eight octants are images of one another
+    halo = lambda shards: sum(0 if s is None else int(s.numel()) for sh in shards for s in sh.send_idx)
+    assert halo(boxes) < 0.75 * halo(slabs)
+    nbrs = {}
+    for i, j in pairs:
+        nbrs.setdefault(int(i), set()).add(int(j))
+    for r, b in enumerate(boxes):
+        have = set(b.owned_idx.tolist())
+        for q, peer in enumerate(boxes):
+            if q != r and peer.send_idx[r] is not None:
+                have |= set(peer.owned_idx[peer.send_idx[r]].tolist())
+        for i in b.owned_idx.tolist():
+            assert nbrs.get(i, set()) <= have
