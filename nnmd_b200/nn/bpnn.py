@@ -357,19 +357,27 @@ class BPNN(torch.nn.Module):
             # the epoch's frame order goes to the device once; every step then reads its batch through a device cursor
             order = loader._epoch_order()
             if getattr(self, "_perm", None) is None or self._perm.numel() < order.numel():
-                self._perm = torch.empty(max(order.numel(), 1), dtype=torch.int64, device=self.device)
+                # sized for the whole dataset: a longer epoch later (train after a short warm-up subset) must not move
+                # the buffer, or every captured step would have to be captured again
+                self._perm = torch.empty(max(order.numel(), len(loader.base), 1), dtype=torch.int64, device=self.device)
                 self._cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
             self._perm[:order.numel()].copy_(order, non_blocking=False)
             self._cursor.zero_()
             feed = (loader.base, self._perm, self._cursor)
             left = order.numel()
-            for _ in tqdm(range(n_steps), desc=desc, total=n_steps):
+            eager_gather = os.environ.get("NNMD_EAGER_GATHER", "0") == "1"  # A/B: the batch gathered by a per-step host call
+            for k in tqdm(range(n_steps), desc=desc, total=n_steps):
                 if left <= 0:
                     self._train_step_empty()
                     continue
                 nb = min(loader.batch_size, left)
                 left -= nb
-                self._step_plan(self._plan_for(shapes, nb), feed)
+                plan = self._plan_for(shapes, nb)
+                if eager_gather:
+                    plan.load_indexed(loader.base, self._perm[k * loader.batch_size:k * loader.batch_size + nb])
+                    self._step_plan(plan)
+                else:
+                    self._step_plan(plan, feed)
             if world > 1:
                 import torch.distributed as td
                 td.all_reduce(self._acc_multi)

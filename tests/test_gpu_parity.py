@@ -831,7 +831,7 @@ def test_edge_kernel_forms_agree(with_grad, kind):
     """The moment form of K3e (default, nnmd_set_option("edge_form", 1): B = b dE/dx and V = b E come out of ONE moment per
     centre, scaled by the edge's own radial factor when the edge retires) against the derivative-record form of round 1
     (edge_form 0): same sums in a different association, so G, dG and the fused forces agree to fp32 round-off
-    (column-normwise 2e-6; the parity tests hold each form to the oracle separately through the default).  Multi-row
+    (column-normwise 5e-6; the parity tests hold each form to the oracle separately through the default).  Multi-row
     workload and a tiny one where most warps get no row at all (termination path); G4 and G5."""
     from nnmd_b200 import _lib
     from nnmd_b200.engine import fused_force
@@ -855,11 +855,11 @@ def test_edge_kernel_forms_agree(with_grad, kind):
                 torch.cuda.synchronize()
                 assert int(flag.item()) == 0
                 out.append((G, dG, F))
-            assert col_relerr(out[1][0], out[0][0], 1) < 2e-6
+            assert col_relerr(out[1][0], out[0][0], 1) < 5e-6
             fmax = float(out[0][2].abs().max())
             assert float((out[1][2] - out[0][2]).abs().max()) < 5e-6 * fmax
             if with_grad:
-                assert col_relerr(out[1][1], out[0][1], 1) < 2e-6
+                assert col_relerr(out[1][1], out[0][1], 1) < 5e-6
     finally:
         _lib.set_option("edge_form", 1)
 
