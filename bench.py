@@ -446,20 +446,21 @@ def run_ours(args):
     achieved = bytes_per_atom * n_owned / (ang_ms_per_launch * 1e-3) / 1e9 if ang_ms_per_launch > 0 else 0.0
     traffic = None
     try:  # DRAM bytes of ONE launch of this kernel from the committed ncu --set full capture (scaled if the cell differs)
-        with open(os.path.join(ROOT, "profiles", "r2_k3e_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2_k3m_traffic.json")) as fh:
             tr = json.load(fh)
         traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (n_owned / tr["atoms"])
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "angular_edge4_kernel<true,true> (K3e)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "angular_edgem_kernel<true,true,uint16_t> (K3e, moment form)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "traffic_source": "profiles/r2_k3e_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                "traffic_source": "profiles/r2_k3m_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                 "ms_per_launch": ang_ms_per_launch, "algorithmic_bytes_per_atom": bytes_per_atom,
                 "note": "K3e is bound by the FP32 FMA pipe and the SFU (ex2), not by HBM: see fp32_pipe/sfu_pipe, DESIGN.md, profiles/",
                 "stage_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()}}
     # compute-side view of the same kernel against the MEASURED pipe peaks (tools/microbench.cu -> profiles/microbench_r1.json):
-    # one (edge, third atom, function) costs 11 FMA-pipe lane-ops and 1.5 ex2; records per atom
-    # = closed ordered (j,k) pairs / 2 = triangles-per-atom (3 edges x 1/3 ownership)
+    # one (edge, third atom, function) costs 9 FMA-pipe lane-ops in the moment form of K3e (3 ladder multiplications + 6
+    # accumulations; the round-1 form needed 11) and about one ex2 (3 per record and lane for 4 functions, plus the record's
+    # own 15); records per atom = closed ordered (j,k) pairs / 2 = triangles-per-atom (3 edges x 1/3 ownership)
     try:
         with open(os.path.join(ROOT, "profiles", "microbench_r1.json")) as fh:
             mb = json.load(fh)
@@ -467,10 +468,14 @@ def run_ours(args):
         mb = None
     if mb is not None and ang_ms_per_launch > 0 and args.tri_per_atom > 0:
         rec = args.tri_per_atom * (mean_nbrs / 78.0) ** 2 * n_owned  # free surfaces of the wrap-only cell thin the rows
-        fma_ops = rec * n_ang * 11.0
-        sfu_ops = rec * n_ang * 1.5
+        fma_ops = rec * n_ang * 9.0
+        sfu_ops = rec * n_ang * 1.0
         roofline["fp32_pipe"] = {"achieved_lane_ops_per_s": fma_ops / (ang_ms_per_launch * 1e-3), "peak": mb["ffma_lane_ops_per_s"],
                                  "frac": fma_ops / (ang_ms_per_launch * 1e-3) / mb["ffma_lane_ops_per_s"],
+                                 "ops_per_record_and_function": 9,
+                                 "frac_in_round1_op_model": rec * n_ang * 11.0 / (ang_ms_per_launch * 1e-3) / mb["ffma_lane_ops_per_s"],
+                                 "note": "frac counts the operations this kernel executes (9); frac_in_round1_op_model prices the same "
+                                         "records at the 11 operations of the round-1 kernel (0.456 then), i.e. the speed-up in its units",
                                  "peak_source": "measured, tools/microbench.cu (FFMA and FFMA2 give the same lane rate)"}
         roofline["sfu_pipe"] = {"achieved_lane_ops_per_s": sfu_ops / (ang_ms_per_launch * 1e-3), "peak": mb["mufu_ex2_lane_ops_per_s"],
                                 "frac": sfu_ops / (ang_ms_per_launch * 1e-3) / mb["mufu_ex2_lane_ops_per_s"]}

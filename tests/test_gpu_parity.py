@@ -838,11 +838,11 @@ def test_edge_kernel_forms_agree(with_grad, kind):
     from nnmd_b200.features.calculate_sf import get_plan, raw_descriptors
     from nnmd_b200.neighbor import build_neighbor_list
     from nnmd_b200.workloads import bench_table, fcc_cell
-    sfd = bench_table()
-    sfd = dict(sfd, features=[f if f == 2 else kind for f in sfd["features"]])
-    plan = get_plan(sfd, torch.float32, torch.device(DEV))
     try:
-        for ncell in (7, 1):
+        for ncell in (7, 1):  # a multi-row workload and a tiny one
+            sfd = bench_table()
+            sfd = dict(sfd, features=[f if f == 2 else kind for f in sfd["features"]])
+            plan = get_plan(sfd, torch.float32, torch.device(DEV))
             pos, cell, pbc = fcc_cell(ncell, dtype=torch.float32)
             nl = build_neighbor_list(pos[None].to(DEV), cell.to(DEV), pbc.to(DEV), 6.0)
             torch.manual_seed(ncell)
@@ -860,6 +860,22 @@ def test_edge_kernel_forms_agree(with_grad, kind):
             assert float((out[1][2] - out[0][2]).abs().max()) < 5e-6 * fmax
             if with_grad:
                 assert col_relerr(out[1][1], out[0][1], 1) < 5e-6
+        # rows of more than 256 entries (rc = 12 on a 500-atom cluster): the queue of K3e holds 15 + 15 bit entries instead of
+        # 8 + 8.  The truth is the fp64 vertex-centric kernel on the same positions; the moment form sums per edge before it
+        # adds to the row, which keeps 10^5-term sums at 5e-6 (measured) where the round-1 form reaches 4e-5.
+        sfd = bench_table(rc=12.0)
+        sfd = dict(sfd, features=[f if f == 2 else kind for f in sfd["features"]])
+        pos, cell, pbc = fcc_cell(5, dtype=torch.float32)
+        nl = build_neighbor_list(pos[None].to(DEV), cell.to(DEV), pbc.to(DEV), 12.0)
+        assert nl.max_row > 256
+        nl64 = build_neighbor_list(pos[None].double().to(DEV), cell.double().to(DEV), pbc.double().to(DEV), 12.0)
+        G64, dG64, _ = raw_descriptors(get_plan(sfd, torch.float64, torch.device(DEV)), nl64, with_grad=True)
+        _lib.set_option("edge_form", 1)
+        G, dG, flag = raw_descriptors(get_plan(sfd, torch.float32, torch.device(DEV)), nl, with_grad=with_grad)
+        torch.cuda.synchronize()
+        assert int(flag.item()) == 0 and col_relerr(G, G64, 1) < 1e-5
+        if with_grad:
+            assert col_relerr(dG, dG64, 1) < 2e-5
     finally:
         _lib.set_option("edge_form", 1)
 
