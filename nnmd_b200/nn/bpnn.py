@@ -259,19 +259,44 @@ class BPNN(torch.nn.Module):
             self._plans[key] = plan
         return plan
 
-    def _step_plan(self, plan, feed=None):
-        """Run one plan.  feed=None: its buffers were loaded by the caller.  feed=(dataset, perm, cursor): the batch is
+    def _step_plan(self, plan, feed=None, repeat: int = 1):
+        """Run one plan (`repeat` > 1: that many consecutive steps of it -- needs a feed).  feed=None: its buffers were loaded by the caller.  feed=(dataset, perm, cursor): the batch is
         perm[cursor : cursor + n_frames] of the dataset, gathered on the device and the cursor advanced there -- the gather
         is part of the captured step, so a batch costs the host one graph replay and nothing else.
 
         One rank: the whole step is one CUDA graph.  Several ranks with a peer window (dist.PeerWindow: the gradient
         all-reduce is a kernel over NVLink peer memory): still ONE graph -- gather, forward, backward, all-reduce, optimizer,
         loss accounting.  Several ranks on NCCL: gather + forward + backward (graph 1) | all-reduce | optimizer (graph 2);
-        capturing the NCCL all-reduce hung on this stack (torch 2.11 / NCCL 2.28, 2 GPUs)."""
+        capturing the NCCL all-reduce hung on this stack (torch 2.11 / NCCL 2.28, 2 GPUs).
+
+        repeat > 1 (one-graph case only): ONE graph holds `repeat` whole steps -- a 0.12 ms step is launch-bound on the host
+        as soon as several ranks share the box's cores and wait for each other in every all-reduce; a chunk of steps per
+        replay takes the host out of the loop."""
         multi = self._flat_grads.world_size() > 1
         key = None if feed is None else (plan.source_key(feed[0]), int(feed[1].data_ptr()), int(feed[2].data_ptr()))
         if plan.graphs is not None and plan.graph_key != key:
-            plan.graphs = None  # captured for another feed (dataset, permutation buffer): capture again
+            plan.graphs, plan.chunk_graphs = None, {}  # captured for another feed (dataset, permutation buffer): capture again
+        if repeat > 1:
+            if plan.graphs is None or len(plan.graphs) != 1 or feed is None:
+                for _ in range(repeat):  # no single-graph step (yet): one at a time
+                    self._step_plan(plan, feed)
+                return
+            g = plan.chunk_graphs.get(repeat)
+            if g is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=plan.graphs[0].pool()):
+                    for _ in range(repeat):
+                        plan.load_indexed(feed[0], feed[1], cursor=feed[2])
+                        plan.run()
+                        if multi:
+                            self._flat_grads.allreduce(plan.n_frames)
+                        self.optim.step()
+                        if multi:
+                            self._acc_multi.addcdiv_(plan.out, self._flat_grads.count, value=float(plan.n_frames))
+                plan.chunk_graphs[repeat] = g
+            g.replay()
+            return
 
         def load():
             if feed is not None:
@@ -365,19 +390,24 @@ class BPNN(torch.nn.Module):
             self._cursor.zero_()
             feed = (loader.base, self._perm, self._cursor)
             left = order.numel()
-            eager_gather = os.environ.get("NNMD_EAGER_GATHER", "0") == "1"  # A/B: the batch gathered by a per-step host call
-            for k in tqdm(range(n_steps), desc=desc, total=n_steps):
+            chunk = max(int(os.environ.get("NNMD_STEP_CHUNK", "8")), 1)  # full-batch steps per graph replay
+            bar = iter(tqdm(range(n_steps), desc=desc, total=n_steps))  # progress bar only with DEBUG set (as the reference)
+            k = 0
+            while k < n_steps:
                 if left <= 0:
                     self._train_step_empty()
+                    k += 1
+                    next(bar, None)
                     continue
                 nb = min(loader.batch_size, left)
-                left -= nb
                 plan = self._plan_for(shapes, nb)
-                if eager_gather:
-                    plan.load_indexed(loader.base, self._perm[k * loader.batch_size:k * loader.batch_size + nb])
-                    self._step_plan(plan)
-                else:
-                    self._step_plan(plan, feed)
+                rep = chunk if (chunk > 1 and left >= chunk * loader.batch_size and plan.graphs is not None
+                                and len(plan.graphs) == 1) else 1
+                self._step_plan(plan, feed, repeat=rep)
+                left -= nb * rep
+                k += rep
+                for _ in range(rep):
+                    next(bar, None)
             if world > 1:
                 import torch.distributed as td
                 td.all_reduce(self._acc_multi)

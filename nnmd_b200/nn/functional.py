@@ -145,6 +145,7 @@ class TrainStepPlan:
         self.ws = torch.zeros(int(self.lib.nnmd_loss_workspace_bytes(B)), dtype=torch.uint8, device=self.device)
         self.graphs = None
         self.graph_key = None  # what the captured step reads its batch from (BPNN._step_plan)
+        self.chunk_graphs = {}  # repeat count -> one graph holding that many consecutive steps
         # parameter / gradient pointer tables (the optimizer updates parameters in place: the pointers are stable)
         self._keep = []
         self.tables = []

@@ -411,3 +411,35 @@ def test_gather_rows_matches_index_select():
     assert lib.nnmd_gather_rows(n, P(src), P(dst), bad_rows, _lib.ptr(sel), sel.numel(), _lib.stream_ptr()) != 0
     assert b"multiple of 4" in lib.nnmd_last_error()
     assert lib.nnmd_gather_rows(n, P(src), P(dst), rows, _lib.ptr(sel), 0, _lib.stream_ptr()) == 0
+
+
+def test_chunked_graph_replay_is_bit_identical_to_single_steps(monkeypatch):
+    """Eight consecutive full-batch steps in ONE graph replay (device cursor over the epoch's frame order: `_step_plan`
+    with repeat) against one replay per step (NNMD_STEP_CHUNK=1): same kernels on the same batches in the same order, so the
+    epoch losses and the weights are bit-identical -- over shuffled epochs with 21 full batches and a ragged last one."""
+    from nnmd_b200.nn import BPNN, TrainAtomicDataset
+    from nnmd_b200.nn.bpnn import batch_loader
+    torch.manual_seed(3)
+    M, N, Fd = 21 * 6 + 4, 5, 9
+    g = torch.rand(M, N, Fd, device=DEV)
+    dg = torch.randn(M, N, Fd, 3, device=DEV)
+    E = torch.rand(M, 1, device=DEV)
+    Fr = torch.randn(M, N, 3, device=DEV) * 0.1
+    cfg = dict(atom_species=["X"], input_sizes=[Fd], hidden_sizes=[[12, 8]], learning_rate=0.01, l2_regularization=1e-4,
+               e_loss_coeff=1.0, f_loss_coeff=0.5, load_models=False, path="", optimizer="adamw", batch_size=6, epochs=1)
+    results = []
+    for chunk in ("8", "1"):
+        monkeypatch.setenv("NNMD_STEP_CHUNK", chunk)
+        torch.manual_seed(5)
+        net = BPNN(dtype=torch.float32)
+        net.config(cfg)
+        ds = TrainAtomicDataset({"X": (g.clone().requires_grad_(True), dg)}, E, Fr, {})
+        loader = batch_loader(ds, 6, shuffle=True)
+        losses = [[float(v) for v in net._train_loop(ep, loader)] for ep in range(3)]
+        used = [sorted(p.chunk_graphs) for p in net._plans.values()]
+        results.append((losses, [p.detach().clone() for p in net.atomic_nets[0].parameters()], used))
+    (la, pa, ua), (lb, pb, ub) = results
+    assert [8] in ua and all(u == [] for u in ub)  # the chunked run did replay eight-step graphs
+    assert la == lb
+    for a, b in zip(pa, pb):
+        assert torch.equal(a, b)

@@ -94,7 +94,7 @@ def train_bench(config: str, dev, rank: int, world: int, frames: int = 20000, ba
             done += n
         return last
 
-    first = run(max(warmup, 3))
+    first = run(max(warmup, 3) + len(loader))  # at least one whole epoch: every graph of the step (single, chunk of 8) is captured before the clock starts
     torch.cuda.synchronize()
     if world > 1:
         td.barrier()
