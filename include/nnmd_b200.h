@@ -296,6 +296,10 @@ void nnmd_peer_destroy(nnmd_peer *p);
 int64_t nnmd_peer_capacity(const nnmd_peer *p);
 int nnmd_peer_status(nnmd_peer *p, int *status);
 int nnmd_peer_allreduce_weighted_f32(nnmd_peer *p, float *buf, int64_t n, void *stream);
+/* the same with the rank's weight b_r as an argument (it is what gets summed into buf[n-1]) and, optionally, the loss
+ * accounting of the step: loss_acc[0..3) += loss_in[0..3) * b_r / sum_r b_r (both NULL to skip) */
+int nnmd_peer_allreduce_step_f32(nnmd_peer *p, float *buf, int64_t n, float weight, const float *loss_in, float *loss_acc,
+                                 void *stream);
 /* plain sum of buf[0..n) over the ranks, in place (the total energy of a spatially sharded structure) */
 int nnmd_peer_allreduce_sum_f32(nnmd_peer *p, float *buf, int64_t n, void *stream);
 int nnmd_peer_halo_exchange(nnmd_peer *p, const void *own, int64_t n_own, const int64_t *send_idx, const int32_t *dst_peer,

@@ -102,6 +102,8 @@ _SIGNATURES = {
     "nnmd_peer_capacity": (ctypes.c_int64, [ctypes.c_void_p]),
     "nnmd_peer_status": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
     "nnmd_peer_allreduce_weighted_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "nnmd_peer_allreduce_step_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p]),
     "nnmd_peer_allreduce_sum_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "nnmd_peer_halo_exchange": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,

@@ -91,8 +91,12 @@ __device__ __forceinline__ void signal_and_wait(char *const *peer_base, int64_t 
 // loads of ALL ranks for its elements, then adds them up in rank order.
 constexpr int PEER_AR_THREADS = 512;
 template <bool WEIGHTED>
+// weight_arg >= 0: the rank's weight comes as an argument (and is what ends up summed in buf[n-1]) instead of being read from
+// buf[n-1]; loss_in / loss_acc (optional, 3 floats): loss_acc += loss_in * b_r / sum_r b_r, this rank's share of the
+// global-batch loss -- both fold the two one-element kernels around the all-reduce of the training step into it.
 __global__ void __launch_bounds__(PEER_AR_THREADS) peer_allreduce_kernel(char *const *peer_base, int64_t cap_bytes, int rank, int world,
-                                                                         float *buf, int64_t n, int64_t per, uint32_t *status) {
+                                                                         float *buf, int64_t n, int64_t per, uint32_t *status,
+                                                                         float weight_arg, const float *loss_in, float *loss_acc) {
     const int b = blockIdx.x;
     __shared__ uint32_t s_step;
     __shared__ const float *s_src[PEER_MAX_WORLD];
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(PEER_AR_THREADS) peer_allreduce_kernel(char *c
     if (threadIdx.x < PEER_MAX_WORLD)
         s_src[threadIdx.x] = threadIdx.x < world ? reinterpret_cast<const float *>(peer_base[threadIdx.x] + (step & 1) * cap_bytes) : nullptr;
     const int64_t lo = int64_t(b) * per, hi = min(n, lo + per);
-    const float bw = WEIGHTED ? buf[n - 1] : 1.f;
+    const float bw = WEIGHTED ? (weight_arg >= 0.f ? weight_arg : buf[n - 1]) : 1.f;
     float *mine = reinterpret_cast<float *>(base + (step & 1) * cap_bytes);
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) mine[i] = (WEIGHTED && i == n - 1) ? bw : buf[i] * bw;
     if (WEIGHTED && threadIdx.x == 0) mine[n + b] = bw;
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(PEER_AR_THREADS) peer_allreduce_kernel(char *c
 #pragma unroll
         for (int r = 0; r < PEER_MAX_WORLD; ++r) wsum += w[r];
         inv = wsum > 0.f ? 1.f / wsum : 0.f;
+        if (loss_acc != nullptr && b == 0 && threadIdx.x < 3) loss_acc[threadIdx.x] += loss_in[threadIdx.x] * bw * inv;
     }
     for (int64_t i = i0; i < hi; i += blockDim.x) {
         if (i != i0) {
@@ -246,7 +251,8 @@ extern "C" int nnmd_peer_status(nnmd_peer *p, int *status) {
     return NNMD_OK;
 }
 
-static int peer_allreduce(nnmd_peer *p, float *buf, int64_t n, bool weighted, void *stream) {
+static int peer_allreduce(nnmd_peer *p, float *buf, int64_t n, bool weighted, void *stream, float weight = -1.f,
+                          const float *loss_in = nullptr, float *loss_acc = nullptr) {
     if (!p || !buf || n < (weighted ? 2 : 1)) return set_err(NNMD_ERR_INVALID, "peer_allreduce: bad arguments");
     // mailbox: payload n floats, then the weight once per block (see the kernel)
     int blocks = int(std::min<int64_t>(PEER_MAX_BLOCKS, (n + PEER_AR_THREADS - 1) / PEER_AR_THREADS));
@@ -255,12 +261,19 @@ static int peer_allreduce(nnmd_peer *p, float *buf, int64_t n, bool weighted, vo
         return set_err(NNMD_ERR_CAPACITY, "peer_allreduce: %lld floats exceed the window (%lld bytes per parity)", (long long)n, (long long)p->cap_bytes);
     const int64_t per = (n + blocks - 1) / blocks;
     cudaStream_t st = (cudaStream_t)stream;
-    if (weighted) peer_allreduce_kernel<true><<<blocks, PEER_AR_THREADS, 0, st>>>(p->d_peer_base, p->cap_bytes, p->rank, p->world, buf, n, per, p->d_status);
-    else peer_allreduce_kernel<false><<<blocks, PEER_AR_THREADS, 0, st>>>(p->d_peer_base, p->cap_bytes, p->rank, p->world, buf, n, per, p->d_status);
+    if (weighted) peer_allreduce_kernel<true><<<blocks, PEER_AR_THREADS, 0, st>>>(p->d_peer_base, p->cap_bytes, p->rank, p->world, buf, n, per, p->d_status, weight, loss_in, loss_acc);
+    else peer_allreduce_kernel<false><<<blocks, PEER_AR_THREADS, 0, st>>>(p->d_peer_base, p->cap_bytes, p->rank, p->world, buf, n, per, p->d_status, -1.f, nullptr, nullptr);
     NNMD_LAUNCH_CHECK("peer_allreduce_kernel");
     return NNMD_OK;
 }
 extern "C" int nnmd_peer_allreduce_weighted_f32(nnmd_peer *p, float *buf, int64_t n, void *stream) { return peer_allreduce(p, buf, n, true, stream); }
+// the all-reduce of one training step: weight = frames of this rank's batch (>= 0); loss_in (3 floats: this rank's batch-mean
+// losses) is added to loss_acc with the rank's share of the global batch; both may be NULL
+extern "C" int nnmd_peer_allreduce_step_f32(nnmd_peer *p, float *buf, int64_t n, float weight, const float *loss_in, float *loss_acc,
+                                            void *stream) {
+    if (weight < 0.f || (loss_in == nullptr) != (loss_acc == nullptr)) return set_err(NNMD_ERR_INVALID, "peer_allreduce_step: bad arguments");
+    return peer_allreduce(p, buf, n, true, stream, weight, loss_in, loss_acc);
+}
 extern "C" int nnmd_peer_allreduce_sum_f32(nnmd_peer *p, float *buf, int64_t n, void *stream) { return peer_allreduce(p, buf, n, false, stream); }
 
 // One halo exchange: push the n_send rows named by send_idx into the peers' staging areas, synchronise, then assemble

@@ -97,6 +97,12 @@ class PeerWindow:
         with torch.cuda.device(buf.device):
             _lib.check(self._lib.nnmd_peer_allreduce_weighted_f32(self.handle, _lib.ptr(buf), buf.numel(), _lib.stream_ptr()))
 
+    def allreduce_step(self, buf: torch.Tensor, weight: float, loss_in=None, loss_acc=None) -> None:
+        from . import _lib
+        with torch.cuda.device(buf.device):
+            _lib.check(self._lib.nnmd_peer_allreduce_step_f32(self.handle, _lib.ptr(buf), buf.numel(), float(weight), _lib.ptr(loss_in),
+                                                              _lib.ptr(loss_acc), _lib.stream_ptr()))
+
     def allreduce_sum(self, buf: torch.Tensor) -> None:
         from . import _lib
         with torch.cuda.device(buf.device):
@@ -357,27 +363,30 @@ class FlatGradients:
     def world_size(self) -> int:
         return _world()[1]
 
-    def allreduce(self, n_frames: int | None = None) -> None:
+    def allreduce(self, n_frames: int | None = None, loss_in=None, loss_acc=None) -> bool:
         """Global-batch gradient from per-rank batch-mean gradients.  n_frames = frames of THIS rank's batch (0 when the
-        rank has none left this step; None = equal batches everywhere, plain average).  No-op on one rank."""
+        rank has none left this step; None = equal batches everywhere, plain average).  No-op on one rank.
+        loss_in / loss_acc (float32 (3,) on the device): on the peer-window route the kernel also adds this rank's share of the
+        global-batch loss, loss_in * b_r / sum_r b_r, to loss_acc; returns True when it did (else the caller does)."""
         rank, world = _world()
         if world == 1:
-            return
+            return False
         if n_frames is None:
             td.all_reduce(self.flat, op=td.ReduceOp.SUM)
             self.flat /= world
-            return
-        self.count.fill_(float(n_frames))
+            return False
         if self.window is None and not self._window_tried:
             self._window_tried = True
             if self.buf.dtype == torch.float32:
                 self.window = PeerWindow.create(4 * (self.buf.numel() + 64), self.buf.device)
         if self.window is not None:  # one kernel over NVLink peer memory, capturable into the step's CUDA graph
-            self.window.allreduce_weighted(self.buf)
-            return
+            self.window.allreduce_step(self.buf, float(n_frames), loss_in, loss_acc)
+            return loss_acc is not None
+        self.count.fill_(float(n_frames))
         self.flat *= float(n_frames)
         td.all_reduce(self.buf, op=td.ReduceOp.SUM)
         self.flat /= self.count
+        return False
 
     def graph_capturable(self) -> bool:
         """True when `allreduce` is plain kernels on the current stream (one rank, or a connected peer window)."""

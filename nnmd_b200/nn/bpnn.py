@@ -289,11 +289,9 @@ class BPNN(torch.nn.Module):
                     for _ in range(repeat):
                         plan.load_indexed(feed[0], feed[1], cursor=feed[2])
                         plan.run()
-                        if multi:
-                            self._flat_grads.allreduce(plan.n_frames)
-                        self.optim.step()
-                        if multi:
+                        if multi and not self._flat_grads.allreduce(plan.n_frames, plan.out, self._acc_multi):
                             self._acc_multi.addcdiv_(plan.out, self._flat_grads.count, value=float(plan.n_frames))
+                        self.optim.step()
                 plan.chunk_graphs[repeat] = g
             g.replay()
             return
@@ -310,11 +308,10 @@ class BPNN(torch.nn.Module):
                     with torch.cuda.graph(whole):
                         load()
                         plan.run()
-                        if multi:
-                            self._flat_grads.allreduce(plan.n_frames)
-                        self.optim.step()
-                        if multi:  # this rank's share of the global-batch loss: out * b_r / sum_r b_r
+                        # this rank's share of the global-batch loss, out * b_r / sum_r b_r, is added by the all-reduce kernel
+                        if multi and not self._flat_grads.allreduce(plan.n_frames, plan.out, self._acc_multi):
                             self._acc_multi.addcdiv_(plan.out, self._flat_grads.count, value=float(plan.n_frames))
+                        self.optim.step()
                     plan.graphs = (whole,)
                 else:
                     fwd_bwd, opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
