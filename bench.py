@@ -415,10 +415,11 @@ def run_ours(args):
         torch.cuda.empty_cache()
         train = {}
         for cfg_name in ("li", "bin"):
-            dataset = bench_train.build_dataset(cfg_name, args.train_frames, dev, rank, world)
-            entry = bench_train.train_bench(cfg_name, dev, rank, world, args.train_frames, 500, args.train_steps, 5, "weak", dataset)
+            # weak scaling keeps the work PER GPU fixed: --train-frames frames (and one batch of 500) on every rank
+            dataset = bench_train.build_dataset(cfg_name, args.train_frames * world, dev, rank, world)
+            entry = bench_train.train_bench(cfg_name, dev, rank, world, args.train_frames * world, 500, args.train_steps, 5, "weak", dataset)
             if world > 1:  # the reference's optimisation: global batch stays 500 frames
-                strong = bench_train.train_bench(cfg_name, dev, rank, world, args.train_frames, 500, args.train_steps, 5, "strong", dataset)
+                strong = bench_train.train_bench(cfg_name, dev, rank, world, args.train_frames * world, 500, args.train_steps, 5, "strong", dataset)
                 entry["strong"] = {k: strong[k] for k in ("global_batch_frames", "ms_per_step", "frames_per_s", "atoms_per_s")}
             if world == 1 and rank == 0 and not args.no_cpu_baseline:
                 entry["cpu_baseline"] = bench_train.reference_train_baseline(cfg_name, *dataset)

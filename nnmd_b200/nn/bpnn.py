@@ -225,15 +225,49 @@ class BPNN(torch.nn.Module):
         self._flat_grads.allreduce(0)
         self.optim.step()
 
-    def _epoch_steps(self, n_local: int) -> int:
-        """Steps per epoch = the longest rank's batch count (one scalar all-reduce per epoch): per-rank frame shards can
-        differ by one frame, hence by one batch, and every step issues a collective."""
+    def _epoch_steps(self, n_local: int, loader=None) -> int:
+        """Steps per epoch = the longest rank's batch count: per-rank frame shards can differ by one frame, hence by one
+        batch, and every step issues a collective.  One scalar all-reduce (and one host sync) per LOADER, not per epoch: the
+        answer is remembered per loader object -- every rank runs the same program, so the same loader is met again on all
+        ranks at once (a weak dictionary: a freed loader cannot alias a new one)."""
         if dist._world()[1] == 1:
             return n_local
+        import weakref
         import torch.distributed as td
+        cache = getattr(self, "_steps_cache", None)
+        if cache is None:
+            cache = self._steps_cache = weakref.WeakKeyDictionary()
+        try:
+            hit = cache.get(loader) if loader is not None else None
+        except TypeError:  # not weak-referenceable
+            hit, loader = None, None
+        if hit is not None and hit[0] == n_local:
+            return hit[1]
         t = torch.tensor([n_local], dtype=torch.int64, device=self.device)
         td.all_reduce(t, op=td.ReduceOp.MAX)
-        return int(t.item())
+        n = int(t.item())
+        if loader is not None:
+            cache[loader] = (n_local, n)
+        return n
+
+    def _upload_order(self, order: torch.Tensor) -> None:
+        """The epoch's frame order -> self._perm without a host sync: two pinned staging buffers used in turn, each guarded
+        by an event (the host may be a whole epoch ahead of the device)."""
+        n = order.numel()
+        st = getattr(self, "_perm_stage", None)
+        if st is None or st[0][0].numel() < n:
+            cap = max(n, self._perm.numel())
+            st = self._perm_stage = [[torch.empty(cap, dtype=torch.int64).pin_memory(), None] for _ in range(2)]
+            self._perm_turn = 0
+        buf, ev = st[self._perm_turn]
+        if ev is not None:
+            ev.synchronize()
+        buf[:n].copy_(order)
+        self._perm[:n].copy_(buf[:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st[self._perm_turn][1] = ev
+        self._perm_turn ^= 1
 
     # ---- fused step: K6 -> K4c -> K8 -> K4c' -> K7 on static buffers, replayed from CUDA graphs
     def _fused_ok(self, g, dG) -> bool:
@@ -365,7 +399,7 @@ class BPNN(torch.nn.Module):
             # gradients live in one flat buffer: a single in-place all-reduce per step when frames are sharded
             self._flat_grads = FlatGradients([p for net in self.atomic_nets for p in net.parameters()])
             self._plans, self._opt_ready, self._acc_carry = {}, False, None
-        n_steps = self._epoch_steps(len(loader))
+        n_steps = self._epoch_steps(len(loader), loader)
         if getattr(self, "_acc_multi", None) is None:  # persistent: the captured step adds into it
             self._acc_multi = torch.zeros(3, device=self.device)
         self._acc_multi.zero_()
@@ -383,7 +417,7 @@ class BPNN(torch.nn.Module):
                 # the buffer, or every captured step would have to be captured again
                 self._perm = torch.empty(max(order.numel(), len(loader.base), 1), dtype=torch.int64, device=self.device)
                 self._cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
-            self._perm[:order.numel()].copy_(order, non_blocking=False)
+            self._upload_order(order)
             self._cursor.zero_()
             feed = (loader.base, self._perm, self._cursor)
             left = order.numel()
@@ -406,9 +440,7 @@ class BPNN(torch.nn.Module):
                 for _ in range(rep):
                     next(bar, None)
             if world > 1:
-                import torch.distributed as td
-                td.all_reduce(self._acc_multi)
-                tot = self._acc_multi / n_steps
+                tot = dist.allreduce_sum(self._acc_multi.clone()) / n_steps  # peer-window kernel where available: no host sync
                 return tot[0], tot[1], tot[2]
             for plan in self._plans.values():
                 tot += plan.acc
