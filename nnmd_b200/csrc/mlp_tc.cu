@@ -70,8 +70,14 @@ __device__ __forceinline__ void fill_frags(float4 *dst, const float *W, int ld_n
     }
 }
 
+// warps per block: they share one copy of the weight fragments (160 kB for 96-64-64-1), so the warps of ONE block are all the
+// memory-level parallelism an SM gets for the dG rows of the fused epilogue
+#ifndef NNMD_TC_WARPS
+#define NNMD_TC_WARPS 16  // 8: 1.50 ms, 12: 1.23, 16: 1.17, 20: 1.16 (spills), 24: 1.29 per 1M atoms (fused tail, 96-64-64-1)
+#endif
+constexpr int TC_WARPS = NNMD_TC_WARPS;
 template <int K0T, int H1T, int H2T, bool FUSED = false>
-__global__ void __launch_bounds__(256, 1) mlp_tc_kernel(TcArgs a) {
+__global__ void __launch_bounds__(32 * TC_WARPS, 1) mlp_tc_kernel(TcArgs a) {
     if (FUSED && a.flag != nullptr && (*a.flag & NNMD_FLAG_OVERFLOW)) return;  // incomplete neighbour list: G / dG are not valid
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *f_fwd0 = reinterpret_cast<float4 *>(smem_raw);   // x  (K0) -> z1 (H1):  k = input feature, n = neuron of layer 0
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(256, 1) mlp_tc_kernel(TcArgs a) {
     const int lane = lane_id(), warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int64_t n_groups = (a.n_rows + 15) / 16;
     bool bad = false;
-    for (int64_t grp = int64_t(blockIdx.x) * 8 + warp; grp < n_groups; grp += int64_t(gridDim.x) * 8) {
+    for (int64_t grp = int64_t(blockIdx.x) * TC_WARPS + warp; grp < n_groups; grp += int64_t(gridDim.x) * TC_WARPS) {
         const int64_t r0 = grp * 16 + g, r1 = r0 + 8;
         const bool v0 = r0 < a.n_rows, v1 = r1 < a.n_rows;
         if (FUSED) {
@@ -265,12 +271,12 @@ static int tc_launch(const TcArgs &a, cudaStream_t st) {
     auto kern = mlp_tc_kernel<K0T, H1T, H2T, FUSED>;
     NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int occ = 1;
-    NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+    NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * TC_WARPS, smem));
     if (occ < 1) occ = 1;
     const int64_t n_groups = (a.n_rows + 15) / 16;
-    const int64_t blocks = std::min<int64_t>((n_groups + 7) / 8, int64_t(sm_count()) * occ);
+    const int64_t blocks = std::min<int64_t>((n_groups + TC_WARPS - 1) / TC_WARPS, int64_t(sm_count()) * occ);
     ProfScope prof(PROF_MLP, st);
-    kern<<<unsigned(blocks), 256, smem, st>>>(a);
+    kern<<<unsigned(blocks), 32 * TC_WARPS, smem, st>>>(a);
     NNMD_LAUNCH_CHECK("mlp_tc_kernel");
     return NNMD_OK;
 }

@@ -543,6 +543,9 @@ class BPNN(torch.nn.Module):
         name = self.criterion.__class__.__name__
         for epoch in range(epochs):
             e_loss, f_loss, loss = self._train_loop(epoch, train_loader)
+            fg = getattr(self, "_flat_grads", None)
+            if fg is not None and fg.window is not None:
+                fg.window.check()  # a peer that never arrived at an all-reduce (the .item() below synchronises anyway)
             self.net_log.info(f"Epoch {epoch + 1}: training:   "
                               + line.format(e_loss=e_loss.item(), f_loss=f_loss.item(), loss=name, total=loss.item()))
             e_loss, f_loss, loss = self._validate(epoch, val_loader)
