@@ -399,6 +399,8 @@ def run_ours(args):
     e2e = {"value": n_atoms / dt, "unit": "atoms/s", "h2d_bytes_per_step": int(host.numel() * host.element_size()) * world,
            "d2h_bytes_per_step": int(F.numel() * F.element_size() + E.numel() * E.element_size()) * world, "api": api, "ms_per_step": dt * 1e3}
 
+    if getattr(shard, "_window", None) is not None:
+        shard._window.check()  # raises if a peer ever failed to arrive at a halo exchange
     # ---- checksum of the structure the LAST timed step computed: must agree across N = 1, 2, 4, 8 to fp32 round-off
     chk = torch.stack([res.forces.double().abs().sum(), *res.forces.double().sum(dim=(0, 1))])
     if world > 1:

@@ -107,6 +107,9 @@ def train_bench(config: str, dev, rank: int, world: int, frames: int = 20000, ba
     if world > 1:
         td.all_reduce(ms, op=td.ReduceOp.MAX)
     step_ms = float(ms.item()) / steps
+    fg = getattr(net, "_flat_grads", None)
+    if fg is not None and fg.window is not None:
+        fg.window.check()  # raises if a peer ever failed to arrive at an all-reduce (the timing would be of garbage)
     global_batch = per_rank * world
     return {"config": LABELS[config], "n_gpus": world, "scaling": scaling, "global_batch_frames": global_batch,
             "ms_per_step": step_ms, "frames_per_s": global_batch / (step_ms * 1e-3),
