@@ -55,6 +55,19 @@ def _worker(rank, world, port, out_dir):
     bp = BPNN(use_cuda=False)
     n_local = -(-int((127 + rank) * 0.8) // 101)
     assert bp._epoch_steps(n_local) == 2
+
+    class _Loader:  # the answer is remembered per loader object: the second epoch issues no collective (and no host sync)
+        pass
+    ld = _Loader()
+    assert bp._epoch_steps(n_local, ld) == 2 and bp._steps_cache[ld] == (n_local, 2)
+    calls = []
+    orig = td.all_reduce
+    td.all_reduce = lambda *a, **k: calls.append(1) or orig(*a, **k)
+    try:
+        assert bp._epoch_steps(n_local, ld) == 2 and not calls
+        assert bp._epoch_steps(n_local + 1, ld) == 3 and len(calls) == 1   # a changed length asks again (on every rank)
+    finally:
+        td.all_reduce = orig
     frames = list(dist.shard_frames(11))
     # dataset build on pre-sharded frames: the target scaling uses the GLOBAL extrema (one MIN and one MAX all-reduce)
     from nnmd_b200.nn.dataset import cache_name, scale_targets
