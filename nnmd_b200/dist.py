@@ -75,7 +75,8 @@ class PeerWindow:
             if rank == 0 and not cls._warned:
                 cls._warned = True
                 why = next((v for v in verdicts if v), None) or next((g[1] for g in gathered if g[1]), "ranks on different hosts")
-                print(f"nnmd_b200: peer windows unavailable ({why}); using NCCL for the exchanges", flush=True)
+                import sys
+                print(f"nnmd_b200: peer windows unavailable ({why}); using NCCL for the exchanges", file=sys.stderr, flush=True)
             return None
         return cls(handle, lib, int(lib.nnmd_peer_capacity(handle)))
 

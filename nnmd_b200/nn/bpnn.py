@@ -358,7 +358,9 @@ class BPNN(torch.nn.Module):
                 plan.graph_key = key
                 # a capture does not execute: fall through to the replay below
             except Exception as exc:  # capture not possible here: stay eager, loudly
-                print(f"nnmd_b200: CUDA-graph capture of the training step failed ({exc!r}); continuing without graphs")
+                import sys
+                print(f"nnmd_b200: CUDA-graph capture of the training step failed ({exc!r}); continuing without graphs",
+                      file=sys.stderr, flush=True)
                 self._graphs_ok = False
         if plan.graphs is not None and len(plan.graphs) == 1:
             plan.graphs[0].replay()
