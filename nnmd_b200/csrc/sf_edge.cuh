@@ -578,7 +578,10 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         const size_t smem = size_t(wpb) * 16 * a.cap;
         auto kern = edge_gather_kernel<MODE>;
         NNMD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * 16);
+#ifndef NNMD_GATHER_BPS
+#define NNMD_GATHER_BPS 16
+#endif
+        int64_t blocks = std::min<int64_t>((a.n_rows + wpb - 1) / wpb, int64_t(sm_count()) * NNMD_GATHER_BPS);
         ProfScope prof(PROF_GATHER, st);
         kern<<<unsigned(blocks), wpb * 32, smem, st>>>(a);
         NNMD_LAUNCH_CHECK("edge_gather_kernel");
