@@ -493,8 +493,15 @@ __global__ void __launch_bounds__(256) nlist_rows_kernel(const T *__restrict__ p
 // One CTA per occupied cell: the candidates of its 9 z-runs (27 cells) are staged ONCE in shared memory and shared by
 // every atom of the cell, instead of every atom streaming ~600 candidate positions through L2 on its own
 // (that form, nlist_rows_kernel above, is L2-bound and remains the path for cells whose candidate set does not fit).
-constexpr int CELL_MCAND = 1536;
-constexpr int CELL_WARPS = 4;
+#ifndef NNMD_CELL_MCAND
+#define NNMD_CELL_MCAND 768   // staged candidates per cell (20 B each): 1536 -> 768 lets twice the blocks share an SM (K1 2.22 -> 1.89 ms per 1M atoms);
+                               // cells with more candidates take the unstaged loop
+#endif
+#ifndef NNMD_CELL_WARPS
+#define NNMD_CELL_WARPS 4
+#endif
+constexpr int CELL_MCAND = NNMD_CELL_MCAND;
+constexpr int CELL_WARPS = NNMD_CELL_WARPS;
 
 template <typename T> __device__ __forceinline__ void load_pos_smem(const T *p, int i, T &x, T &y, T &z);
 template <> __device__ __forceinline__ void load_pos_smem<float>(const float *p, int i, float &x, float &y, float &z) {
@@ -642,7 +649,10 @@ static int launch_cell_kernel(const T *spos, int64_t n_frames, int64_t n_atoms, 
     int occ = 1;
     NNMD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CELL_WARPS * 32, smem));
     if (occ < 1) occ = 1;
-    int64_t blocks = std::min<int64_t>(n_frames * std::max<int64_t>(cap, 1), int64_t(sm_count()) * occ * 4);
+#ifndef NNMD_CELL_WAVES
+#define NNMD_CELL_WAVES 32  // grid = resident blocks x this (cells cost differently: 2: 2.04, 4: 1.89, 8: 1.83, 32: 1.79 ms per 1M atoms)
+#endif
+    int64_t blocks = std::min<int64_t>(n_frames * std::max<int64_t>(cap, 1), int64_t(sm_count()) * occ * NNMD_CELL_WAVES);
     if (blocks < 1) blocks = 1;
     kern<<<unsigned(blocks), CELL_WARPS * 32, smem, st>>>(spos, n_frames, n_atoms, n_centres, cap, h, cell_start, order, rc, counts,
                                                          ecounts, offsets, max_row, idx, stats, idx_cap, go);
