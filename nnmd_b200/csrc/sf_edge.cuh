@@ -573,7 +573,10 @@ static int launch_edge(const AngGroup &g, EdgeArgs a, cudaStream_t st) {
         NNMD_LAUNCH_CHECK("angular_edge_kernel");
     }
     {
-        int wpb = 8;
+#ifndef NNMD_GATHER_WPB
+#define NNMD_GATHER_WPB 8
+#endif
+        int wpb = NNMD_GATHER_WPB;
         while (wpb > 1 && size_t(wpb) * 16 * a.cap > 160 * 1024) wpb >>= 1;
         const size_t smem = size_t(wpb) * 16 * a.cap;
         auto kern = edge_gather_kernel<MODE>;
