@@ -321,8 +321,11 @@ def run_ours(args):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = _lib.launch_count()
-    barrier()
     with ClockSampler(local_rank) as clocks:
+        # the barrier comes AFTER the sampler has started: NVML initialisation takes a different time on every rank (tens of
+        # ms), and at N>1 a rank that enters the loop early spends that skew waiting in the first halo exchange -- inside its
+        # first timed step (seen once at 8 GPUs: 8.48 ms per step over kernel sums of 7.35 ms)
+        barrier()
         for k in range(args.steps):
             flush_buf.zero_()
             starts[k].record()
